@@ -1,0 +1,175 @@
+// Train-mode BatchNorm (+residual)(+ReLU) on per-point [rows, C] tensors, forward and backward, and the
+// TF-form Adam update.  Replaces slim.batch_norm / tf.nn.relu after the 1x1 convs of
+// /root/reference/dgcnn/ops.py:53,68,131,134 and tf.train.AdamOptimizer (trainval.py:17,80).
+// slim.batch_norm defaults: is_training=True (always -- SURVEY.md section 0), center=True, scale=False,
+// epsilon=1e-3, biased batch variance over every non-channel axis.
+#include "common.cuh"
+
+namespace dgcnn {
+
+constexpr int BN_THREADS = 256;
+constexpr int BN_BLOCKS_PER_SM = 8;
+
+static inline int bn_max_blocks() { return num_sms() * BN_BLOCKS_PER_SM; }
+static inline int bn_blocks(int64_t rows) {
+  int64_t need = (rows + 63) / 64;
+  int nb = bn_max_blocks();
+  return (int)(need < nb ? (need < 1 ? 1 : need) : nb);
+}
+
+// MODE 0: partial (sum z, sum z^2).   MODE 1: partial (sum g_pre, sum g_pre*zhat)
+template <int MODE>
+__global__ void __launch_bounds__(BN_THREADS)
+    bn_colsum_kernel(const float* __restrict__ z, const float* __restrict__ out, const float* __restrict__ gout,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, int relu, int64_t rows, int C,
+                     float* __restrict__ partial) {
+  __shared__ float red[2][4][64];
+  const int cl = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int c = blockIdx.y * 64 + cl;
+  const bool ok = c < C;
+  const int64_t rpb = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t rbeg = (int64_t)blockIdx.x * rpb;
+  const int64_t rend = rbeg + rpb < rows ? rbeg + rpb : rows;
+  float a = 0.f, q = 0.f;
+  float mu = 0.f, rs = 0.f;
+  if (MODE == 1 && ok) {
+    mu = mean[c];
+    rs = rstd[c];
+  }
+  if (ok) {
+    for (int64_t r = rbeg + rg; r < rend; r += 4) {
+      const int64_t o = r * C + c;
+      if (MODE == 0) {
+        const float v = z[o];
+        a += v;
+        q = fmaf(v, v, q);
+      } else {
+        float gp = gout[o];
+        if (relu && !(out[o] > 0.f)) gp = 0.f;
+        a += gp;
+        q = fmaf(gp, (z[o] - mu) * rs, q);
+      }
+    }
+  }
+  red[0][rg][cl] = a;
+  red[1][rg][cl] = q;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6;
+    const float t = red[which][0][cl] + red[which][1][cl] + red[which][2][cl] + red[which][3][cl];
+    if (ok) partial[((int64_t)blockIdx.x * 2 + which) * C + c] = t;
+  }
+}
+
+__global__ void bn_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mean,
+                                  const float* __restrict__ rstd, const float* __restrict__ beta,
+                                  const float* __restrict__ res, int relu, int64_t total, int C,
+                                  float* __restrict__ out) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    float y = fmaf(z[e] - mean[c], rstd[c], beta[c]);
+    if (res) y += res[e];
+    if (relu) y = fmaxf(y, 0.f);
+    out[e] = y;
+  }
+}
+
+__global__ void bn_act_bwd_kernel(const float* __restrict__ z, const float* __restrict__ out,
+                                  const float* __restrict__ gout, const float* __restrict__ mean,
+                                  const float* __restrict__ rstd, const float* __restrict__ s1,
+                                  const float* __restrict__ s2, int relu, int64_t total, int C, float inv_rows,
+                                  float* __restrict__ gz, float* __restrict__ gpre) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    float gp = gout[e];
+    if (relu && !(out[e] > 0.f)) gp = 0.f;
+    const float rs = rstd[c];
+    const float zh = (z[e] - mean[c]) * rs;
+    gz[e] = rs * (gp - s1[c] * inv_rows - zh * (s2[c] * inv_rows));
+    if (gpre) gpre[e] = gp;
+  }
+}
+
+__global__ void adam_tf_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                               float* __restrict__ v, int64_t n, float lr_t, float b1, float b2, float eps,
+                               float gscale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+static inline int ew_blocks(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace dgcnn
+
+using namespace dgcnn;
+
+extern "C" size_t dgcnn_bn_workspace_bytes(int C) {
+  if (C <= 0) return 0;
+  return ((size_t)bn_max_blocks() * 2 * C + (size_t)C) * sizeof(float);
+}
+
+extern "C" int dgcnn_bn_act_fwd(const float* z, int64_t rows, int C, const float* beta, const float* residual,
+                                int relu, float* out, float* mean, float* rstd, void* ws, size_t ws_bytes,
+                                dgcnn_stream_t stream) {
+  DG_REQUIRE(z && beta && out && mean && rstd && ws, DGCNN_ERR_INVALID, "bn_act_fwd: null pointer");
+  DG_REQUIRE(rows > 0 && C > 0, DGCNN_ERR_INVALID, "bn_act_fwd: bad shape rows=%lld C=%d", (long long)rows, C);
+  DG_REQUIRE(ws_bytes >= dgcnn_bn_workspace_bytes(C), DGCNN_ERR_WORKSPACE, "bn_act_fwd: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = bn_blocks(rows);
+  dim3 grid(nb, cdiv(C, 64));
+  bn_colsum_kernel<0><<<grid, BN_THREADS, 0, st>>>(z, nullptr, nullptr, nullptr, nullptr, 0, rows, C, (float*)ws);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("bn_colsum_kernel<0>");
+  int rc = launch_finalize_stats((const float*)ws, nb, C, (double)rows, 1e-3f, mean, rstd, st);
+  if (rc) return rc;
+  const int64_t total = rows * C;
+  bn_act_fwd_kernel<<<ew_blocks(total), 256, 0, st>>>(z, mean, rstd, beta, residual, relu, total, C, out);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("bn_act_fwd_kernel");
+  return DGCNN_OK;
+}
+
+extern "C" int dgcnn_bn_act_bwd(const float* z, const float* out, const float* g_out, int64_t rows, int C,
+                                const float* mean, const float* rstd, int relu, float* g_z, float* g_beta,
+                                float* g_pre, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
+  DG_REQUIRE(z && g_out && mean && rstd && g_z && g_beta && ws, DGCNN_ERR_INVALID, "bn_act_bwd: null pointer");
+  DG_REQUIRE(!relu || out, DGCNN_ERR_INVALID, "bn_act_bwd: relu backward needs the forward output");
+  DG_REQUIRE(rows > 0 && C > 0, DGCNN_ERR_INVALID, "bn_act_bwd: bad shape rows=%lld C=%d", (long long)rows, C);
+  DG_REQUIRE(ws_bytes >= dgcnn_bn_workspace_bytes(C), DGCNN_ERR_WORKSPACE, "bn_act_bwd: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = bn_blocks(rows);
+  float* partial = (float*)ws;
+  float* s2 = partial + (size_t)bn_max_blocks() * 2 * C;
+  dim3 grid(nb, cdiv(C, 64));
+  bn_colsum_kernel<1><<<grid, BN_THREADS, 0, st>>>(z, out, g_out, mean, rstd, relu, rows, C, partial);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("bn_colsum_kernel<1>");
+  int rc = launch_finalize_sums(partial, nb, C, g_beta, s2, st);
+  if (rc) return rc;
+  const int64_t total = rows * C;
+  bn_act_bwd_kernel<<<ew_blocks(total), 256, 0, st>>>(z, out, g_out, mean, rstd, g_beta, s2, relu, total, C,
+                                                      1.0f / (float)rows, g_z, g_pre);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("bn_act_bwd_kernel");
+  return DGCNN_OK;
+}
+
+extern "C" int dgcnn_adam_tf_step(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1,
+                                  float b2, float eps, float grad_scale, dgcnn_stream_t stream) {
+  DG_REQUIRE(p && g && m && v, DGCNN_ERR_INVALID, "adam_tf_step: null pointer");
+  DG_REQUIRE(n > 0, DGCNN_ERR_INVALID, "adam_tf_step: n=%lld", (long long)n);
+  adam_tf_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_t, b1, b2, eps, grad_scale);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("adam_tf_kernel");
+  return DGCNN_OK;
+}

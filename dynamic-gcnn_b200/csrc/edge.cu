@@ -1,0 +1,404 @@
+// EdgeConv gather path.
+//   edge_feature(+bwd): /root/reference/dgcnn/ops.py:21-40 materialised (API parity for edges()).
+//   edgeconv_*        : ops.py:45-57 fused -- gather -> conv0 -> BN(train) -> ReLU -> max_k / mean_k with
+//                       z_ij = u_i + v_{idx(i,j)} (uv = x.[Wa-Wb | Wb], formed by dgcnn_gemm), so neither the
+//                       [B,N,k,2C] edge tensor nor the [B,N,k,F] activation ever exists in HBM.
+// Work split of the gather passes: one warp per point, lanes over channels (lane, lane+32 of a 64-channel
+// chunk; chunk = blockIdx.y), neighbours unrolled for memory-level parallelism.  v rows are 256 B and the
+// whole uv table (25 MB at B=24,N=2048,F=64) is L2-resident, so these passes run at L2 gather rate.
+#include "common.cuh"
+
+namespace dgcnn {
+
+constexpr int EC_THREADS = 256;          // 8 warps
+constexpr int EC_WARPS = EC_THREADS / 32;
+constexpr int STAT_BLOCKS_PER_SM = 8;
+
+// ------------------------------------------------------------------------------------------ edges()
+__global__ void edge_feature_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx,
+                                    float* __restrict__ out, int N, int C, int k, int64_t total) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int C2 = 2 * C;
+  const int ch = (int)(e % C2);
+  const int64_t edge = e / C2;      // (b*N + i)*k + j
+  const int64_t pt = edge / k;      // b*N + i
+  const int64_t b = pt / N;
+  const float* xi = x + pt * C;
+  if (ch < C) {
+    out[e] = xi[ch];                                          // ops.py:35-37 central
+  } else {
+    const int64_t nb = b * N + idx[edge];                     // ops.py:30-34 flat gather
+    out[e] = __fsub_rn(x[nb * C + (ch - C)], xi[ch - C]);     // ops.py:39 neighbours - central
+  }
+}
+
+__global__ void edge_feature_bwd_kernel(const float* __restrict__ g, const int32_t* __restrict__ idx,
+                                        float* __restrict__ gx, int N, int C, int k, int64_t total) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over P*k*C
+  if (e >= total) return;
+  const int ch = (int)(e % C);
+  const int64_t edge = e / C;
+  const int64_t pt = edge / k;
+  const int64_t b = pt / N;
+  const float gc = g[edge * 2 * C + ch];
+  const float gn = g[edge * 2 * C + C + ch];
+  atomicAdd(gx + pt * C + ch, gc - gn);
+  atomicAdd(gx + (b * N + idx[edge]) * C + ch, gn);
+}
+
+// ------------------------------------------------------------------------------- fused EdgeConv passes
+struct EcArgs {
+  const float* uv;      // [P, 2F]   u | v
+  const int32_t* idx;   // [P, k]    neighbour index inside the cloud
+  int P, N, F, k;
+};
+
+// Load this point's k neighbour rows (global point index) into lanes; broadcast later by shuffle.
+__device__ __forceinline__ void load_nbrs(const EcArgs& a, int p, int lane, int (&rows)[2]) {
+  const int base = (p / a.N) * a.N;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int j = s * 32 + lane;
+    rows[s] = (j < a.k) ? base + a.idx[(int64_t)p * a.k + j] : 0;
+  }
+}
+// offset (in floats) of neighbour j's v row inside uv; j is warp-uniform
+__device__ __forceinline__ int64_t nbr_off(const EcArgs& a, const int (&rows)[2], int j) {
+  const int r = (j < 32) ? __shfl_sync(FULL, rows[0], j) : __shfl_sync(FULL, rows[1], j - 32);
+  return (int64_t)r * (2 * a.F) + a.F;
+}
+
+// pass 1 forward: zmax, tie count, per-block partial sum / sum of squares
+__global__ void __launch_bounds__(EC_THREADS)
+    ec_fwd_stats_kernel(EcArgs a, float* __restrict__ zmax, float* __restrict__ cnt, float* __restrict__ partial) {
+  __shared__ float red[2][EC_WARPS][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int f0 = blockIdx.y * 64 + lane, f1 = f0 + 32;
+  const bool ok0 = f0 < a.F, ok1 = f1 < a.F;
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  for (int p = blockIdx.x * EC_WARPS + warp; p < a.P; p += gridDim.x * EC_WARPS) {
+    int rows[2];
+    load_nbrs(a, p, lane, rows);
+    const float* up = a.uv + (int64_t)p * 2 * a.F;
+    const float u0 = ok0 ? up[f0] : 0.f, u1 = ok1 ? up[f1] : 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, c0 = 0.f, c1 = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < a.k; ++j) {
+      const float* vp = a.uv + nbr_off(a, rows, j);
+      const float z0 = u0 + (ok0 ? __ldg(vp + f0) : 0.f);
+      const float z1 = u1 + (ok1 ? __ldg(vp + f1) : 0.f);
+      s0 += z0; q0 = fmaf(z0, z0, q0);
+      s1 += z1; q1 = fmaf(z1, z1, q1);
+      if (z0 > m0) { m0 = z0; c0 = 1.f; } else if (z0 == m0) c0 += 1.f;
+      if (z1 > m1) { m1 = z1; c1 = 1.f; } else if (z1 == m1) c1 += 1.f;
+    }
+    if (ok0) { zmax[(int64_t)p * a.F + f0] = m0; cnt[(int64_t)p * a.F + f0] = c0; }
+    if (ok1) { zmax[(int64_t)p * a.F + f1] = m1; cnt[(int64_t)p * a.F + f1] = c1; }
+  }
+  red[0][warp][lane] = s0; red[0][warp][lane + 32] = s1;
+  red[1][warp][lane] = q0; red[1][warp][lane + 32] = q1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < EC_WARPS; ++w) t += red[which][w][c];
+    const int f = blockIdx.y * 64 + c;
+    if (f < a.F) partial[((int64_t)blockIdx.x * 2 + which) * a.F + f] = t;
+  }
+}
+
+// partial [nblk][2][C] -> mean, rstd (double, fixed order => deterministic)
+__global__ void finalize_stats_kernel(const float* __restrict__ partial, int nblk, int C, double count, float eps,
+                                      float* __restrict__ mean, float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += (double)partial[((int64_t)b * 2 + 0) * C + c];
+    q += (double)partial[((int64_t)b * 2 + 1) * C + c];
+  }
+  const double m = s / count;
+  double var = q / count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// partial [nblk][2][C] -> plain sums s1, s2
+__global__ void finalize_sums_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ s1,
+                                     float* __restrict__ s2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b2 = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    a += (double)partial[((int64_t)b * 2 + 0) * C + c];
+    b2 += (double)partial[((int64_t)b * 2 + 1) * C + c];
+  }
+  s1[c] = (float)a;
+  s2[c] = (float)b2;
+}
+
+// pass 2 forward: out_max, out_mean
+__global__ void __launch_bounds__(EC_THREADS)
+    ec_fwd_apply_kernel(EcArgs a, const float* __restrict__ zmax, const float* __restrict__ mean,
+                        const float* __restrict__ rstd, const float* __restrict__ beta, float* __restrict__ omax,
+                        float* __restrict__ omean) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int f0 = blockIdx.y * 64 + lane, f1 = f0 + 32;
+  const bool ok0 = f0 < a.F, ok1 = f1 < a.F;
+  const float mu0 = ok0 ? mean[f0] : 0.f, mu1 = ok1 ? mean[f1] : 0.f;
+  const float r0 = ok0 ? rstd[f0] : 0.f, r1 = ok1 ? rstd[f1] : 0.f;
+  const float b0 = ok0 ? beta[f0] : 0.f, b1 = ok1 ? beta[f1] : 0.f;
+  const float invk = 1.0f / (float)a.k;
+  for (int p = blockIdx.x * EC_WARPS + warp; p < a.P; p += gridDim.x * EC_WARPS) {
+    int rows[2];
+    load_nbrs(a, p, lane, rows);
+    const float* up = a.uv + (int64_t)p * 2 * a.F;
+    const float u0 = ok0 ? up[f0] : 0.f, u1 = ok1 ? up[f1] : 0.f;
+    float y0 = 0.f, y1 = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < a.k; ++j) {
+      const float* vp = a.uv + nbr_off(a, rows, j);
+      const float z0 = u0 + (ok0 ? __ldg(vp + f0) : 0.f);
+      const float z1 = u1 + (ok1 ? __ldg(vp + f1) : 0.f);
+      y0 += fmaxf(fmaf(z0 - mu0, r0, b0), 0.f);
+      y1 += fmaxf(fmaf(z1 - mu1, r1, b1), 0.f);
+    }
+    const int64_t o = (int64_t)p * a.F;
+    if (ok0) {
+      omean[o + f0] = y0 * invk;
+      omax[o + f0] = fmaxf(fmaf(zmax[o + f0] - mu0, r0, b0), 0.f);  // BN(+)ReLU are monotone: max commutes
+    }
+    if (ok1) {
+      omean[o + f1] = y1 * invk;
+      omax[o + f1] = fmaxf(fmaf(zmax[o + f1] - mu1, r1, b1), 0.f);
+    }
+  }
+}
+
+// backward pass 1: s1 = sum g_pre, s2 = sum g_pre * zhat (per-block partials)
+// g_y_ij  = g_mean_i/k + [z_ij == zmax_i] g_max_i / cnt_i      (tf reduce_mean / reduce_max grads; ties share)
+// g_pre_ij = g_y_ij * [pre_ij > 0]                             (ReluGrad)
+template <bool APPLY>
+__global__ void __launch_bounds__(EC_THREADS)
+    ec_bwd_kernel(EcArgs a, const float* __restrict__ zmax, const float* __restrict__ cnt,
+                  const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ beta,
+                  const float* __restrict__ gmax, const float* __restrict__ gmean, const float* __restrict__ s1,
+                  const float* __restrict__ s2, float* __restrict__ partial, float* __restrict__ guv) {
+  __shared__ float red[2][EC_WARPS][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int f0 = blockIdx.y * 64 + lane, f1 = f0 + 32;
+  const bool ok0 = f0 < a.F, ok1 = f1 < a.F;
+  const float mu0 = ok0 ? mean[f0] : 0.f, mu1 = ok1 ? mean[f1] : 0.f;
+  const float r0 = ok0 ? rstd[f0] : 0.f, r1 = ok1 ? rstd[f1] : 0.f;
+  const float b0 = ok0 ? beta[f0] : 0.f, b1 = ok1 ? beta[f1] : 0.f;
+  const float invk = 1.0f / (float)a.k;
+  const float invE = 1.0f / ((float)a.P * (float)a.k);
+  float m10 = 0.f, m11 = 0.f, m20 = 0.f, m21 = 0.f;
+  if (APPLY) {
+    m10 = ok0 ? s1[f0] * invE : 0.f; m11 = ok1 ? s1[f1] * invE : 0.f;
+    m20 = ok0 ? s2[f0] * invE : 0.f; m21 = ok1 ? s2[f1] * invE : 0.f;
+  }
+  float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+  for (int p = blockIdx.x * EC_WARPS + warp; p < a.P; p += gridDim.x * EC_WARPS) {
+    int rows[2];
+    load_nbrs(a, p, lane, rows);
+    const float* up = a.uv + (int64_t)p * 2 * a.F;
+    const int64_t o = (int64_t)p * a.F;
+    const float u0 = ok0 ? up[f0] : 0.f, u1 = ok1 ? up[f1] : 0.f;
+    const float zm0 = ok0 ? zmax[o + f0] : 0.f, zm1 = ok1 ? zmax[o + f1] : 0.f;
+    const float gm0 = ok0 ? gmean[o + f0] * invk : 0.f, gm1 = ok1 ? gmean[o + f1] * invk : 0.f;
+    const float gx0 = ok0 ? gmax[o + f0] / cnt[o + f0] : 0.f, gx1 = ok1 ? gmax[o + f1] / cnt[o + f1] : 0.f;
+    float gu0 = 0.f, gu1 = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < a.k; ++j) {
+      const int64_t off = nbr_off(a, rows, j);
+      const float* vp = a.uv + off;
+      const float z0 = u0 + (ok0 ? __ldg(vp + f0) : 0.f);
+      const float z1 = u1 + (ok1 ? __ldg(vp + f1) : 0.f);
+      const float zh0 = (z0 - mu0) * r0, zh1 = (z1 - mu1) * r1;
+      const bool act0 = fmaf(z0 - mu0, r0, b0) > 0.f, act1 = fmaf(z1 - mu1, r1, b1) > 0.f;
+      const float gp0 = act0 ? gm0 + (z0 == zm0 ? gx0 : 0.f) : 0.f;
+      const float gp1 = act1 ? gm1 + (z1 == zm1 ? gx1 : 0.f) : 0.f;
+      if (!APPLY) {
+        a0 += gp0; q0 = fmaf(gp0, zh0, q0);
+        a1 += gp1; q1 = fmaf(gp1, zh1, q1);
+      } else {
+        const float gz0 = r0 * (gp0 - m10 - zh0 * m20);
+        const float gz1 = r1 * (gp1 - m11 - zh1 * m21);
+        gu0 += gz0; gu1 += gz1;
+        if (ok0) atomicAdd(guv + off + f0, gz0);   // scatter-add into the v half (tf.gather grad)
+        if (ok1) atomicAdd(guv + off + f1, gz1);
+      }
+    }
+    if (APPLY) {
+      float* gup = guv + (int64_t)p * 2 * a.F;
+      if (ok0) gup[f0] = gu0;
+      if (ok1) gup[f1] = gu1;
+    }
+  }
+  if (!APPLY) {
+    red[0][warp][lane] = a0; red[0][warp][lane + 32] = a1;
+    red[1][warp][lane] = q0; red[1][warp][lane + 32] = q1;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < EC_WARPS; ++w) t += red[which][w][c];
+      const int f = blockIdx.y * 64 + c;
+      if (f < a.F) partial[((int64_t)blockIdx.x * 2 + which) * a.F + f] = t;
+    }
+  }
+}
+
+// zero only the v half of g_uv [P,2F] (u half is fully overwritten by bwd_apply)
+__global__ void zero_vhalf_kernel(float* __restrict__ guv, int64_t P, int F) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P * F) return;
+  guv[(e / F) * 2 * F + F + (e % F)] = 0.f;
+}
+
+int launch_finalize_stats(const float* partial, int nblk, int C, double count, float eps, float* mean, float* rstd,
+                          cudaStream_t st) {
+  finalize_stats_kernel<<<cdiv(C, 128), 128, 0, st>>>(partial, nblk, C, count, eps, mean, rstd);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("finalize_stats_kernel");
+  return DGCNN_OK;
+}
+int launch_finalize_sums(const float* partial, int nblk, int C, float* s1, float* s2, cudaStream_t st) {
+  finalize_sums_kernel<<<cdiv(C, 128), 128, 0, st>>>(partial, nblk, C, s1, s2);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("finalize_sums_kernel");
+  return DGCNN_OK;
+}
+
+static inline int stat_blocks(int P) {
+  int nb = num_sms() * STAT_BLOCKS_PER_SM;
+  const int need = cdiv(P, EC_WARPS);
+  return nb < need ? nb : need;
+}
+static inline int max_stat_blocks() { return num_sms() * STAT_BLOCKS_PER_SM; }
+
+static int ec_check(const float* uv, const int32_t* idx, int B, int N, int F, int k) {
+  DG_REQUIRE(uv && idx, DGCNN_ERR_INVALID, "edgeconv: null pointer");
+  DG_REQUIRE(B > 0 && N > 0 && F > 0, DGCNN_ERR_INVALID, "edgeconv: bad shape B=%d N=%d F=%d", B, N, F);
+  DG_REQUIRE(k >= 1 && k <= N, DGCNN_ERR_INVALID, "edgeconv: need 1 <= k <= N (k=%d N=%d)", k, N);
+  DG_REQUIRE(k <= DGCNN_KNN_MAX_K, DGCNN_ERR_UNSUPPORTED, "edgeconv: k=%d > %d", k, DGCNN_KNN_MAX_K);
+  DG_REQUIRE((int64_t)B * N < (1ll << 31) / 2, DGCNN_ERR_UNSUPPORTED, "edgeconv: B*N too large");
+  return DGCNN_OK;
+}
+
+}  // namespace dgcnn
+
+using namespace dgcnn;
+
+extern "C" int dgcnn_edge_feature(const float* x, const int32_t* idx, float* out, int B, int N, int C, int k,
+                                  dgcnn_stream_t stream) {
+  DG_REQUIRE(x && idx && out, DGCNN_ERR_INVALID, "edge_feature: null pointer");
+  DG_REQUIRE(B > 0 && N > 0 && C > 0 && k > 0, DGCNN_ERR_INVALID, "edge_feature: bad shape");
+  const int64_t total = (int64_t)B * N * k * 2 * C;
+  const int64_t blocks = (total + 255) / 256;
+  DG_REQUIRE(blocks < (1ll << 31), DGCNN_ERR_UNSUPPORTED, "edge_feature: too many elements");
+  edge_feature_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, idx, out, N, C, k, total);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("edge_feature_kernel");
+  return DGCNN_OK;
+}
+
+extern "C" int dgcnn_edge_feature_bwd(const float* g_out, const int32_t* idx, float* gx, int B, int N, int C, int k,
+                                      dgcnn_stream_t stream) {
+  DG_REQUIRE(g_out && idx && gx, DGCNN_ERR_INVALID, "edge_feature_bwd: null pointer");
+  DG_REQUIRE(B > 0 && N > 0 && C > 0 && k > 0, DGCNN_ERR_INVALID, "edge_feature_bwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(gx, 0, (size_t)B * N * C * sizeof(float), st) != cudaSuccess)
+    return set_err(DGCNN_ERR_CUDA, "edge_feature_bwd: memset failed");
+  const int64_t total = (int64_t)B * N * k * C;
+  const int64_t blocks = (total + 255) / 256;
+  DG_REQUIRE(blocks < (1ll << 31), DGCNN_ERR_UNSUPPORTED, "edge_feature_bwd: too many elements");
+  edge_feature_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(g_out, idx, gx, N, C, k, total);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("edge_feature_bwd_kernel");
+  return DGCNN_OK;
+}
+
+extern "C" size_t dgcnn_edgeconv_workspace_bytes(int F) {
+  if (F <= 0) return 0;
+  return (size_t)max_stat_blocks() * 2 * F * sizeof(float);
+}
+
+extern "C" int dgcnn_edgeconv_fwd_stats(const float* uv, const int32_t* idx, int B, int N, int F, int k, float* zmax,
+                                        float* cnt, float* mean, float* rstd, void* ws, size_t ws_bytes,
+                                        dgcnn_stream_t stream) {
+  int rc = ec_check(uv, idx, B, N, F, k);
+  if (rc) return rc;
+  DG_REQUIRE(zmax && cnt && mean && rstd && ws, DGCNN_ERR_INVALID, "edgeconv_fwd_stats: null pointer");
+  DG_REQUIRE(ws_bytes >= dgcnn_edgeconv_workspace_bytes(F), DGCNN_ERR_WORKSPACE, "edgeconv_fwd_stats: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  EcArgs a{uv, idx, B * N, N, F, k};
+  const int nb = stat_blocks(a.P);
+  dim3 grid(nb, cdiv(F, 64));
+  ec_fwd_stats_kernel<<<grid, EC_THREADS, 0, st>>>(a, zmax, cnt, (float*)ws);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("ec_fwd_stats_kernel");
+  return launch_finalize_stats((const float*)ws, nb, F, (double)a.P * (double)k, 1e-3f, mean, rstd, st);
+}
+
+extern "C" int dgcnn_edgeconv_fwd_apply(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                        const float* zmax, const float* mean, const float* rstd, const float* beta,
+                                        float* out_max, float* out_mean, dgcnn_stream_t stream) {
+  int rc = ec_check(uv, idx, B, N, F, k);
+  if (rc) return rc;
+  DG_REQUIRE(zmax && mean && rstd && beta && out_max && out_mean, DGCNN_ERR_INVALID,
+             "edgeconv_fwd_apply: null pointer");
+  EcArgs a{uv, idx, B * N, N, F, k};
+  dim3 grid(stat_blocks(a.P), cdiv(F, 64));
+  ec_fwd_apply_kernel<<<grid, EC_THREADS, 0, (cudaStream_t)stream>>>(a, zmax, mean, rstd, beta, out_max, out_mean);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("ec_fwd_apply_kernel");
+  return DGCNN_OK;
+}
+
+extern "C" int dgcnn_edgeconv_bwd_stats(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                        const float* zmax, const float* cnt, const float* mean, const float* rstd,
+                                        const float* beta, const float* g_max, const float* g_mean, float* s1,
+                                        float* s2, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
+  int rc = ec_check(uv, idx, B, N, F, k);
+  if (rc) return rc;
+  DG_REQUIRE(zmax && cnt && mean && rstd && beta && g_max && g_mean && s1 && s2 && ws, DGCNN_ERR_INVALID,
+             "edgeconv_bwd_stats: null pointer");
+  DG_REQUIRE(ws_bytes >= dgcnn_edgeconv_workspace_bytes(F), DGCNN_ERR_WORKSPACE, "edgeconv_bwd_stats: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  EcArgs a{uv, idx, B * N, N, F, k};
+  const int nb = stat_blocks(a.P);
+  dim3 grid(nb, cdiv(F, 64));
+  ec_bwd_kernel<false><<<grid, EC_THREADS, 0, st>>>(a, zmax, cnt, mean, rstd, beta, g_max, g_mean, nullptr, nullptr,
+                                                     (float*)ws, nullptr);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("ec_bwd_kernel<stats>");
+  return launch_finalize_sums((const float*)ws, nb, F, s1, s2, st);
+}
+
+extern "C" int dgcnn_edgeconv_bwd_apply(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                        const float* zmax, const float* cnt, const float* mean, const float* rstd,
+                                        const float* beta, const float* g_max, const float* g_mean, const float* s1,
+                                        const float* s2, float* g_uv, dgcnn_stream_t stream) {
+  int rc = ec_check(uv, idx, B, N, F, k);
+  if (rc) return rc;
+  DG_REQUIRE(zmax && cnt && mean && rstd && beta && g_max && g_mean && s1 && s2 && g_uv, DGCNN_ERR_INVALID,
+             "edgeconv_bwd_apply: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  EcArgs a{uv, idx, B * N, N, F, k};
+  const int64_t PF = (int64_t)a.P * F;
+  zero_vhalf_kernel<<<cdiv(PF, 256), 256, 0, st>>>(g_uv, a.P, F);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("zero_vhalf_kernel");
+  dim3 grid(stat_blocks(a.P), cdiv(F, 64));
+  ec_bwd_kernel<true><<<grid, EC_THREADS, 0, st>>>(a, zmax, cnt, mean, rstd, beta, g_max, g_mean, s1, s2, nullptr,
+                                                    g_uv);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("ec_bwd_kernel<apply>");
+  return DGCNN_OK;
+}

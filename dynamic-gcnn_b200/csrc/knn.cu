@@ -1,0 +1,376 @@
+// k_nn hot path: pairwise squared distance + per-row k-smallest, bit-exact with oracle/knn_oracle.c.
+// Replaces the TF kernels behind /root/reference/dgcnn/ops.py:8-19 (BatchMatMul, Square, Sum, Add, Sub,
+// Neg, TopKV2).  fp32 SIMT formulation: every p_ij is ONE sequential-in-c fmaf chain (the oracle's order),
+// the [B,N,N] matrix lives only in registers, selection is a warp-resident sorted list.
+#include "common.cuh"
+
+namespace dgcnn {
+
+constexpr int TM = 64;    // query rows per CTA (8 per warp)
+constexpr int TN = 128;   // candidate columns per tile (4 per lane)
+constexpr int CK = 16;    // channels per pipeline stage
+constexpr int KNN_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------------
+// prep: x [B,N,C] -> xT [B,C,Npad] (channel-major, zero padded) and s [B,Npad] (squared norms).
+// s follows ops.py:14: square (rounded) then sum, sequential in c, no FMA.
+__global__ void knn_prep_kernel(const float* __restrict__ x, float* __restrict__ xT, float* __restrict__ s,
+                                int N, int Npad, int C) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= Npad) return;
+  float* xTb = xT + (size_t)b * C * Npad;
+  float acc = 0.0f;
+  if (n < N) {
+    const float* r = x + ((size_t)b * N + n) * C;
+    for (int c = 0; c < C; ++c) {
+      float v = r[c];
+      xTb[(size_t)c * Npad + n] = v;
+      acc = __fadd_rn(acc, __fmul_rn(v, v));
+    }
+  } else {
+    for (int c = 0; c < C; ++c) xTb[(size_t)c * Npad + n] = 0.0f;
+  }
+  s[(size_t)b * Npad + n] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-resident ascending list of (distance, index) pairs, 32*KS slots: slot p lives in lane p&31,
+// register p>>5.  Order is lexicographic (d, j): equal distances keep the lower index first, which is
+// tf.nn.top_k's tie rule (ops.py:18).  Empty slots hold (+inf, INT_MAX).
+template <int KS>
+struct WarpList {
+  float d[KS];
+  int j[KS];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      d[s] = __int_as_float(0x7f800000);
+      j[s] = 0x7fffffff;
+    }
+  }
+  // value of the (k-1)-th entry = admission threshold
+  __device__ __forceinline__ void tau(int k, float& td, int& tj) const {
+    const int src = (k - 1) & 31;
+    float a = __shfl_sync(FULL, d[0], src);
+    int bj = __shfl_sync(FULL, j[0], src);
+    if (KS == 2) {
+      float a1 = __shfl_sync(FULL, d[KS - 1], src);
+      int b1 = __shfl_sync(FULL, j[KS - 1], src);
+      if (k > 32) {
+        a = a1;
+        bj = b1;
+      }
+    }
+    td = a;
+    tj = bj;
+  }
+  __device__ __forceinline__ void insert(float nd, int nj, int lane) {
+    bool less0 = (d[0] < nd) || (d[0] == nd && j[0] < nj);
+    int rank = __popc(__ballot_sync(FULL, less0));
+    if (KS == 2) {
+      bool less1 = (d[KS - 1] < nd) || (d[KS - 1] == nd && j[KS - 1] < nj);
+      int rank1 = __popc(__ballot_sync(FULL, less1));
+      float u1d = __shfl_up_sync(FULL, d[KS - 1], 1);
+      int u1j = __shfl_up_sync(FULL, j[KS - 1], 1);
+      if (rank < 32) {
+        float cd = __shfl_sync(FULL, d[0], 31);
+        int cj = __shfl_sync(FULL, j[0], 31);
+        if (lane == 0) {
+          d[KS - 1] = cd;
+          j[KS - 1] = cj;
+        } else {
+          d[KS - 1] = u1d;
+          j[KS - 1] = u1j;
+        }
+      } else {
+        if (lane == rank1) {
+          d[KS - 1] = nd;
+          j[KS - 1] = nj;
+        } else if (lane > rank1) {
+          d[KS - 1] = u1d;
+          j[KS - 1] = u1j;
+        }
+      }
+    }
+    float u0d = __shfl_up_sync(FULL, d[0], 1);
+    int u0j = __shfl_up_sync(FULL, j[0], 1);
+    if (rank < 32) {
+      if (lane == rank) {
+        d[0] = nd;
+        j[0] = nj;
+      } else if (lane > rank) {
+        d[0] = u0d;
+        j[0] = u0j;
+      }
+    }
+  }
+};
+
+// Offer 4 candidates per lane (dv[q], column cj[q]) to the list; td/tj = running threshold.
+template <int KS>
+__device__ __forceinline__ void warp_offer4(WarpList<KS>& L, const float (&dv)[4], const int (&cj)[4], int N,
+                                            int k, float& td, int& tj, int lane) {
+  unsigned pend = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    bool p = (cj[q] < N) && (dv[q] < td || (dv[q] == td && cj[q] < tj));
+    pend |= (p ? 1u : 0u) << q;
+  }
+  unsigned any = __ballot_sync(FULL, pend != 0);
+  while (any) {
+    const int src = __ffs(any) - 1;
+    float cd = (pend & 1u) ? dv[0] : (pend & 2u) ? dv[1] : (pend & 4u) ? dv[2] : dv[3];
+    int cc = (pend & 1u) ? cj[0] : (pend & 2u) ? cj[1] : (pend & 4u) ? cj[2] : cj[3];
+    const float nd = __shfl_sync(FULL, cd, src);
+    const int nj = __shfl_sync(FULL, cc, src);
+    if (lane == src) pend &= pend - 1;
+    if (nd < td || (nd == td && nj < tj)) {  // warp-uniform
+      L.insert(nd, nj, lane);
+      L.tau(k, td, tj);
+    }
+    any = __ballot_sync(FULL, pend != 0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiled distance kernel.  CTA = 64 query rows of one cloud x all candidate columns, streamed in
+// 128-column tiles and 16-channel stages through a 2-deep cp.async ring.  Thread micro-tile:
+// 8 rows (the warp's rows, smem-broadcast) x 4 columns (lane*4..+3).  The same warp that computes a
+// row also selects for it, so selection needs no shared memory and no CTA barrier.
+template <int KS, bool WRITE_D>
+__global__ void __launch_bounds__(KNN_THREADS, 2)
+    knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ s, int N, int Npad, int C, int k,
+                    int32_t* __restrict__ idx, float* __restrict__ D) {
+  __shared__ __align__(16) float As[2][CK][TM];
+  __shared__ __align__(16) float Bs[2][CK][TN];
+  __shared__ __align__(16) float sBs[2][TN];
+  __shared__ float sAs[TM];
+
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * TM;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* xTb = xT + (size_t)b * C * Npad;
+  const float* sb = s + (size_t)b * Npad;
+  const int T = Npad / TN;
+  const int Q = (C + CK - 1) / CK;
+  const int S = T * Q;
+
+  if (tid < TM) sAs[tid] = sb[r0 + tid];
+
+  auto load_stage = [&](int st) {
+    const int t = st / Q, q = st - t * Q, buf = st & 1;
+    const int c0 = q * CK;
+    const int ck = min(CK, C - c0);
+    for (int e = tid; e < ck * (TM / 4); e += KNN_THREADS) {
+      const int cc = e / (TM / 4), v = e % (TM / 4);
+      cp_async16(&As[buf][cc][v * 4], xTb + (size_t)(c0 + cc) * Npad + r0 + v * 4);
+    }
+    for (int e = tid; e < ck * (TN / 4); e += KNN_THREADS) {
+      const int cc = e / (TN / 4), v = e % (TN / 4);
+      cp_async16(&Bs[buf][cc][v * 4], xTb + (size_t)(c0 + cc) * Npad + t * TN + v * 4);
+    }
+    if (q == 0 && tid < TN / 4) cp_async16(&sBs[t & 1][tid * 4], sb + t * TN + tid * 4);
+  };
+
+  WarpList<KS> L[8];
+  float tau_d[8];
+  int tau_j[8];
+  if (!WRITE_D) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      L[r].init();
+      tau_d[r] = __int_as_float(0x7f800000);
+      tau_j[r] = 0x7fffffff;
+    }
+  }
+
+  float acc[8][4];
+  load_stage(0);
+  cp_async_commit();
+  for (int st = 0; st < S; ++st) {
+    if (st + 1 < S) load_stage(st + 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const int t = st / Q, q = st - t * Q, buf = st & 1;
+    const int ck = min(CK, C - q * CK);
+    if (q == 0) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0f;
+    }
+#pragma unroll 4
+    for (int cc = 0; cc < ck; ++cc) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][cc][warp * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][cc][warp * 8 + 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][cc][lane * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = __fmaf_rn(a[r], bb[c], acc[r][c]);
+    }
+    if (q == Q - 1) {
+      const float4 sj4 = *reinterpret_cast<const float4*>(&sBs[t & 1][lane * 4]);
+      const float sj[4] = {sj4.x, sj4.y, sj4.z, sj4.w};
+      const int col0 = t * TN + lane * 4;
+      const int cj[4] = {col0, col0 + 1, col0 + 2, col0 + 3};
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float si = sAs[warp * 8 + r];
+        float dv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)  // ops.py:16: (s_i + s_j) - 2*p ; +0 canonicalises -0
+          dv[c] = __fadd_rn(__fsub_rn(__fadd_rn(si, sj[c]), __fmul_rn(2.0f, acc[r][c])), 0.0f);
+        if (WRITE_D) {
+          const int row = r0 + warp * 8 + r;
+          if (row < N) {
+            float* drow = D + ((size_t)b * N + row) * N;
+            if ((N & 3) == 0 && col0 + 3 < N) {
+              *reinterpret_cast<float4*>(drow + col0) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (cj[c] < N) drow[cj[c]] = dv[c];
+            }
+          }
+        } else {
+          warp_offer4<KS>(L[r], dv, cj, N, k, tau_d[r], tau_j[r], lane);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (!WRITE_D) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int row = r0 + warp * 8 + r;
+      if (row < N) {
+        int32_t* o = idx + ((size_t)b * N + row) * k;
+#pragma unroll
+        for (int sl = 0; sl < KS; ++sl) {
+          const int pos = sl * 32 + lane;
+          if (pos < k) o[pos] = L[r].j[sl];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row top-k on a materialised matrix (ops.py:18 alone): one warp per row, coalesced 128 B reads.
+template <int KS>
+__global__ void __launch_bounds__(256) topk_rows_kernel(const float* __restrict__ D, int64_t rows, int N, int k,
+                                                        int32_t* __restrict__ idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* dr = D + row * (int64_t)N;
+  WarpList<KS> L;
+  L.init();
+  float td = __int_as_float(0x7f800000);
+  int tj = 0x7fffffff;
+  for (int c0 = 0; c0 < N; c0 += 128) {
+    float dv[4];
+    int cj[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      cj[q] = c0 + q * 32 + lane;
+      dv[q] = (cj[q] < N) ? __fadd_rn(__ldg(dr + cj[q]), 0.0f) : 0.0f;
+    }
+    warp_offer4<KS>(L, dv, cj, N, k, td, tj, lane);
+  }
+  int32_t* o = idx + row * (int64_t)k;
+#pragma unroll
+  for (int sl = 0; sl < KS; ++sl) {
+    const int pos = sl * 32 + lane;
+    if (pos < k) o[pos] = L.j[sl];
+  }
+}
+
+static inline int npad_of(int N) { return ((N + TN - 1) / TN) * TN; }
+
+static int knn_common(const float* x, int B, int N, int C, void* ws, size_t ws_bytes, cudaStream_t st,
+                      float** xT, float** s, int* Npad) {
+  DG_REQUIRE(x && ws, DGCNN_ERR_INVALID, "knn: null pointer");
+  DG_REQUIRE(B > 0 && N > 0 && C > 0, DGCNN_ERR_INVALID, "knn: bad shape B=%d N=%d C=%d", B, N, C);
+  DG_REQUIRE(B <= 65535, DGCNN_ERR_UNSUPPORTED, "knn: B=%d > 65535", B);
+  DG_REQUIRE(((uintptr_t)ws & 15) == 0, DGCNN_ERR_INVALID, "knn: workspace must be 16-byte aligned");
+  DG_REQUIRE(ws_bytes >= dgcnn_knn_workspace_bytes(B, N, C), DGCNN_ERR_WORKSPACE,
+             "knn: workspace %zu < %zu bytes", ws_bytes, dgcnn_knn_workspace_bytes(B, N, C));
+  *Npad = npad_of(N);
+  *xT = reinterpret_cast<float*>(ws);
+  *s = *xT + (size_t)B * C * (*Npad);
+  dim3 g(cdiv(*Npad, 256), B);
+  knn_prep_kernel<<<g, 256, 0, st>>>(x, *xT, *s, N, *Npad, C);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("knn_prep_kernel");
+  return DGCNN_OK;
+}
+
+}  // namespace dgcnn
+
+using namespace dgcnn;
+
+extern "C" size_t dgcnn_knn_workspace_bytes(int B, int N, int C) {
+  if (B <= 0 || N <= 0 || C <= 0) return 0;
+  const size_t Npad = npad_of(N);
+  return ((size_t)B * C * Npad + (size_t)B * Npad) * sizeof(float);
+}
+
+extern "C" int dgcnn_pairwise_distance(const float* x, float* D, int B, int N, int C, void* ws, size_t ws_bytes,
+                                       dgcnn_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_REQUIRE(D, DGCNN_ERR_INVALID, "pairwise_distance: null output");
+  DG_REQUIRE(((uintptr_t)D & 15) == 0, DGCNN_ERR_INVALID, "pairwise_distance: D must be 16-byte aligned");
+  float *xT = nullptr, *s = nullptr;
+  int Npad = 0;
+  int rc = knn_common(x, B, N, C, ws, ws_bytes, st, &xT, &s, &Npad);
+  if (rc) return rc;
+  dim3 g(cdiv(N, TM), B);
+  knn_tile_kernel<1, true><<<g, KNN_THREADS, 0, st>>>(xT, s, N, Npad, C, 1, nullptr, D);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("knn_tile_kernel<D>");
+  return DGCNN_OK;
+}
+
+extern "C" int dgcnn_knn(const float* x, int32_t* idx, int B, int N, int C, int k, void* ws, size_t ws_bytes,
+                         dgcnn_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_REQUIRE(idx, DGCNN_ERR_INVALID, "knn: null output");
+  DG_REQUIRE(k >= 1 && k <= N, DGCNN_ERR_INVALID, "knn: need 1 <= k <= N (k=%d, N=%d)", k, N);
+  DG_REQUIRE(k <= DGCNN_KNN_MAX_K, DGCNN_ERR_UNSUPPORTED, "knn: k=%d > %d", k, DGCNN_KNN_MAX_K);
+  float *xT = nullptr, *s = nullptr;
+  int Npad = 0;
+  int rc = knn_common(x, B, N, C, ws, ws_bytes, st, &xT, &s, &Npad);
+  if (rc) return rc;
+  dim3 g(cdiv(N, TM), B);
+  if (k <= 32)
+    knn_tile_kernel<1, false><<<g, KNN_THREADS, 0, st>>>(xT, s, N, Npad, C, k, idx, nullptr);
+  else
+    knn_tile_kernel<2, false><<<g, KNN_THREADS, 0, st>>>(xT, s, N, Npad, C, k, idx, nullptr);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("knn_tile_kernel");
+  return DGCNN_OK;
+}
+
+extern "C" int dgcnn_topk_rows(const float* D, int32_t* idx, int64_t rows, int N, int k, dgcnn_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_REQUIRE(D && idx, DGCNN_ERR_INVALID, "topk_rows: null pointer");
+  DG_REQUIRE(rows > 0 && N > 0, DGCNN_ERR_INVALID, "topk_rows: bad shape rows=%lld N=%d", (long long)rows, N);
+  DG_REQUIRE(k >= 1 && k <= N, DGCNN_ERR_INVALID, "topk_rows: need 1 <= k <= N (k=%d, N=%d)", k, N);
+  DG_REQUIRE(k <= DGCNN_KNN_MAX_K, DGCNN_ERR_UNSUPPORTED, "topk_rows: k=%d > %d", k, DGCNN_KNN_MAX_K);
+  const int wpb = 8;
+  const int64_t blocks = (rows + wpb - 1) / wpb;
+  DG_REQUIRE(blocks < (1ll << 31), DGCNN_ERR_UNSUPPORTED, "topk_rows: too many rows");
+  if (k <= 32)
+    topk_rows_kernel<1><<<(unsigned)blocks, wpb * 32, 0, st>>>(D, rows, N, k, idx);
+  else
+    topk_rows_kernel<2><<<(unsigned)blocks, wpb * 32, 0, st>>>(D, rows, N, k, idx);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("topk_rows_kernel");
+  return DGCNN_OK;
+}

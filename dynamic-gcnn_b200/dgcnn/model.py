@@ -1,0 +1,107 @@
+"""dgcnn.model -- mirror of /root/reference/dgcnn/model.py:9-106 (same `build(point_cloud, flags)` signature).
+
+The EdgeConv stack (the hot path) runs on the hand-written kernels behind dgcnn.ops; the head follows the
+reference op for op.  Variables are created-or-reused in the default VariableStore under the caller's scope
+(trainval opens "dgcnn" like trainval.py:29), with the reference's TF variable names.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .head import conv_bn_relu_dense
+from .variables import default_store
+
+DROPOUT_KEEP = 0.7  # model.py:91: tf.nn.dropout(net, 0.7, None) -> keep_prob
+
+
+def build(point_cloud, flags, dropout_mask=None):
+    """-> logits [B,N,NUM_CLASS] (ReLU'd and batch-normalised like the reference's `Final`, model.py:94-101).
+
+    `dropout_mask` (optional, {0,1} keep mask [B,N,1,width]) replaces the random draw -- used by parity tests.
+    """
+    num_edge_conv = int(flags.EDGE_CONV_LAYERS)
+    num_edge_filters = flags.EDGE_CONV_FILTERS
+    num_fc = int(flags.FC_LAYERS)
+    num_fc_filters = flags.FC_FILTERS
+    is_training = bool(flags.TRAIN)
+    k = int(flags.KVALUE)
+    debug = bool(flags.DEBUG)
+    num_class = int(flags.NUM_CLASS)
+
+    net = point_cloud
+    batch_size, num_point = net.shape[0], net.shape[1]
+    if debug:
+        print("\n")
+        print("Shape %s ... Name %s" % (tuple(net.shape), "points"))
+
+    if flags.MODEL_NAME == "dgcnn":
+        tensors = ops.repeat_edge_conv(net, repeat=num_edge_conv, k=k, num_filters=num_edge_filters,
+                                       trainable=is_training, debug=debug)
+    elif flags.MODEL_NAME in ["residual-dgcnn", "residual-dgcnn-nofc"]:
+        tensors = ops.repeat_residual_edge_conv(net, repeat=num_edge_conv, k=k, num_filters=num_edge_filters,
+                                                trainable=is_training, debug=debug)
+    else:
+        print("Unsupported MODEL_NAME: %s" % flags.MODEL_NAME)
+        raise NotImplementedError
+
+    if flags.MODEL_NAME == "residual-dgcnn-nofc":                      # model.py:45-58
+        net = conv_bn_relu_dense(tensors[-1], "Final", num_class, True)
+        if debug: print("Shape %s ... Name %s" % (tuple(net.shape), "Final"))
+        return net.squeeze(-2)
+
+    concat = torch.cat([tensors[3 * i + 2] for i in range(num_edge_conv)], dim=-1)   # model.py:60-63
+    net = conv_bn_relu_dense(concat, "MergedEdgeConv", 1024, True)                   # model.py:65-72
+    if debug: print("Shape %s ... Name %s" % (tuple(net.shape), "MergedEdgeConv"))
+    tensors = tensors + [net]                                                        # model.py:74
+
+    g = net.amax(dim=1, keepdim=True)                                                # model.py:77 global max pool
+    if debug: print("Shape %s ... Name %s" % (tuple(g.shape), "maxpool0"))
+    g = g.reshape(batch_size, -1, 1, 1024).expand(batch_size, num_point, 1, 1024)    # model.py:80-81
+    net = torch.cat([g] + tensors, dim=3)                                            # model.py:83-85
+    if debug: print("Shape %s ... Name %s" % (tuple(net.shape), "concat"))
+
+    net = ops.fc(net=net, repeat=num_fc, num_filters=num_fc_filters, trainable=is_training, debug=debug)
+
+    if is_training:                                                                  # model.py:90-91
+        if dropout_mask is None:
+            net = torch.nn.functional.dropout(net, p=1.0 - DROPOUT_KEEP, training=True)
+        else:
+            net = net * dropout_mask / DROPOUT_KEEP
+        if debug: print("Shape %s ... Name %s" % (tuple(net.shape), "dropout"))
+
+    net = conv_bn_relu_dense(net, "Final", num_class, True)                          # model.py:94-101
+    if debug: print("Shape %s ... Name %s" % (tuple(net.shape), "Final"))
+    net = net.squeeze(-2)                                                            # model.py:104
+    return net
+
+
+def declare_variables(flags, num_channel: int, device) -> None:
+    """Create every variable build() would create, without running it (the TF graph is built -- and its
+    variables exist -- before the first batch: trainval.py:26-55, main_funcs.py:70-93 restore)."""
+    st = default_store()
+    L = int(flags.EDGE_CONV_LAYERS)
+    filt = ops._listify(flags.EDGE_CONV_FILTERS, L, "num_filters")
+    train = bool(flags.TRAIN)
+    cin = int(num_channel)
+    for i in range(L):
+        with st.variable_scope("EdgeConv%d" % i):
+            ops._conv_bn_vars("conv0", 2 * cin, int(filt[i]), train, device)
+            ops._conv_bn_vars("conv1", 2 * int(filt[i]), ops.CONV1_WIDTH, train, device)
+            if flags.MODEL_NAME != "dgcnn" and i > 0 and filt[i] != filt[i - 1]:
+                ops._conv_bn_vars("shortcut", ops.CONV1_WIDTH, int(filt[i]), train, device)
+        cin = ops.CONV1_WIDTH
+    if flags.MODEL_NAME == "residual-dgcnn-nofc":
+        ops._conv_bn_vars("Final", ops.CONV1_WIDTH, int(flags.NUM_CLASS), True, device)
+        return
+    if flags.MODEL_NAME not in ("dgcnn", "residual-dgcnn"):
+        print("Unsupported MODEL_NAME: %s" % flags.MODEL_NAME)
+        raise NotImplementedError
+    ops._conv_bn_vars("MergedEdgeConv", ops.CONV1_WIDTH * L, 1024, True, device)
+    width = 1024 + sum(2 * int(f) + ops.CONV1_WIDTH for f in filt) + 1024
+    nfc = int(flags.FC_LAYERS)
+    fcf = ops._listify(flags.FC_FILTERS, nfc, "num_filters")
+    for j in range(nfc):
+        ops._conv_bn_vars("FC%d" % j, width, int(fcf[j]), train, device)
+        width = int(fcf[j])
+    ops._conv_bn_vars("Final", width, int(flags.NUM_CLASS), True, device)

@@ -1,0 +1,356 @@
+"""dgcnn.ops -- B200-native mirror of /root/reference/dgcnn/ops.py (same names, arguments, error behaviour).
+
+    k_nn(points, k)                       ops.py:8    -> idx [B,N,k] int32
+    edges(points, k=20)                   ops.py:21   -> [B,N,k,2C]
+    edge_conv(point_cloud, k, num_filters, trainable, activation=relu, debug=False)   ops.py:42
+    repeat_edge_conv(...)                 ops.py:75
+    repeat_residual_edge_conv(...)        ops.py:100
+    fc(net, repeat, num_filters, trainable, debug=False)                              ops.py:142
+plus the names BASELINE.json's north_star uses for the same surface:
+    pairwise_distance(points) -> [B,N,N] ; knn(adj_matrix, k) -> idx ; get_edge_feature(points, nn_idx, k)
+
+Every hot-path op calls hand-written sm_100a CUDA through the C ABI in include/dgcnn_b200.h
+(ctypes binding in _native.py).  Inputs are torch CUDA fp32 tensors; there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import _native as nv
+from .variables import default_store, variable_scope
+
+relu = "relu"  # stand-in for tf.nn.relu as the `activation` argument (None = linear, ops.py:121)
+
+BN_EPS = 1e-3
+CONV1_WIDTH = 64  # ops.py:63
+
+
+# =============================================================================== raw kernels
+def k_nn(points: torch.Tensor, k: int) -> torch.Tensor:
+    """ops.py:8-19.  Fused distance + top-k; the [B,N,N] matrix is never written.  Not differentiable
+    (only the indices are used downstream, ops.py:19,34)."""
+    x = nv.require_cuda(points.detach(), "points")
+    if x.dim() != 3:
+        raise ValueError("k_nn: points must be [B,N,C]")
+    B, N, C = x.shape
+    k = int(k)
+    L = nv.lib()
+    need = L.dgcnn_knn_workspace_bytes(B, N, C)
+    ws = nv.workspace(x.device, need, "knn")
+    idx = torch.empty((B, N, k), dtype=torch.int32, device=x.device)
+    nv.check(L.dgcnn_knn(x.data_ptr(), idx.data_ptr(), B, N, C, k, ws.data_ptr(), ws.numel(),
+                         nv.stream_ptr(x.device)), "k_nn")
+    return idx
+
+
+def pairwise_distance(points: torch.Tensor) -> torch.Tensor:
+    """ops.py:11-16 materialised: D[b,i,j] = (s_i + s_j) - 2 x_i.x_j  -> [B,N,N]."""
+    x = nv.require_cuda(points.detach(), "points")
+    if x.dim() != 3:
+        raise ValueError("pairwise_distance: points must be [B,N,C]")
+    B, N, C = x.shape
+    L = nv.lib()
+    ws = nv.workspace(x.device, L.dgcnn_knn_workspace_bytes(B, N, C), "knn")
+    D = torch.empty((B, N, N), dtype=torch.float32, device=x.device)
+    nv.check(L.dgcnn_pairwise_distance(x.data_ptr(), D.data_ptr(), B, N, C, ws.data_ptr(), ws.numel(),
+                                       nv.stream_ptr(x.device)), "pairwise_distance")
+    return D
+
+
+def knn(adj_matrix: torch.Tensor, k: int = 20) -> torch.Tensor:
+    """ops.py:18 alone (north-star name): k smallest entries per row of a distance matrix, ascending,
+    ties -> lower index.  adj_matrix [..., N] -> idx [..., k] int32."""
+    D = nv.require_cuda(adj_matrix.detach(), "adj_matrix")
+    N = D.shape[-1]
+    rows = D.numel() // N
+    idx = torch.empty(D.shape[:-1] + (int(k),), dtype=torch.int32, device=D.device)
+    nv.check(nv.lib().dgcnn_topk_rows(D.data_ptr(), idx.data_ptr(), rows, N, int(k), nv.stream_ptr(D.device)), "knn")
+    return idx
+
+
+class _EdgeFeature(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx):
+        x = nv.require_cuda(points, "points")
+        ix = nv.require_cuda(idx, "idx", torch.int32)
+        B, N, C = x.shape
+        k = ix.shape[-1]
+        out = torch.empty((B, N, k, 2 * C), dtype=torch.float32, device=x.device)
+        nv.check(nv.lib().dgcnn_edge_feature(x.data_ptr(), ix.data_ptr(), out.data_ptr(), B, N, C, k,
+                                             nv.stream_ptr(x.device)), "edges")
+        ctx.save_for_backward(ix)
+        ctx.shape = (B, N, C, k)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (ix,) = ctx.saved_tensors
+        B, N, C, k = ctx.shape
+        g = nv.require_cuda(g, "grad")
+        gx = torch.empty((B, N, C), dtype=torch.float32, device=g.device)
+        nv.check(nv.lib().dgcnn_edge_feature_bwd(g.data_ptr(), ix.data_ptr(), gx.data_ptr(), B, N, C, k,
+                                                 nv.stream_ptr(g.device)), "edges_bwd")
+        return gx, None
+
+
+def get_edge_feature(point_cloud: torch.Tensor, nn_idx: torch.Tensor, k: Optional[int] = None) -> torch.Tensor:
+    """ops.py:30-39 with the indices supplied (north-star name) -> [B,N,k,2C]."""
+    if k is not None and nn_idx.shape[-1] != int(k):
+        raise ValueError("get_edge_feature: nn_idx has k=%d, argument says %d" % (nn_idx.shape[-1], int(k)))
+    return _EdgeFeature.apply(point_cloud, nn_idx)
+
+
+def edges(points: torch.Tensor, k: int = 20) -> torch.Tensor:
+    """ops.py:21-40."""
+    return _EdgeFeature.apply(points, k_nn(points, k))
+
+
+# =============================================================================== differentiable blocks
+def _gemm_raw(A, Bm, M, N, K, tA, tB):
+    L = nv.lib()
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    need = L.dgcnn_gemm_workspace_bytes(M, N, K, tA, tB)
+    ws = nv.workspace(A.device, need, "gemm") if need else None
+    nv.check(L.dgcnn_gemm(A.data_ptr(), Bm.data_ptr(), out.data_ptr(), M, N, K, tA, tB, nv.ptr(ws),
+                          ws.numel() if ws is not None else 0, nv.stream_ptr(A.device)), "gemm")
+    return out
+
+
+class _Conv1x1(torch.autograd.Function):
+    """slim.conv2d(kernel_size=1, stride=1, VALID) on channels-last data = [P,Cin] x [Cin,Cout]."""
+
+    @staticmethod
+    def forward(ctx, a, w):
+        a = nv.require_cuda(a, "conv input")
+        w = nv.require_cuda(w, "conv weights")
+        ctx.save_for_backward(a, w)
+        return _gemm_raw(a, w, a.shape[0], w.shape[1], a.shape[1], 0, 0)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, w = ctx.saved_tensors
+        g = nv.require_cuda(g, "grad")
+        P, Cin = a.shape
+        Cout = w.shape[1]
+        ga = gw = None
+        if ctx.needs_input_grad[0]:
+            ga = _gemm_raw(g, w, P, Cin, Cout, 0, 1)  # g . W^T
+        if ctx.needs_input_grad[1]:
+            gw = _gemm_raw(a, g, Cin, Cout, P, 1, 0)  # A^T . g  (split over the P points)
+        return ga, gw
+
+
+class _EdgeConvGather(torch.autograd.Function):
+    """ops.py:45-57 after the algebraic split z_ij = u_i + v_idx(i,j): BN(train)+ReLU+max_k/mean_k."""
+
+    @staticmethod
+    def forward(ctx, uv, idx, beta, B, N, k):
+        uv = nv.require_cuda(uv, "uv")
+        idx = nv.require_cuda(idx, "idx", torch.int32)
+        beta = nv.require_cuda(beta, "beta")
+        P, F2 = uv.shape
+        F = F2 // 2
+        dev = uv.device
+        L = nv.lib()
+        st = nv.stream_ptr(dev)
+        ws = nv.workspace(dev, L.dgcnn_edgeconv_workspace_bytes(F), "stats")
+        zmax = torch.empty((P, F), dtype=torch.float32, device=dev)
+        cnt = torch.empty((P, F), dtype=torch.float32, device=dev)
+        mean = torch.empty(F, dtype=torch.float32, device=dev)
+        rstd = torch.empty(F, dtype=torch.float32, device=dev)
+        nv.check(L.dgcnn_edgeconv_fwd_stats(uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(),
+                                            cnt.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), st), "edgeconv_fwd_stats")
+        omax = torch.empty((P, F), dtype=torch.float32, device=dev)
+        omean = torch.empty((P, F), dtype=torch.float32, device=dev)
+        nv.check(L.dgcnn_edgeconv_fwd_apply(uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(),
+                                            mean.data_ptr(), rstd.data_ptr(), beta.data_ptr(), omax.data_ptr(),
+                                            omean.data_ptr(), st), "edgeconv_fwd_apply")
+        ctx.save_for_backward(uv, idx, beta, zmax, cnt, mean, rstd)
+        ctx.dims = (B, N, F, k)
+        return omax, omean
+
+    @staticmethod
+    def backward(ctx, gmax, gmean):
+        uv, idx, beta, zmax, cnt, mean, rstd = ctx.saved_tensors
+        B, N, F, k = ctx.dims
+        dev = uv.device
+        L = nv.lib()
+        st = nv.stream_ptr(dev)
+        gmax = nv.require_cuda(gmax, "grad max")
+        gmean = nv.require_cuda(gmean, "grad mean")
+        ws = nv.workspace(dev, L.dgcnn_edgeconv_workspace_bytes(F), "stats")
+        s1 = torch.empty(F, dtype=torch.float32, device=dev)
+        s2 = torch.empty(F, dtype=torch.float32, device=dev)
+        common = (uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(), cnt.data_ptr(), mean.data_ptr(),
+                  rstd.data_ptr(), beta.data_ptr(), gmax.data_ptr(), gmean.data_ptr(), s1.data_ptr(), s2.data_ptr())
+        nv.check(L.dgcnn_edgeconv_bwd_stats(*common, ws.data_ptr(), ws.numel(), st), "edgeconv_bwd_stats")
+        guv = torch.empty_like(uv)
+        nv.check(L.dgcnn_edgeconv_bwd_apply(*common, guv.data_ptr(), st), "edgeconv_bwd_apply")
+        return guv, None, s1, None, None, None
+
+
+class _BnAct(torch.autograd.Function):
+    """slim.batch_norm (train mode, beta only, eps 1e-3) [+ residual] [+ ReLU] on a [P,C] tensor."""
+
+    @staticmethod
+    def forward(ctx, z, beta, residual, relu_flag):
+        z = nv.require_cuda(z, "z")
+        beta = nv.require_cuda(beta, "beta")
+        res = nv.require_cuda(residual, "residual") if residual is not None else None
+        P, C = z.shape
+        dev = z.device
+        L = nv.lib()
+        ws = nv.workspace(dev, L.dgcnn_bn_workspace_bytes(C), "stats")
+        out = torch.empty_like(z)
+        mean = torch.empty(C, dtype=torch.float32, device=dev)
+        rstd = torch.empty(C, dtype=torch.float32, device=dev)
+        nv.check(L.dgcnn_bn_act_fwd(z.data_ptr(), P, C, beta.data_ptr(), nv.ptr(res), int(bool(relu_flag)),
+                                    out.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    nv.stream_ptr(dev)), "bn_act_fwd")
+        ctx.save_for_backward(z, out, mean, rstd)
+        ctx.relu = bool(relu_flag)
+        ctx.has_res = res is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        z, out, mean, rstd = ctx.saved_tensors
+        g = nv.require_cuda(g, "grad")
+        P, C = z.shape
+        dev = z.device
+        L = nv.lib()
+        ws = nv.workspace(dev, L.dgcnn_bn_workspace_bytes(C), "stats")
+        gz = torch.empty_like(z)
+        gbeta = torch.empty(C, dtype=torch.float32, device=dev)
+        gpre = torch.empty_like(z) if ctx.has_res else None
+        nv.check(L.dgcnn_bn_act_bwd(z.data_ptr(), out.data_ptr(), g.data_ptr(), P, C, mean.data_ptr(),
+                                    rstd.data_ptr(), int(ctx.relu), gz.data_ptr(), gbeta.data_ptr(), nv.ptr(gpre),
+                                    ws.data_ptr(), ws.numel(), nv.stream_ptr(dev)), "bn_act_bwd")
+        return gz, gbeta, gpre, None
+
+
+# =============================================================================== variables (slim.conv2d)
+def _conv_bn_vars(scope: str, cin: int, cout: int, trainable: bool, device):
+    """Variables slim.conv2d(normalizer_fn=slim.batch_norm) creates under `scope`: weights (xavier, no bias)
+    and BatchNorm/beta (zeros; beta is always trainable, scale=False => no gamma)  [TF-default]."""
+    st = default_store()
+    with st.variable_scope(scope):
+        w = st.get_variable("weights", (cin, cout), "xavier", trainable=trainable, device=device)
+        with st.variable_scope("BatchNorm"):
+            b = st.get_variable("beta", (cout,), "zeros", trainable=True, device=device)
+    return w, b
+
+
+def _conv_bn_act(net2d, scope, cout, trainable, activation, residual2d=None):
+    """1x1 conv + BN(train) [+ residual] + activation on a [P,Cin] tensor, all through the C ABI."""
+    w, b = _conv_bn_vars(scope, net2d.shape[1], cout, trainable, net2d.device)
+    z = _Conv1x1.apply(net2d, w)
+    return _BnAct.apply(z, b, residual2d, activation is not None)
+
+
+def _dbg(debug, t, name):
+    if debug:
+        print("Shape %s ... Name %s" % (tuple(t.shape), name))
+
+
+def _cur_scope():
+    return "/".join(default_store()._scope)
+
+
+# =============================================================================== reference API
+def edge_conv(point_cloud, k, num_filters, trainable, activation=relu, debug=False, _residual=None) -> List[torch.Tensor]:
+    """ops.py:42-73 -> [net_max [B,N,1,F], net_mean [B,N,1,F], net [B,N,1,64]].
+
+    edges() -> conv0 is evaluated as  [x_i, x_j-x_i].[Wa;Wb] = x_i.(Wa-Wb) + x_j.Wb : one per-point GEMM
+    (uv) followed by two L2-resident gather passes; nothing of size B*N*k*{2C,F} touches HBM.
+    `_residual` (private) fuses ops.py:134's relu(shortcut + net) into conv1's BN epilogue.
+    """
+    x = nv.require_cuda(point_cloud, "point_cloud")
+    if x.dim() != 3:
+        raise ValueError("edge_conv: point_cloud must be [B,N,C]")
+    B, N, C = x.shape
+    k = int(k)
+    F = int(num_filters)
+    idx = k_nn(x, k)                                                            # ops.py:23
+    _dbg(debug, torch.empty(B, N, k, 2 * C, device="meta"), _cur_scope() + "/edges (never materialised)")
+    w0, b0 = _conv_bn_vars("conv0", 2 * C, F, trainable, x.device)              # ops.py:47-54
+    wp = torch.cat([w0[:C] - w0[C:], w0[C:]], dim=1)                            # [C, 2F] = [Wa-Wb | Wb]
+    uv = _Conv1x1.apply(x.reshape(B * N, C), wp)
+    net_max, net_mean = _EdgeConvGather.apply(uv, idx, b0, B, N, k)             # ops.py:53-57
+    _dbg(debug, torch.empty(B, N, k, F, device="meta"), _cur_scope() + "/conv0 (never materialised)")
+    net = torch.cat([net_max, net_mean], dim=-1)                                # ops.py:58
+    _dbg(debug, net_max.view(B, N, 1, F), _cur_scope() + "/Max")
+    _dbg(debug, net_mean.view(B, N, 1, F), _cur_scope() + "/Mean")
+    _dbg(debug, net.view(B, N, 1, 2 * F), _cur_scope() + "/concat")
+    res2d = _residual.reshape(B * N, CONV1_WIDTH) if _residual is not None else None
+    act = relu if (_residual is not None) else activation
+    net = _conv_bn_act(net, "conv1", CONV1_WIDTH, trainable, act, res2d)        # ops.py:62-70 (+134)
+    _dbg(debug, net.view(B, N, 1, CONV1_WIDTH), _cur_scope() + "/conv1")
+    return [net_max.view(B, N, 1, F), net_mean.view(B, N, 1, F), net.view(B, N, 1, CONV1_WIDTH)]
+
+
+def _listify(v, repeat, what):
+    if not type(v) == type(list()):
+        return [int(v)] * repeat
+    if not len(v) == repeat:
+        print("Length of %s != repeat" % what)
+        raise ValueError
+    return v
+
+
+def repeat_edge_conv(point_cloud, repeat, k, num_filters, trainable, debug=False):
+    """ops.py:75-98."""
+    repeat = int(repeat)
+    k = _listify(k, repeat, "k")
+    num_filters = _listify(num_filters, repeat, "num_filters")
+    net = point_cloud
+    tensors = []
+    for i in range(repeat):
+        with variable_scope("EdgeConv%d" % i):
+            tensors += edge_conv(net, k[i], num_filters[i], trainable, debug=debug)
+            net = tensors[-1].squeeze(-2)
+    return tensors
+
+
+def repeat_residual_edge_conv(point_cloud, repeat, k, num_filters, trainable, debug=False):
+    """ops.py:100-140."""
+    repeat = int(repeat)
+    k = _listify(k, repeat, "k")
+    num_filters = _listify(num_filters, repeat, "num_filters")
+    net = point_cloud
+    tensors = []
+    shortcut = None
+    for i in range(repeat):
+        with variable_scope("EdgeConv%d" % i):
+            if shortcut is None:
+                tensors += edge_conv(net, k[i], num_filters[i], trainable, debug=debug)
+            else:
+                if not num_filters[i] == num_filters[i - 1]:            # ops.py:124-133
+                    B, N = shortcut.shape[0], shortcut.shape[1]
+                    if int(num_filters[i]) != CONV1_WIDTH:
+                        # the reference would fail in tf.add here: conv1 is 64 wide whatever num_filters says
+                        raise ValueError("shortcut conv to %d channels cannot be added to the 64-channel conv1 "
+                                         "output (ops.py:63,134)" % int(num_filters[i]))
+                    sc = _conv_bn_act(shortcut.reshape(B * N, -1), "shortcut", int(num_filters[i]), trainable, None)
+                    shortcut = sc.view(B, N, 1, -1)
+                # conv1 with activation=None, then relu(shortcut + out)  (ops.py:121,134) fused in one epilogue
+                tensors += edge_conv(net, k[i], num_filters[i], trainable, activation=None, debug=debug,
+                                     _residual=shortcut)
+            net = tensors[-1]
+            shortcut = tensors[-1]
+            net = net.squeeze(-2)
+    return tensors
+
+
+def fc(net, repeat, num_filters, trainable, debug=False):
+    """ops.py:142-163: repeat x (1x1 conv + BN + ReLU) on [B,N,1,C]."""
+    repeat = int(repeat)
+    num_filters = _listify(num_filters, repeat, "num_filters")
+    from .head import conv_bn_relu_dense
+    for i in range(repeat):
+        net = conv_bn_relu_dense(net, "FC%d" % i, int(num_filters[i]), trainable)
+        _dbg(debug, net, _cur_scope() + "/FC%d" % i)
+    return net

@@ -1,0 +1,199 @@
+"""dgcnn.trainval -- mirror of /root/reference/dgcnn/trainval.py:7-129 (same class and method names).
+
+What changes underneath:
+  * the reference builds one TF "tower" per GPU inside ONE process and averages gradients on /cpu:0
+    (trainval.py:16,26-29,59-69).  Here it is one process per GPU (torchrun); tower i of `flags.GPUS` is run by
+    rank  i * world // len(GPUS); with a single process all towers run back to back on the one device.
+  * every trainable variable and its gradient live in ONE flat fp32 buffer.  Each tower's backward adds
+    grad/len(GPUS) into it (accumulation over micro-steps is a SUM, trainval.py:79); apply_gradient() issues
+    a single NCCL all-reduce(sum) of that buffer -- the only collective -- and one fused TF-form Adam kernel.
+  * BatchNorm statistics stay per tower micro-batch (the reference's BN is per tower), so no SyncBN.
+  * `sess` is accepted and ignored.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native as nv
+from . import model as _model
+from .parallel import allreduce_flat_, tower_assignment
+from .variables import VariableStore, set_default_store, default_store
+
+
+class trainval(object):
+    ADAM_B1, ADAM_B2, ADAM_EPS = 0.9, 0.999, 1e-8  # tf.train.AdamOptimizer defaults
+
+    def __init__(self, flags):
+        self._flags = flags
+        self._store = None
+
+    # ------------------------------------------------------------------ setup
+    def _pick_device(self):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dgcnn.trainval needs a CUDA device (B200); there is no CPU fallback")
+        self._world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self._rank = dist.get_rank() if self._world > 1 else 0
+        local = int(os.environ.get("LOCAL_RANK", "0")) if self._world > 1 else 0
+        dev = torch.device("cuda", local % torch.cuda.device_count())
+        torch.cuda.set_device(dev)
+        return dev
+
+    def initialize(self):
+        f = self._flags
+        self._device = self._pick_device()
+        # towers this rank executes (main_funcs.py:145-152 cuts one slice per entry of flags.GPUS)
+        self._towers = tower_assignment(len(f.GPUS), self._world, self._rank)
+        seed = int(getattr(f, "SEED", 0))
+        self._store = VariableStore(device=self._device, seed=seed if seed >= 0 else 0)
+        old = set_default_store(self._store)
+        try:
+            with self._store.variable_scope("dgcnn"):                  # trainval.py:29
+                _model.declare_variables(f, int(f.NUM_CHANNEL), self._device)
+        finally:
+            set_default_store(old)
+        if f.TRAIN:
+            self._store.flatten(extra=2)                                # +2: loss, accuracy ride along
+            n = self._store.num_trainable
+            self._adam_m = torch.zeros(n, dtype=torch.float32, device=self._device)
+            self._adam_v = torch.zeros(n, dtype=torch.float32, device=self._device)
+            self._adam_t = 0
+        self.last_loss = None
+        self.last_accuracy = None
+
+    @property
+    def variables(self) -> VariableStore:
+        return self._store
+
+    # ------------------------------------------------------------------ helpers
+    def _to_dev(self, a, dtype):
+        if a is None:
+            return None
+        t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))
+        return t.to(self._device, dtype=dtype, non_blocking=True)
+
+    def feed_dict(self, data, label=None, weight=None):
+        """trainval.py:87-95: per-tower inputs.  Returns {tower: (points, labels, weights)} for this rank's towers,
+        already on the device (the host->device copy of the reference's feed_dict)."""
+        res = {}
+        for i in self._towers:
+            res[i] = (self._to_dev(data[i], torch.float32),
+                      self._to_dev(label[i], torch.int64) if label is not None else None,
+                      self._to_dev(weight[i], torch.float32) if weight is not None else None)
+        return res
+
+    def _forward(self, points, labels, weights, dropout_mask=None):
+        old = set_default_store(self._store)
+        try:
+            with self._store.variable_scope("dgcnn"):
+                pred = _model.build(points, self._flags, dropout_mask=dropout_mask)      # trainval.py:38
+        finally:
+            set_default_store(old)
+        softmax = torch.softmax(pred, dim=-1)                                             # trainval.py:39
+        accuracy = loss = None
+        if labels is not None:
+            accuracy = (pred.argmax(dim=2) == labels).to(torch.float32).mean()           # trainval.py:41-42
+            xent = torch.nn.functional.cross_entropy(pred.reshape(-1, pred.shape[-1]), labels.reshape(-1),
+                                                     reduction="none").reshape(labels.shape)
+            if weights is not None:                                                       # trainval.py:47-51
+                xent = xent * weights
+            loss = xent.mean()                                                            # trainval.py:52
+        return softmax, accuracy, loss
+
+    # ------------------------------------------------------------------ reference API
+    def make_summary(self, sess, data, label, weight):
+        if not self._flags.TRAIN:
+            raise NotImplementedError
+        with torch.no_grad():
+            res = self.inference(sess, data, label, weight)
+        return {"accuracy": float(res[-2]), "loss": float(res[-1])}
+
+    def inference(self, sess, data, label=None, weight=None):
+        """trainval.py:103-108 -> [softmax per tower..., (accuracy, loss)]."""
+        feeds = self.feed_dict(data, label, weight)
+        outs, accs, losses = [], [], []
+        with torch.no_grad():
+            for i in self._towers:
+                pts, lab, wgt = feeds[i]
+                sm, acc, loss = self._forward(pts, lab, wgt)
+                outs.append(sm)
+                if lab is not None:
+                    accs.append(acc)
+                    losses.append(loss)
+        ops = [o.cpu().numpy() for o in outs]
+        if label is not None:
+            ops += [float(torch.stack(accs).mean()), float(torch.stack(losses).mean())]
+        return ops
+
+    def accum_gradient(self, sess, data, label, weight=None, summary=False, sync=True):
+        """trainval.py:110-119 -> [None, accuracy, loss(, summary)].  Adds this micro-batch's tower-averaged
+        gradient into the flat accumulator.  sync=False returns 0-d device tensors instead of floats."""
+        if not self._flags.TRAIN:
+            raise NotImplementedError
+        feeds = self.feed_dict(data, label, weight)
+        G = float(len(self._flags.GPUS))
+        accs, losses = [], []
+        for i in self._towers:
+            pts, lab, wgt = feeds[i]
+            _, acc, loss = self._forward(pts, lab, wgt)
+            (loss / G).backward()                               # grads mean over towers: trainval.py:64-69
+            accs.append(acc.detach())
+            losses.append(loss.detach())
+        if losses:
+            acc = torch.stack(accs).mean()
+            loss = torch.stack(losses).mean()
+            fg = self._store.flat_grad
+            scale = len(self._towers) / G
+            fg[-2] += loss * scale
+            fg[-1] += acc * scale
+        else:
+            acc = loss = torch.zeros((), device=self._device)
+        res = [None, acc, loss] if not sync else [None, float(acc), float(loss)]
+        if summary:
+            res.append({"accuracy": float(acc), "loss": float(loss)})
+        return res
+
+    def zero_gradients(self, sess=None):
+        if not self._flags.TRAIN:
+            raise NotImplementedError
+        self._store.flat_grad.zero_()
+        return [None]
+
+    def apply_gradient(self, sess=None):
+        """trainval.py:125-129: ONE all-reduce of the flat gradient buffer, then fused Adam (TF form)."""
+        if not self._flags.TRAIN:
+            raise NotImplementedError
+        st = self._store
+        fg = st.flat_grad
+        allreduce_flat_(fg)                                      # towers were pre-divided by len(GPUS)
+        n = st.num_trainable
+        self.last_loss, self.last_accuracy = fg[-2], fg[-1]      # summed over micro-steps, mean over towers
+        self._adam_t += 1
+        t = self._adam_t
+        lr = float(self._flags.LEARNING_RATE)
+        lr_t = lr * math.sqrt(1.0 - self.ADAM_B2 ** t) / (1.0 - self.ADAM_B1 ** t)
+        nv.check(nv.lib().dgcnn_adam_tf_step(st.flat_param.data_ptr(), fg.data_ptr(), self._adam_m.data_ptr(),
+                                             self._adam_v.data_ptr(), n, lr_t, self.ADAM_B1, self.ADAM_B2,
+                                             self.ADAM_EPS, 1.0, nv.stream_ptr(self._device)), "adam_tf_step")
+        return None
+
+    # ------------------------------------------------------------------ checkpoints (tf.train.Saver stand-in)
+    def save(self, prefix: str, global_step: int) -> str:
+        path = "%s-%d" % (prefix, int(global_step))
+        blob = {"variables": self._store.state_dict(), "iteration": int(global_step)}
+        if self._flags.TRAIN:
+            blob.update(adam_m=self._adam_m.cpu(), adam_v=self._adam_v.cpu(), adam_t=self._adam_t)
+        torch.save(blob, path)
+        return path
+
+    def restore(self, path: str) -> None:
+        blob = torch.load(path, map_location="cpu")
+        self._store.load_state_dict(blob["variables"])
+        if self._flags.TRAIN and "adam_m" in blob:
+            self._adam_m.copy_(blob["adam_m"])
+            self._adam_v.copy_(blob["adam_v"])
+            self._adam_t = int(blob["adam_t"])

@@ -1,0 +1,121 @@
+/*
+ * dgcnn_b200.h -- C ABI of the B200-native EdgeConv hot path (libdgcnn_b200.so, sm_100a).
+ *
+ * The reference (DeepLearnPhysics/dynamic-gcnn) has no native code and no FFI: its boundary
+ * is the Python function API of dgcnn/ops.py + dgcnn/model.py, whose arithmetic is executed
+ * by TensorFlow-1.x kernels.  Each entry point below replaces the TF kernels behind one
+ * piece of that API (file:line cited per function).  The Python mirror
+ * (dynamic-gcnn_b200/dgcnn/ops.py) binds these with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers + sizes, all DEVICE pointers unless stated; fp32 / int32, row-major,
+ *     channels-last ([B,N,C]) exactly like the reference's tensors (ops.py:9).
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*), re-entrant,
+ *     and allocates nothing: the caller owns all buffers including `ws` scratch, sized by the
+ *     matching *_workspace_bytes().
+ *   - return 0 on success, negative DGCNN_ERR_* otherwise; text via dgcnn_last_error()
+ *     (thread-local).  Bad shapes never abort the process.
+ *   - no CPU fallback: without a CUDA device every compute entry returns DGCNN_ERR_CUDA.
+ */
+#ifndef DGCNN_B200_H_
+#define DGCNN_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGCNN_OK 0
+#define DGCNN_ERR_INVALID (-1)     /* bad shape / null pointer / misaligned buffer */
+#define DGCNN_ERR_UNSUPPORTED (-2) /* valid request outside the compiled envelope (e.g. k > 64) */
+#define DGCNN_ERR_WORKSPACE (-3)   /* ws_bytes too small */
+#define DGCNN_ERR_CUDA (-4)        /* launch / runtime failure */
+
+#define DGCNN_KNN_MAX_K 64
+
+typedef void* dgcnn_stream_t; /* cudaStream_t */
+
+int dgcnn_abi_version(void);
+const char* dgcnn_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t dgcnn_launch_count(void);
+
+/* ---- k_nn: dgcnn/ops.py:8-19 -------------------------------------------------------------
+ * D[b,i,j] = fl(fl(s_i + s_j) - 2*p_ij), s = sum_c fl(x_c^2) (sequential, no FMA),
+ * p = sequential-in-c fmaf chain (oracle/knn_oracle.c fixes this order).                   */
+size_t dgcnn_knn_workspace_bytes(int B, int N, int C);
+/* ops.py:11-16 ("pairwise_distance"): x [B,N,C] -> D [B,N,N] */
+int dgcnn_pairwise_distance(const float* x, float* D, int B, int N, int C, void* ws, size_t ws_bytes,
+                            dgcnn_stream_t stream);
+/* ops.py:8-19 fused ("knn"): the [B,N,N] matrix never leaves the SM.  idx [B,N,k] int32, nearest
+ * first, self included, equal distances -> lower index first (tf.nn.top_k sorted=True).     */
+int dgcnn_knn(const float* x, int32_t* idx, int B, int N, int C, int k, void* ws, size_t ws_bytes,
+              dgcnn_stream_t stream);
+/* ops.py:18 on a materialised matrix: D [rows,N] -> idx [rows,k] (k smallest, same tie rule) */
+int dgcnn_topk_rows(const float* D, int32_t* idx, int64_t rows, int N, int k, dgcnn_stream_t stream);
+
+/* ---- edges (= get_edge_feature): dgcnn/ops.py:21-40 ----------------------------------------
+ * out[b,i,j,:] = concat(x[b,i,:], x[b,idx[b,i,j],:] - x[b,i,:])  -> [B,N,k,2C]              */
+int dgcnn_edge_feature(const float* x, const int32_t* idx, float* out, int B, int N, int C, int k,
+                       dgcnn_stream_t stream);
+/* gradient of the above wrt x (tf.gather grad = scatter-add): g_out [B,N,k,2C] -> gx [B,N,C] */
+int dgcnn_edge_feature_bwd(const float* g_out, const int32_t* idx, float* gx, int B, int N, int C, int k,
+                           dgcnn_stream_t stream);
+
+/* ---- 1x1 conv as a per-point GEMM: slim.conv2d kernel_size=1, ops.py:47-54,62-70 -----------
+ * C[M,N] = op(A)[M,K] . op(B)[K,N], fp32, each output one sequential-in-k fmaf chain per
+ * k-split.  transA: A is stored [K,M]; transB: B is stored [N,K].                            */
+size_t dgcnn_gemm_workspace_bytes(int M, int N, int K, int transA, int transB);
+int dgcnn_gemm(const float* A, const float* B, float* C, int M, int N, int K, int transA, int transB,
+               void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+
+/* ---- fused EdgeConv core: ops.py:45-57 (edges -> conv0 -> BN(train) -> ReLU -> max_k, mean_k)
+ * Uses [x_i, x_j - x_i].[Wa;Wb] = x_i.(Wa-Wb) + x_j.Wb: the caller first forms
+ * uv[P, 2F] = x[P,C] . [Wa-Wb | Wb] with dgcnn_gemm (P = B*N), so that z_ij = u_i + v_{idx(i,j)}
+ * and the [B,N,k,2C] / [B,N,k,F] tensors are never materialised.
+ *   fwd_stats : gather pass 1 -> zmax[P,F] = max_j z_ij, cnt[P,F] = #{j: z_ij == zmax},
+ *               BN batch statistics mean[F], rstd[F] = 1/sqrt(var_biased + 1e-3) over all B*N*k
+ *   fwd_apply : gather pass 2 -> out_max[P,F] = relu((zmax-mean)*rstd+beta),
+ *               out_mean[P,F] = mean_j relu((z_ij-mean)*rstd+beta)
+ *   bwd_stats : s1[F] = sum g_pre (= d beta), s2[F] = sum g_pre*zhat
+ *   bwd_apply : g_uv[P,2F] (u half written, v half scatter-added; zeroed inside)             */
+size_t dgcnn_edgeconv_workspace_bytes(int F);
+int dgcnn_edgeconv_fwd_stats(const float* uv, const int32_t* idx, int B, int N, int F, int k, float* zmax,
+                             float* cnt, float* mean, float* rstd, void* ws, size_t ws_bytes,
+                             dgcnn_stream_t stream);
+int dgcnn_edgeconv_fwd_apply(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                             const float* zmax, const float* mean, const float* rstd, const float* beta,
+                             float* out_max, float* out_mean, dgcnn_stream_t stream);
+int dgcnn_edgeconv_bwd_stats(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                             const float* zmax, const float* cnt, const float* mean, const float* rstd,
+                             const float* beta, const float* g_max, const float* g_mean, float* s1,
+                             float* s2, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+int dgcnn_edgeconv_bwd_apply(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                             const float* zmax, const float* cnt, const float* mean, const float* rstd,
+                             const float* beta, const float* g_max, const float* g_mean, const float* s1,
+                             const float* s2, float* g_uv, dgcnn_stream_t stream);
+
+/* ---- train-mode BatchNorm (+residual) (+ReLU) on a [rows,C] per-point tensor ---------------
+ * slim.batch_norm defaults (is_training=True, center=True, scale=False, eps=1e-3) after a 1x1 conv:
+ * ops.py:53,68 ; residual add + relu: ops.py:134.
+ *   fwd: out = act((z-mean)*rstd + beta [+ residual]); mean/rstd [C] are outputs (saved for bwd)
+ *   bwd: g_pre = g_out * (relu ? out>0 : 1)  (optional output, = gradient of the residual)
+ *        g_beta = sum g_pre ; g_z = rstd*(g_pre - mean(g_pre) - zhat*mean(g_pre*zhat))      */
+size_t dgcnn_bn_workspace_bytes(int C);
+int dgcnn_bn_act_fwd(const float* z, int64_t rows, int C, const float* beta, const float* residual, int relu,
+                     float* out, float* mean, float* rstd, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+int dgcnn_bn_act_bwd(const float* z, const float* out, const float* g_out, int64_t rows, int C,
+                     const float* mean, const float* rstd, int relu, float* g_z, float* g_beta, float* g_pre,
+                     void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+
+/* ---- tf.train.AdamOptimizer update on a flat buffer: trainval.py:17,80 --------------------
+ * g' = g*grad_scale; m = b1*m+(1-b1)g'; v = b2*v+(1-b2)g'^2; p -= lr_t*m/(sqrt(v)+eps),
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller (epsilon outside the bias correction). */
+int dgcnn_adam_tf_step(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1,
+                       float b2, float eps, float grad_scale, dgcnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGCNN_B200_H_ */
