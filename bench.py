@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py -- points/sec, forward+backward+Adam, of the full DGCNN segmentation model on synthetic clouds.
+
+Workload (BASELINE.json configs[1]): 4 EdgeConv layers + FC head, N=2048, k=20, C=3, 24 clouds per GPU, fp32.
+With --gpus N (launched under torchrun) every rank keeps 24 clouds (weak scaling: global batch 24*N, which at
+N=8 is configs[3]) and the step ends with ONE NCCL all-reduce of the flat gradient buffer.
+
+A "step" = zero_gradients + accum_gradient (fwd+bwd of the rank's 24 clouds) + apply_gradient through the
+reference-facing trainer API (dgcnn.trainval).  Two timings:
+  value : inputs already resident in HBM, no host read inside the loop; CUDA events, max over ranks.
+  e2e   : the same call with pinned HOST inputs (H2D copy every step) and a device->host read of the loss
+          every step.
+roofline    : the fused k_nn launch on the [24,2048,64] feature clouds (dominant hand-written kernel), timed
+              live with CUDA events on the launching stream inside the timed steps.
+cpu_baseline: the oracle (reference-equivalent CPU restatement; TF1 cannot be installed) on a bounded sample.
+--impl reference : that CPU arm alone, with all host threads.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "dynamic-gcnn_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+B_PER_GPU, NPTS, KNN, CH, LAYERS, FILT, FCF, NCLS = 24, 2048, 20, 3, 4, 64, [512, 256], 2
+METRIC = "points/sec fwd+bwd, B=24 N=2048 k=20, at 1/2/4/8 B200; EdgeConv HBM GB/s"
+CPU_SAMPLE_B = 4  # clouds per CPU-baseline step (BN statistics are per micro-batch, cost is linear in clouds)
+
+
+def make_flags(n_gpus):
+    from types import SimpleNamespace
+    return SimpleNamespace(NUM_CLASS=NCLS, MODEL_NAME="dgcnn", TRAIN=True, KVALUE=KNN, DEBUG=False,
+                           EDGE_CONV_LAYERS=LAYERS, EDGE_CONV_FILTERS=FILT, FC_LAYERS=len(FCF), FC_FILTERS=list(FCF),
+                           LEARNING_RATE=1e-3, GPUS=list(range(n_gpus)), MINIBATCH_SIZE=B_PER_GPU,
+                           NUM_CHANNEL=CH, WEIGHT_KEY="", SEED=0, BATCH_SIZE=B_PER_GPU * n_gpus, NUM_POINT=NPTS)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons DURING the timed region (pynvml; nvidia-smi's clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_baseline_run(steps, warmup):
+    """Reference-equivalent CPU restatement (oracle) timed on the host cores: TF-literal graph (materialised
+    [B,N,N] distances, top_k, gathered edge tensor, 1x1 convs as matmuls, train-mode BN, autograd backward)."""
+    from oracle import dgcnn_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fl = O.make_flags(EDGE_CONV_LAYERS=LAYERS, EDGE_CONV_FILTERS=FILT, KVALUE=KNN, FC_FILTERS=list(FCF), NUM_CLASS=NCLS,
+                      TRAIN=True)
+    P = O.init_params(fl, CH, seed=0)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand((CPU_SAMPLE_B, NPTS, CH), generator=g)
+    y = torch.randint(0, NCLS, (CPU_SAMPLE_B, NPTS), generator=g)
+    for _ in range(warmup):
+        O.train_step_reference(x, y, fl, P)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.train_step_reference(x, y, fl, P)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"value": CPU_SAMPLE_B * NPTS / dt, "unit": "points/s", "cores": cores, "kind": "port",
+            "sample": "%d of %d clouds per step (N=%d k=%d L=%d, fwd+bwd, no optimizer), %d steps after %d warm-up; "
+                      "torch-CPU restatement of the TF1 graph (TF1 not installable)" % (CPU_SAMPLE_B, B_PER_GPU, NPTS,
+                                                                                       KNN, LAYERS, steps, warmup),
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline_run(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "points/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": "configs[1]: full DGCNN seg, 4 EdgeConv + FC(512,256) head, N=2048 k=20 C=3, 24 clouds per GPU, "
+                        "fwd+bwd+Adam" + ("" if n == 1 else "; %d GPUs = global batch %d, one NCCL grad all-reduce" %
+                                          (n, n * B_PER_GPU)),
+            "clouds_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * n, "points": NPTS, "k": KNN, "channels": CH,
+            "edge_conv_layers": LAYERS, "parallelism": "dp%d" % n,
+            "l2": "no explicit flush: one step streams >2 GB of activations per GPU, far beyond the 126 MB L2"}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import dgcnn
+    from dgcnn import _native, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs CUDA (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, "--gpus %d but WORLD_SIZE=%d (launch with torchrun)" % (args.gpus, world)
+
+    fl = make_flags(world)
+    tr = dgcnn.trainval(fl)
+    tr.initialize()
+    tower = tr._towers[0]
+
+    # synthetic inputs: a small ring of distinct batches, pinned on the host and mirrored on the device
+    g = torch.Generator().manual_seed(1234 + rank)
+    ring = 4
+    h_pts = [torch.rand((B_PER_GPU, NPTS, CH), generator=g).pin_memory() for _ in range(ring)]
+    h_lab = [torch.randint(0, NCLS, (B_PER_GPU, NPTS), generator=g, dtype=torch.int64).pin_memory() for _ in range(ring)]
+    d_pts = [t.to(dev) for t in h_pts]
+    d_lab = [t.to(dev) for t in h_lab]
+
+    def feed(lst, i):
+        out = [None] * world
+        out[tower] = lst[i % ring]
+        return out
+
+    def step(i, host):
+        tr.zero_gradients(None)
+        res = tr.accum_gradient(None, feed(h_pts if host else d_pts, i), feed(h_lab if host else d_lab, i), sync=host)
+        tr.apply_gradient(None)
+        return res[2]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(host, steps, with_events=False):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        n0 = _native.launch_count()
+        if with_events:
+            ops._knn_events = []
+        e0.record()
+        for i in range(steps):
+            step(i, host)
+        e1.record()
+        barrier()
+        ev, ops._knn_events = ops._knn_events, None
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), _native.launch_count() - n0, ev
+
+    for i in range(args.warmup):
+        step(i, False)
+    for i in range(min(args.warmup, 3)):
+        step(i, True)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, launches, ev = timed(False, args.steps, with_events=True)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    ms_e2e, _, _ = timed(True, args.steps)
+
+    pts_per_step = B_PER_GPU * NPTS * world
+    value = pts_per_step * args.steps / (ms_dev * 1e-3)
+    e2e = pts_per_step * args.steps / (ms_e2e * 1e-3)
+
+    # roofline of the dominant hand-written kernel: fused k_nn on 64-channel features
+    pk, pk_kind = peaks()
+    knn64 = [a.elapsed_time(b) for (_, _, c, _, a, b) in ev if c == 64]
+    knn3 = [a.elapsed_time(b) for (_, _, c, _, a, b) in ev if c == CH]
+    roof = None
+    if knn64:
+        t_ms = float(np.mean(knn64))
+        flops = 2.0 * B_PER_GPU * NPTS * NPTS * 64          # 12.88 GF per layer
+        unfused_bytes = 821.9e6                              # K1 415.3 MB + K2 406.6 MB if the matrix hit HBM
+        ach = flops / (t_ms * 1e-3) / 1e12
+        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        roof = {"kernel": "knn_tile_kernel (dgcnn_knn, C=64 layers)", "bound": "tensor", "achieved": ach, "peak": peak,
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": pk_kind + " bf16 sustained",
+                "ms_per_launch": t_ms, "launches_timed": len(knn64),
+                "effective_unfused_hbm_gbs": unfused_bytes / (t_ms * 1e-3) / 1e9,
+                "note": "fp32 SIMT formulation (bit-exact kNN); compulsory HBM traffic is only 16.5 MB, so the "
+                        "kernel is compute-bound and is reported against the tensor roof",
+                "knn_c3_ms_per_launch": float(np.mean(knn3)) if knn3 else None,
+                "knn_share_of_step": (sum(knn64) + sum(knn3)) / ms_dev}
+
+    if rank == 0:
+        cb = cpu_baseline_run(3, 1) if world == 1 else None
+        line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+                "e2e": {"value": e2e, "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": int(h_pts[0].numel() * 4 + h_lab[0].numel() * 8),
+                        "d2h_bytes_per_step": 8},
+                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}
+        if cb is not None:
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

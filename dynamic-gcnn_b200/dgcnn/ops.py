@@ -27,6 +27,23 @@ BN_EPS = 1e-3
 CONV1_WIDTH = 64  # ops.py:63
 
 
+# test hooks (never set by the product): _knn_trace collects each layer's kNN indices; _knn_forced supplies them
+_knn_trace = None
+_knn_forced = None
+# bench.py hook: when a list, k_nn() brackets its C-ABI call with CUDA events on the launching stream
+_knn_events = None
+
+
+def _layer_knn(x, k):
+    if _knn_forced is not None:
+        idx = next(_knn_forced).to(x.device, torch.int32).contiguous()
+    else:
+        idx = k_nn(x, k)
+    if _knn_trace is not None:
+        _knn_trace.append(idx)
+    return idx
+
+
 # =============================================================================== raw kernels
 def k_nn(points: torch.Tensor, k: int) -> torch.Tensor:
     """ops.py:8-19.  Fused distance + top-k; the [B,N,N] matrix is never written.  Not differentiable
@@ -40,8 +57,15 @@ def k_nn(points: torch.Tensor, k: int) -> torch.Tensor:
     need = L.dgcnn_knn_workspace_bytes(B, N, C)
     ws = nv.workspace(x.device, need, "knn")
     idx = torch.empty((B, N, k), dtype=torch.int32, device=x.device)
+    ev = None
+    if _knn_events is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     nv.check(L.dgcnn_knn(x.data_ptr(), idx.data_ptr(), B, N, C, k, ws.data_ptr(), ws.numel(),
                          nv.stream_ptr(x.device)), "k_nn")
+    if ev is not None:
+        ev[1].record()
+        _knn_events.append((B, N, C, k, ev[0], ev[1]))
     return idx
 
 
@@ -274,13 +298,13 @@ def edge_conv(point_cloud, k, num_filters, trainable, activation=relu, debug=Fal
     B, N, C = x.shape
     k = int(k)
     F = int(num_filters)
-    idx = k_nn(x, k)                                                            # ops.py:23
-    _dbg(debug, torch.empty(B, N, k, 2 * C, device="meta"), _cur_scope() + "/edges (never materialised)")
+    idx = _layer_knn(x, k)                                                      # ops.py:23
+    if debug: _dbg(debug, torch.empty(B, N, k, 2 * C, device="meta"), _cur_scope() + "/edges (never materialised)")
     w0, b0 = _conv_bn_vars("conv0", 2 * C, F, trainable, x.device)              # ops.py:47-54
     wp = torch.cat([w0[:C] - w0[C:], w0[C:]], dim=1)                            # [C, 2F] = [Wa-Wb | Wb]
     uv = _Conv1x1.apply(x.reshape(B * N, C), wp)
     net_max, net_mean = _EdgeConvGather.apply(uv, idx, b0, B, N, k)             # ops.py:53-57
-    _dbg(debug, torch.empty(B, N, k, F, device="meta"), _cur_scope() + "/conv0 (never materialised)")
+    if debug: _dbg(debug, torch.empty(B, N, k, F, device="meta"), _cur_scope() + "/conv0 (never materialised)")
     net = torch.cat([net_max, net_mean], dim=-1)                                # ops.py:58
     _dbg(debug, net_max.view(B, N, 1, F), _cur_scope() + "/Max")
     _dbg(debug, net_mean.view(B, N, 1, F), _cur_scope() + "/Mean")

@@ -373,4 +373,4 @@ def train_step_reference(points, labels, flags, P, weight=None, dropout_mask=Non
             k_nn = saved
     _, acc, loss = softmax_loss_accuracy(logits, labels, weight)
     loss.backward()
-    return float(loss), float(acc), {n: t.grad for n, t in P.items()}
+    return loss.item(), acc.item(), {n: t.grad for n, t in P.items()}

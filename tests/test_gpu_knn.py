@@ -1,0 +1,113 @@
+"""GPU parity of the k_nn hot path (dgcnn_knn / dgcnn_pairwise_distance / dgcnn_topk_rows through the C ABI)
+against the oracle: BIT-EXACT indices and distances, including tie order, ragged N, k edge cases."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp_knn(dg, oracle, x, k):
+    got = dg.ops.k_nn(torch.from_numpy(x).cuda(), k).cpu().numpy()
+    ref = oracle.k_nn(x, k).numpy()
+    assert got.dtype == np.int32 and got.shape == ref.shape
+    bad = (got != ref).sum()
+    assert bad == 0, "%d / %d indices differ" % (bad, ref.size)
+
+
+@pytest.mark.parametrize("B,N,C,k", [
+    (2, 512, 3, 20),      # BASELINE configs[0]
+    (3, 100, 3, 20),      # ragged: N not a multiple of the 64-row / 128-column tiles
+    (2, 129, 4, 16),
+    (1, 1, 3, 1),         # single point
+    (2, 64, 64, 64),      # k == N == tile edge, two list registers per lane
+    (2, 300, 64, 40),     # production k (scripts/lsf/train_dgcnn.sh:28)
+    (1, 257, 17, 33),     # odd channel count across the 16-channel stage boundary
+    (2, 200, 130, 7),     # many channel stages
+    (1, 70, 5, 70),       # k == N, ragged
+])
+def test_knn_random_bit_exact(dg, oracle, cuda, B, N, C, k):
+    rng = np.random.RandomState(B * 1000 + N + C + k)
+    _cmp_knn(dg, oracle, rng.rand(B, N, C).astype(np.float32), k)
+    _cmp_knn(dg, oracle, rng.randn(B, N, C).astype(np.float32) * 3.0, k)
+
+
+def test_knn_lattice_ties_bit_exact(dg, oracle, cuda):
+    rng = np.random.RandomState(0)
+    for hi, N, k in ((6, 400, 20), (768, 1024, 20), (3, 333, 40)):
+        x = rng.randint(0, hi, size=(2, N, 3)).astype(np.float32)   # voxel lattice: ties everywhere
+        _cmp_knn(dg, oracle, x, k)
+        got = dg.ops.k_nn(torch.from_numpy(x).cuda(), k).cpu().numpy()
+        d = ((x[:, :, None, :].astype(np.int64) - x[:, None, :, :].astype(np.int64)) ** 2).sum(-1)
+        assert np.array_equal(got, np.argsort(d, axis=-1, kind="stable")[:, :, :k])   # analytic answer
+
+
+def test_knn_duplicates_and_hand_cases(dg, oracle, cuda):
+    x = np.zeros((1, 6, 3), np.float32)
+    x[0, 3:] = 1.0
+    assert dg.ops.k_nn(torch.from_numpy(x).cuda(), 3).cpu().tolist() == [[[0, 1, 2]] * 3 + [[3, 4, 5]] * 3]
+    line = torch.arange(5, dtype=torch.float32).reshape(1, 5, 1).cuda()
+    assert dg.ops.k_nn(line, 3).cpu().tolist() == [[[0, 1, 2], [1, 0, 2], [2, 1, 3], [3, 2, 4], [4, 3, 2]]]
+    _cmp_knn(dg, oracle, np.zeros((2, 150, 8), np.float32), 20)   # all points identical: pure index order
+
+
+@pytest.mark.parametrize("B,N,C", [(2, 512, 3), (2, 130, 64), (1, 77, 9), (3, 256, 33)])
+def test_pairwise_distance_bit_exact(dg, oracle, cuda, B, N, C):
+    rng = np.random.RandomState(N + C)
+    x = (rng.randn(B, N, C) * 2).astype(np.float32)
+    got = dg.ops.pairwise_distance(torch.from_numpy(x).cuda()).cpu().numpy()
+    ref = oracle.pairwise_distance(x).numpy()
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))   # bit for bit
+    assert np.array_equal(got, np.swapaxes(got, 1, 2))                # symmetric by construction
+
+
+@pytest.mark.parametrize("rows,N,k", [(64, 2048, 20), (10, 64, 64), (33, 129, 40), (7, 5, 1)])
+def test_topk_rows_bit_exact(dg, oracle, cuda, rows, N, k):
+    rng = np.random.RandomState(rows + N)
+    D = rng.rand(rows, N).astype(np.float32)
+    D[:, ::3] = np.round(D[:, ::3] * 8) / 8   # inject exact ties
+    got = dg.ops.knn(torch.from_numpy(D).cuda(), k).cpu().numpy()
+    assert np.array_equal(got, oracle.topk_rows(D, k).numpy())
+    assert np.array_equal(got, np.argsort(D, axis=-1, kind="stable")[:, :k])
+
+
+def test_fused_equals_unfused(dg, cuda):
+    x = torch.rand(2, 777, 16, device=cuda)
+    assert torch.equal(dg.ops.k_nn(x, 24), dg.ops.knn(dg.ops.pairwise_distance(x), 24))
+
+
+def test_knn_error_behaviour(dg, cuda):
+    x = torch.rand(1, 8, 3, device=cuda)
+    with pytest.raises(ValueError):
+        dg.ops.k_nn(x, 9)          # k > N
+    with pytest.raises(ValueError):
+        dg.ops.k_nn(x, 0)
+    with pytest.raises(NotImplementedError):
+        dg.ops.k_nn(torch.rand(1, 128, 3, device=cuda), 65)
+    with pytest.raises(ValueError):
+        dg.ops.k_nn(torch.rand(8, 3, device=cuda), 2)
+    with pytest.raises(TypeError):
+        dg.ops.k_nn(x.double(), 2)
+
+
+def test_knn_full_size_config2(dg, oracle, cuda):
+    """BASELINE configs[1] shape (B=24, N=2048, k=20), both channel counts of the model: whole-tensor equality
+    with the oracle (it finishes in ~1 s at this size) plus size-independent properties."""
+    g = torch.Generator().manual_seed(1234)
+    for C in (3, 64):
+        x = torch.rand((24, 2048, C), generator=g)
+        xc = x.cuda()
+        idx = dg.ops.k_nn(xc, 20)
+        assert torch.equal(idx.cpu(), oracle.k_nn(x, 20))
+        # sortedness of the selected distances, every index in range, no duplicates per row
+        D = dg.ops.pairwise_distance(xc[:2])
+        sel = torch.gather(D, 2, idx[:2].long())
+        assert (sel[:, :, 1:] >= sel[:, :, :-1]).all()
+        assert int(idx.min()) >= 0 and int(idx.max()) < 2048
+        assert (torch.sort(idx, dim=-1).values.diff(dim=-1) > 0).all()
+        # k-th selected distance bounds everything not selected
+        kth = sel[:, :, -1:]
+        mask = torch.ones_like(D, dtype=torch.bool).scatter_(2, idx[:2].long(), False)
+        assert (D[mask].reshape(2, 2048, -1) >= kth).all()
+        # determinism / idempotence
+        assert torch.equal(idx, dg.ops.k_nn(xc, 20))
