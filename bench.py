@@ -188,11 +188,16 @@ def run_ours(args):
         n0 = _native.launch_count()
         if with_events:
             ops._knn_events = []
+        prof = with_events and os.environ.get("DGCNN_PROFILE") == "1"   # ncu --profile-from-start off
+        if prof:
+            torch.cuda.profiler.start()
         e0.record()
         for i in range(steps):
             step(i, host)
         e1.record()
         barrier()
+        if prof:
+            torch.cuda.profiler.stop()
         ev, ops._knn_events = ops._knn_events, None
         ms = e0.elapsed_time(e1)
         t = torch.tensor([ms], device=dev)

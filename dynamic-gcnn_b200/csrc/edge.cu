@@ -109,35 +109,49 @@ __global__ void __launch_bounds__(EC_THREADS)
   }
 }
 
-// partial [nblk][2][C] -> mean, rstd (double, fixed order => deterministic)
-__global__ void finalize_stats_kernel(const float* __restrict__ partial, int nblk, int C, double count, float eps,
-                                      float* __restrict__ mean, float* __restrict__ rstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblk; ++b) {
+// partial [nblk][2][C] -> per-channel totals.  One warp per channel: lane l adds blocks l, l+32, ... in fp64, then a
+// fixed xor-tree across lanes => deterministic for a given grid.
+__device__ __forceinline__ void warp_channel_totals(const float* __restrict__ partial, int nblk, int C, int c,
+                                                    double& s, double& q) {
+  const int lane = threadIdx.x & 31;
+  s = 0.0;
+  q = 0.0;
+  for (int b = lane; b < nblk; b += 32) {
     s += (double)partial[((int64_t)b * 2 + 0) * C + c];
     q += (double)partial[((int64_t)b * 2 + 1) * C + c];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(FULL, s, o);
+    q += __shfl_xor_sync(FULL, q, o);
+  }
+}
+
+__global__ void finalize_stats_kernel(const float* __restrict__ partial, int nblk, int C, double count, float eps,
+                                      float* __restrict__ mean, float* __restrict__ rstd) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s, q;
+  warp_channel_totals(partial, nblk, C, c, s, q);
   const double m = s / count;
   double var = q / count - m * m;
   if (var < 0.0) var = 0.0;
-  mean[c] = (float)m;
-  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if ((threadIdx.x & 31) == 0) {
+    mean[c] = (float)m;
+    rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 
-// partial [nblk][2][C] -> plain sums s1, s2
 __global__ void finalize_sums_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ s1,
                                      float* __restrict__ s2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
-  double a = 0.0, b2 = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    a += (double)partial[((int64_t)b * 2 + 0) * C + c];
-    b2 += (double)partial[((int64_t)b * 2 + 1) * C + c];
+  double a, b2;
+  warp_channel_totals(partial, nblk, C, c, a, b2);
+  if ((threadIdx.x & 31) == 0) {
+    s1[c] = (float)a;
+    s2[c] = (float)b2;
   }
-  s1[c] = (float)a;
-  s2[c] = (float)b2;
 }
 
 // pass 2 forward: out_max, out_mean
@@ -263,13 +277,13 @@ __global__ void zero_vhalf_kernel(float* __restrict__ guv, int64_t P, int F) {
 
 int launch_finalize_stats(const float* partial, int nblk, int C, double count, float eps, float* mean, float* rstd,
                           cudaStream_t st) {
-  finalize_stats_kernel<<<cdiv(C, 128), 128, 0, st>>>(partial, nblk, C, count, eps, mean, rstd);
+  finalize_stats_kernel<<<cdiv(C, 4), 128, 0, st>>>(partial, nblk, C, count, eps, mean, rstd);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("finalize_stats_kernel");
   return DGCNN_OK;
 }
 int launch_finalize_sums(const float* partial, int nblk, int C, float* s1, float* s2, cudaStream_t st) {
-  finalize_sums_kernel<<<cdiv(C, 128), 128, 0, st>>>(partial, nblk, C, s1, s2);
+  finalize_sums_kernel<<<cdiv(C, 4), 128, 0, st>>>(partial, nblk, C, s1, s2);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("finalize_sums_kernel");
   return DGCNN_OK;

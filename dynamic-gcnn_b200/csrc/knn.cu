@@ -35,103 +35,162 @@ __global__ void knn_prep_kernel(const float* __restrict__ x, float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// Warp-resident ascending list of (distance, index) pairs, 32*KS slots: slot p lives in lane p&31,
-// register p>>5.  Order is lexicographic (d, j): equal distances keep the lower index first, which is
-// tf.nn.top_k's tie rule (ops.py:18).  Empty slots hold (+inf, INT_MAX).
+// Per-row selection state, owned by one warp.
+//   * an ascending list of the best 32*KS (distance, index) pairs: slot p lives in lane p&31, register p>>5.
+//     Order is lexicographic (d, j): equal distances keep the lower index first = tf.nn.top_k's tie rule
+//     (ops.py:18).  Empty slots hold (+inf, INT_MAX).
+//   * a 64-entry shared-memory queue of candidates that passed the threshold filter.  Whenever 32 are
+//     queued the warp sorts them with a 32-lane bitonic network and bitonic-merges them into the list
+//     (one ~200-instruction dependent chain per 32 candidates instead of one per candidate).
+// The threshold (td, tj) = list entry k-1 only tightens at drains; stale entries are merely merged and drop off.
+constexpr int QCAP = 64;
+
+__device__ __forceinline__ bool lex_less(float ad, int aj, float bd, int bj) {
+  return (ad < bd) || (ad == bd && aj < bj);
+}
+
+// ascending bitonic sort of one (d, j) pair per lane
+__device__ __forceinline__ void warp_sort32(float& d, int& j, int lane) {
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+    for (int jm = k2 >> 1; jm > 0; jm >>= 1) {
+      const float od = __shfl_xor_sync(FULL, d, jm);
+      const int oj = __shfl_xor_sync(FULL, j, jm);
+      const bool up = (lane & k2) == 0;
+      const bool lower = (lane & jm) == 0;
+      const bool other_less = lex_less(od, oj, d, j);
+      const bool take = (lower == up) ? other_less : !other_less;
+      if (take) {
+        d = od;
+        j = oj;
+      }
+    }
+  }
+}
+
+// d,j hold a bitonic sequence across the 32 lanes -> ascending
+__device__ __forceinline__ void warp_bitonic_merge32(float& d, int& j, int lane) {
+#pragma unroll
+  for (int jm = 16; jm > 0; jm >>= 1) {
+    const float od = __shfl_xor_sync(FULL, d, jm);
+    const int oj = __shfl_xor_sync(FULL, j, jm);
+    const bool lower = (lane & jm) == 0;
+    const bool other_less = lex_less(od, oj, d, j);
+    if (lower ? other_less : !other_less) {
+      d = od;
+      j = oj;
+    }
+  }
+}
+
 template <int KS>
-struct WarpList {
+struct RowSel {
   float d[KS];
   int j[KS];
+  float td;  // admission threshold = entry k-1 of the list
+  int tj;
+  int cnt;   // queued candidates (warp-uniform)
+
   __device__ __forceinline__ void init() {
 #pragma unroll
     for (int s = 0; s < KS; ++s) {
       d[s] = __int_as_float(0x7f800000);
       j[s] = 0x7fffffff;
     }
+    td = __int_as_float(0x7f800000);
+    tj = 0x7fffffff;
+    cnt = 0;
   }
-  // value of the (k-1)-th entry = admission threshold
-  __device__ __forceinline__ void tau(int k, float& td, int& tj) const {
+
+  // merge one candidate per lane (bd, bj; +inf pads) into the list and refresh the threshold
+  __device__ __forceinline__ void merge_batch(float bd, int bj, int k, int lane) {
+    warp_sort32(bd, bj, lane);
+    const float rd = __shfl_sync(FULL, bd, 31 - lane);  // reversed batch
+    const int rj = __shfl_sync(FULL, bj, 31 - lane);
+    if (KS == 1) {
+      if (lex_less(rd, rj, d[0], j[0])) {
+        d[0] = rd;
+        j[0] = rj;
+      }
+      warp_bitonic_merge32(d[0], j[0], lane);
+    } else {
+      // 64 smallest of list(64) U batch(32): C = [L0, min(L1, rev(batch))] is bitonic; merge network over 64
+      if (lex_less(rd, rj, d[KS - 1], j[KS - 1])) {
+        d[KS - 1] = rd;
+        j[KS - 1] = rj;
+      }
+      if (lex_less(d[KS - 1], j[KS - 1], d[0], j[0])) {
+        const float t = d[0];
+        d[0] = d[KS - 1];
+        d[KS - 1] = t;
+        const int u = j[0];
+        j[0] = j[KS - 1];
+        j[KS - 1] = u;
+      }
+      warp_bitonic_merge32(d[0], j[0], lane);
+      warp_bitonic_merge32(d[KS - 1], j[KS - 1], lane);
+    }
     const int src = (k - 1) & 31;
     float a = __shfl_sync(FULL, d[0], src);
-    int bj = __shfl_sync(FULL, j[0], src);
+    int bjj = __shfl_sync(FULL, j[0], src);
     if (KS == 2) {
-      float a1 = __shfl_sync(FULL, d[KS - 1], src);
-      int b1 = __shfl_sync(FULL, j[KS - 1], src);
+      const float a1 = __shfl_sync(FULL, d[KS - 1], src);
+      const int b1 = __shfl_sync(FULL, j[KS - 1], src);
       if (k > 32) {
         a = a1;
-        bj = b1;
+        bjj = b1;
       }
     }
     td = a;
-    tj = bj;
+    tj = bjj;
   }
-  __device__ __forceinline__ void insert(float nd, int nj, int lane) {
-    bool less0 = (d[0] < nd) || (d[0] == nd && j[0] < nj);
-    int rank = __popc(__ballot_sync(FULL, less0));
-    if (KS == 2) {
-      bool less1 = (d[KS - 1] < nd) || (d[KS - 1] == nd && j[KS - 1] < nj);
-      int rank1 = __popc(__ballot_sync(FULL, less1));
-      float u1d = __shfl_up_sync(FULL, d[KS - 1], 1);
-      int u1j = __shfl_up_sync(FULL, j[KS - 1], 1);
-      if (rank < 32) {
-        float cd = __shfl_sync(FULL, d[0], 31);
-        int cj = __shfl_sync(FULL, j[0], 31);
-        if (lane == 0) {
-          d[KS - 1] = cd;
-          j[KS - 1] = cj;
-        } else {
-          d[KS - 1] = u1d;
-          j[KS - 1] = u1j;
-        }
-      } else {
-        if (lane == rank1) {
-          d[KS - 1] = nd;
-          j[KS - 1] = nj;
-        } else if (lane > rank1) {
-          d[KS - 1] = u1d;
-          j[KS - 1] = u1j;
-        }
+
+  // offer 4 candidates per lane; qd/qj = this row's queue (QCAP entries)
+  __device__ __forceinline__ void offer4(const float (&dv)[4], const int (&cj)[4], int N, int k,
+                                         float* __restrict__ qd, int* __restrict__ qj, int lane) {
+    bool p[4];
+    bool anyp = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      p[q] = (cj[q] < N) && lex_less(dv[q], cj[q], td, tj);
+      anyp |= p[q];
+    }
+    if (__ballot_sync(FULL, anyp) == 0) return;
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const unsigned m = __ballot_sync(FULL, p[q]);
+      if (m == 0) continue;  // warp-uniform
+      if (p[q]) {
+        const int pos = cnt + __popc(m & lt);
+        qd[pos] = dv[q];
+        qj[pos] = cj[q];
+      }
+      cnt += __popc(m);
+      if (cnt >= 32) {
+        __syncwarp();
+        cnt -= 32;
+        const float bd = qd[cnt + lane];
+        const int bj = qj[cnt + lane];
+        __syncwarp();
+        merge_batch(bd, bj, k, lane);
       }
     }
-    float u0d = __shfl_up_sync(FULL, d[0], 1);
-    int u0j = __shfl_up_sync(FULL, j[0], 1);
-    if (rank < 32) {
-      if (lane == rank) {
-        d[0] = nd;
-        j[0] = nj;
-      } else if (lane > rank) {
-        d[0] = u0d;
-        j[0] = u0j;
-      }
+  }
+
+  // drain what is left in the queue
+  __device__ __forceinline__ void finish(int k, const float* __restrict__ qd, const int* __restrict__ qj, int lane) {
+    if (cnt > 0) {
+      __syncwarp();
+      const float bd = lane < cnt ? qd[lane] : __int_as_float(0x7f800000);
+      const int bj = lane < cnt ? qj[lane] : 0x7fffffff;
+      cnt = 0;
+      __syncwarp();
+      merge_batch(bd, bj, k, lane);
     }
   }
 };
-
-// Offer 4 candidates per lane (dv[q], column cj[q]) to the list; td/tj = running threshold.
-template <int KS>
-__device__ __forceinline__ void warp_offer4(WarpList<KS>& L, const float (&dv)[4], const int (&cj)[4], int N,
-                                            int k, float& td, int& tj, int lane) {
-  unsigned pend = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    bool p = (cj[q] < N) && (dv[q] < td || (dv[q] == td && cj[q] < tj));
-    pend |= (p ? 1u : 0u) << q;
-  }
-  unsigned any = __ballot_sync(FULL, pend != 0);
-  while (any) {
-    const int src = __ffs(any) - 1;
-    float cd = (pend & 1u) ? dv[0] : (pend & 2u) ? dv[1] : (pend & 4u) ? dv[2] : dv[3];
-    int cc = (pend & 1u) ? cj[0] : (pend & 2u) ? cj[1] : (pend & 4u) ? cj[2] : cj[3];
-    const float nd = __shfl_sync(FULL, cd, src);
-    const int nj = __shfl_sync(FULL, cc, src);
-    if (lane == src) pend &= pend - 1;
-    if (nd < td || (nd == td && nj < tj)) {  // warp-uniform
-      L.insert(nd, nj, lane);
-      L.tau(k, td, tj);
-    }
-    any = __ballot_sync(FULL, pend != 0);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Tiled distance kernel.  CTA = 64 query rows of one cloud x all candidate columns, streamed in
@@ -146,6 +205,9 @@ __global__ void __launch_bounds__(KNN_THREADS, 2)
   __shared__ __align__(16) float Bs[2][CK][TN];
   __shared__ __align__(16) float sBs[2][TN];
   __shared__ float sAs[TM];
+  extern __shared__ __align__(16) unsigned char knn_dyn_smem[];  // candidate queues (selection variant only)
+  float* qd_all = reinterpret_cast<float*>(knn_dyn_smem);           // [TM][QCAP]
+  int* qj_all = reinterpret_cast<int*>(knn_dyn_smem) + TM * QCAP;   // [TM][QCAP]
 
   const int b = blockIdx.y;
   const int r0 = blockIdx.x * TM;
@@ -173,16 +235,10 @@ __global__ void __launch_bounds__(KNN_THREADS, 2)
     if (q == 0 && tid < TN / 4) cp_async16(&sBs[t & 1][tid * 4], sb + t * TN + tid * 4);
   };
 
-  WarpList<KS> L[8];
-  float tau_d[8];
-  int tau_j[8];
+  RowSel<KS> R[8];
   if (!WRITE_D) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      L[r].init();
-      tau_d[r] = __int_as_float(0x7f800000);
-      tau_j[r] = 0x7fffffff;
-    }
+    for (int r = 0; r < 8; ++r) R[r].init();
   }
 
   float acc[8][4];
@@ -238,7 +294,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 2)
             }
           }
         } else {
-          warp_offer4<KS>(L[r], dv, cj, N, k, tau_d[r], tau_j[r], lane);
+          R[r].offer4(dv, cj, N, k, qd_all + (warp * 8 + r) * QCAP, qj_all + (warp * 8 + r) * QCAP, lane);
         }
       }
     }
@@ -247,13 +303,14 @@ __global__ void __launch_bounds__(KNN_THREADS, 2)
   if (!WRITE_D) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
+      R[r].finish(k, qd_all + (warp * 8 + r) * QCAP, qj_all + (warp * 8 + r) * QCAP, lane);
       const int row = r0 + warp * 8 + r;
       if (row < N) {
         int32_t* o = idx + ((size_t)b * N + row) * k;
 #pragma unroll
         for (int sl = 0; sl < KS; ++sl) {
           const int pos = sl * 32 + lane;
-          if (pos < k) o[pos] = L[r].j[sl];
+          if (pos < k) o[pos] = R[r].j[sl];
         }
       }
     }
@@ -265,14 +322,14 @@ __global__ void __launch_bounds__(KNN_THREADS, 2)
 template <int KS>
 __global__ void __launch_bounds__(256) topk_rows_kernel(const float* __restrict__ D, int64_t rows, int N, int k,
                                                         int32_t* __restrict__ idx) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ float qd_s[8][QCAP];
+  __shared__ int qj_s[8][QCAP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
   const float* dr = D + row * (int64_t)N;
-  WarpList<KS> L;
-  L.init();
-  float td = __int_as_float(0x7f800000);
-  int tj = 0x7fffffff;
+  RowSel<KS> R;
+  R.init();
   for (int c0 = 0; c0 < N; c0 += 128) {
     float dv[4];
     int cj[4];
@@ -281,15 +338,18 @@ __global__ void __launch_bounds__(256) topk_rows_kernel(const float* __restrict_
       cj[q] = c0 + q * 32 + lane;
       dv[q] = (cj[q] < N) ? __fadd_rn(__ldg(dr + cj[q]), 0.0f) : 0.0f;
     }
-    warp_offer4<KS>(L, dv, cj, N, k, td, tj, lane);
+    R.offer4(dv, cj, N, k, qd_s[warp], qj_s[warp], lane);
   }
+  R.finish(k, qd_s[warp], qj_s[warp], lane);
   int32_t* o = idx + row * (int64_t)k;
 #pragma unroll
   for (int sl = 0; sl < KS; ++sl) {
     const int pos = sl * 32 + lane;
-    if (pos < k) o[pos] = L.j[sl];
+    if (pos < k) o[pos] = R.j[sl];
   }
 }
+
+constexpr size_t KNN_QUEUE_BYTES = (size_t)TM * QCAP * (sizeof(float) + sizeof(int));
 
 static inline int npad_of(int N) { return ((N + TN - 1) / TN) * TN; }
 
@@ -348,10 +408,16 @@ extern "C" int dgcnn_knn(const float* x, int32_t* idx, int B, int N, int C, int 
   int rc = knn_common(x, B, N, C, ws, ws_bytes, st, &xT, &s, &Npad);
   if (rc) return rc;
   dim3 g(cdiv(N, TM), B);
+  static bool attr_done = false;  // raise the dynamic-smem cap once (idempotent, benign if raced)
+  if (!attr_done) {
+    cudaFuncSetAttribute(knn_tile_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_QUEUE_BYTES);
+    cudaFuncSetAttribute(knn_tile_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_QUEUE_BYTES);
+    attr_done = true;
+  }
   if (k <= 32)
-    knn_tile_kernel<1, false><<<g, KNN_THREADS, 0, st>>>(xT, s, N, Npad, C, k, idx, nullptr);
+    knn_tile_kernel<1, false><<<g, KNN_THREADS, KNN_QUEUE_BYTES, st>>>(xT, s, N, Npad, C, k, idx, nullptr);
   else
-    knn_tile_kernel<2, false><<<g, KNN_THREADS, 0, st>>>(xT, s, N, Npad, C, k, idx, nullptr);
+    knn_tile_kernel<2, false><<<g, KNN_THREADS, KNN_QUEUE_BYTES, st>>>(xT, s, N, Npad, C, k, idx, nullptr);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("knn_tile_kernel");
   return DGCNN_OK;
