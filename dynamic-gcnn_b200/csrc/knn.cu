@@ -193,21 +193,116 @@ struct RowSel {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Shared-memory selection state of the tile kernel (one row = one warp-owned record):
+//   queue  [TM][TQ]      candidates that passed the filter, (d, j) split in two planes
+//   list   [TM][32*KS]   ascending best-so-far list
+//   tau    [TM]          admission threshold (list entry k-1), count [TM] queued candidates
+//   dst    [TM][TN]      the tile's distances, staged so that the per-row selection loop can index rows
+//                        dynamically (each lane reads back exactly the float4 it wrote: conflict-free)
+// Keeping this state out of registers lets the drain (sort + merge, ~200 instructions) exist ONCE in the
+// instruction stream: a first version that kept the lists in registers had to unroll it per row and ran
+// instruction-cache bound (ncu: stall_no_instruction 7 of 14.9 cycles per issue).
+constexpr int TQ = 64;  // 31 left over + 32 appended per ballot
+
+template <int KS>
+struct KnnSel {
+  float* qd;
+  int* qj;
+  float* ld;
+  int* lj;
+  float* taud;
+  int* tauj;
+  int* qcnt;
+  float4* dst;
+  static constexpr int LW = 32 * KS;
+  static constexpr size_t bytes() { return (size_t)TM * (TN * 4 + TQ * 8 + LW * 8 + 12); }
+  __device__ __forceinline__ void carve(unsigned char* base) {
+    dst = reinterpret_cast<float4*>(base);
+    qd = reinterpret_cast<float*>(base + (size_t)TM * TN * 4);
+    qj = reinterpret_cast<int*>(qd + TM * TQ);
+    ld = reinterpret_cast<float*>(qj + TM * TQ);
+    lj = reinterpret_cast<int*>(ld + TM * LW);
+    taud = reinterpret_cast<float*>(lj + TM * LW);
+    tauj = reinterpret_cast<int*>(taud + TM);
+    qcnt = tauj + TM;
+  }
+  __device__ __forceinline__ void init_row(int row, int lane) {
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      ld[row * LW + s * 32 + lane] = __int_as_float(0x7f800000);
+      lj[row * LW + s * 32 + lane] = 0x7fffffff;
+    }
+    if (lane == 0) {
+      taud[row] = __int_as_float(0x7f800000);
+      tauj[row] = 0x7fffffff;
+      qcnt[row] = 0;
+    }
+  }
+  // merge queue entries [base, base+n) (n <= 32) of `row` into its list; refresh tau
+  __device__ __noinline__ void drain(int row, int base, int n, int k, int lane) {
+    RowSel<KS> R;
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      R.d[s] = ld[row * LW + s * 32 + lane];
+      R.j[s] = lj[row * LW + s * 32 + lane];
+    }
+    const float bd = lane < n ? qd[row * TQ + base + lane] : __int_as_float(0x7f800000);
+    const int bj = lane < n ? qj[row * TQ + base + lane] : 0x7fffffff;
+    R.merge_batch(bd, bj, k, lane);
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      ld[row * LW + s * 32 + lane] = R.d[s];
+      lj[row * LW + s * 32 + lane] = R.j[s];
+    }
+    // the hint bound (if any) stays in force until the list itself holds k entries below it
+    const float otd = taud[row];
+    const int otj = tauj[row];
+    __syncwarp();
+    if (lane == 0 && lex_less(R.td, R.tj, otd, otj)) {
+      taud[row] = R.td;
+      tauj[row] = R.tj;
+    }
+  }
+  // Warm start: distances from `row` to k distinct hinted columns bound the k-th smallest distance from above.
+  // Same operation order as the tile loop, so the hinted columns themselves always pass the filter.
+  __device__ __forceinline__ void hint_bound(int rowl, const float* __restrict__ xb, const float* __restrict__ sb,
+                                             const int32_t* __restrict__ hrow, int row, int N, int C, int k, int lane) {
+    float m = -__int_as_float(0x7f800000);
+    const float* xi = xb + (size_t)row * C;
+    const float si = sb[row];
+    for (int h = lane; h < k; h += 32) {
+      int j = hrow[h];
+      j = j < 0 ? 0 : (j >= N ? N - 1 : j);
+      const float* xj = xb + (size_t)j * C;
+      float pacc = 0.0f;
+#pragma unroll 8
+      for (int c = 0; c < C; ++c) pacc = __fmaf_rn(__ldg(xi + c), __ldg(xj + c), pacc);
+      const float dd = __fadd_rn(__fsub_rn(__fadd_rn(si, sb[j]), __fmul_rn(2.0f, pacc)), 0.0f);
+      m = fmaxf(m, dd);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+    if (lane == 0) {
+      taud[rowl] = m;
+      tauj[rowl] = 0x7fffffff;
+    }
+  }
+};
+
 // Tiled distance kernel.  CTA = 64 query rows of one cloud x all candidate columns, streamed in
 // 128-column tiles and 16-channel stages through a 2-deep cp.async ring.  Thread micro-tile:
 // 8 rows (the warp's rows, smem-broadcast) x 4 columns (lane*4..+3).  The same warp that computes a
-// row also selects for it, so selection needs no shared memory and no CTA barrier.
+// row also selects for it, so selection needs no CTA barrier.
 template <int KS, bool WRITE_D>
 __global__ void __launch_bounds__(KNN_THREADS, 2)
-    knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ s, int N, int Npad, int C, int k,
-                    int32_t* __restrict__ idx, float* __restrict__ D) {
+    knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ s, const float* __restrict__ x,
+                    const int32_t* __restrict__ hint, int N, int Npad, int C, int k, int32_t* __restrict__ idx,
+                    float* __restrict__ D) {
   __shared__ __align__(16) float As[2][CK][TM];
   __shared__ __align__(16) float Bs[2][CK][TN];
   __shared__ __align__(16) float sBs[2][TN];
   __shared__ float sAs[TM];
-  extern __shared__ __align__(16) unsigned char knn_dyn_smem[];  // candidate queues (selection variant only)
-  float* qd_all = reinterpret_cast<float*>(knn_dyn_smem);           // [TM][QCAP]
-  int* qj_all = reinterpret_cast<int*>(knn_dyn_smem) + TM * QCAP;   // [TM][QCAP]
+  extern __shared__ __align__(16) unsigned char knn_dyn_smem[];  // selection state (selection variant only)
 
   const int b = blockIdx.y;
   const int r0 = blockIdx.x * TM;
@@ -217,8 +312,26 @@ __global__ void __launch_bounds__(KNN_THREADS, 2)
   const int T = Npad / TN;
   const int Q = (C + CK - 1) / CK;
   const int S = T * Q;
+  const unsigned lt = (1u << lane) - 1u;
 
   if (tid < TM) sAs[tid] = sb[r0 + tid];
+
+  KnnSel<KS> sel;
+  if (!WRITE_D) {
+    sel.carve(knn_dyn_smem);
+#pragma unroll 1
+    for (int r = 0; r < 8; ++r) sel.init_row(warp * 8 + r, lane);
+    __syncwarp();
+    if (hint != nullptr) {
+#pragma unroll 1
+      for (int r = 0; r < 8; ++r) {
+        const int row = r0 + warp * 8 + r;
+        if (row < N)
+          sel.hint_bound(warp * 8 + r, x + (size_t)b * N * C, sb, hint + ((size_t)b * N + row) * k, row, N, C, k, lane);
+      }
+      __syncwarp();
+    }
+  }
 
   auto load_stage = [&](int st) {
     const int t = st / Q, q = st - t * Q, buf = st & 1;
@@ -234,12 +347,6 @@ __global__ void __launch_bounds__(KNN_THREADS, 2)
     }
     if (q == 0 && tid < TN / 4) cp_async16(&sBs[t & 1][tid * 4], sb + t * TN + tid * 4);
   };
-
-  RowSel<KS> R[8];
-  if (!WRITE_D) {
-#pragma unroll
-    for (int r = 0; r < 8; ++r) R[r].init();
-  }
 
   float acc[8][4];
   load_stage(0);
@@ -273,45 +380,93 @@ __global__ void __launch_bounds__(KNN_THREADS, 2)
       const float4 sj4 = *reinterpret_cast<const float4*>(&sBs[t & 1][lane * 4]);
       const float sj[4] = {sj4.x, sj4.y, sj4.z, sj4.w};
       const int col0 = t * TN + lane * 4;
-      const int cj[4] = {col0, col0 + 1, col0 + 2, col0 + 3};
+      // ops.py:16: (s_i + s_j) - 2*p ; +0 canonicalises -0.  acc now holds distances.
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const float si = sAs[warp * 8 + r];
-        float dv[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)  // ops.py:16: (s_i + s_j) - 2*p ; +0 canonicalises -0
-          dv[c] = __fadd_rn(__fsub_rn(__fadd_rn(si, sj[c]), __fmul_rn(2.0f, acc[r][c])), 0.0f);
-        if (WRITE_D) {
+        for (int c = 0; c < 4; ++c)
+          acc[r][c] = __fadd_rn(__fsub_rn(__fadd_rn(si, sj[c]), __fmul_rn(2.0f, acc[r][c])), 0.0f);
+      }
+      if (WRITE_D) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
           const int row = r0 + warp * 8 + r;
           if (row < N) {
             float* drow = D + ((size_t)b * N + row) * N;
             if ((N & 3) == 0 && col0 + 3 < N) {
-              *reinterpret_cast<float4*>(drow + col0) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+              *reinterpret_cast<float4*>(drow + col0) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
             } else {
 #pragma unroll
               for (int c = 0; c < 4; ++c)
-                if (cj[c] < N) drow[cj[c]] = dv[c];
+                if (col0 + c < N) drow[col0 + c] = acc[r][c];
             }
           }
-        } else {
-          R[r].offer4(dv, cj, N, k, qd_all + (warp * 8 + r) * QCAP, qj_all + (warp * 8 + r) * QCAP, lane);
         }
+      } else {
+        if (col0 + 3 >= N) {  // ragged last tile: columns >= N become NaN and fail every comparison
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (col0 + c >= N) acc[r][c] = __int_as_float(0x7fc00000);
+        }
+        // stage the warp's 8x128 distances, then ONE (not unrolled) per-row loop: filter against the row's
+        // threshold, ballot-compacted append to its queue, drain (sort+merge) whenever 32 are queued.
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          sel.dst[(warp * 8 + r) * 32 + lane] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        __syncwarp();
+#pragma unroll 1
+        for (int r = 0; r < 8; ++r) {
+          const int row = warp * 8 + r;
+          const float4 d4 = sel.dst[row * 32 + lane];
+          const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+          float td = sel.taud[row];
+          int tj = sel.tauj[row];
+          // cheap superset test first (one compare per element); the exact (d, j) order only on the rare pass path
+          const bool anyp = (dv[0] <= td) || (dv[1] <= td) || (dv[2] <= td) || (dv[3] <= td);
+          if (__ballot_sync(FULL, anyp) == 0) continue;
+          int cnt = sel.qcnt[row];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int col = col0 + c;
+            const bool p = lex_less(dv[c], col, td, tj);
+            const unsigned m = __ballot_sync(FULL, p);
+            if (m == 0) continue;
+            if (p) {
+              const int pos = cnt + __popc(m & lt);
+              sel.qd[row * TQ + pos] = dv[c];
+              sel.qj[row * TQ + pos] = col;
+            }
+            cnt += __popc(m);
+            if (cnt >= 32) {
+              __syncwarp();
+              cnt -= 32;
+              sel.drain(row, cnt, 32, k, lane);
+              __syncwarp();
+              td = sel.taud[row];
+              tj = sel.tauj[row];
+            }
+          }
+          if (lane == 0) sel.qcnt[row] = cnt;
+        }
+        __syncwarp();
       }
     }
     __syncthreads();
   }
   if (!WRITE_D) {
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < 8; ++r) {
-      R[r].finish(k, qd_all + (warp * 8 + r) * QCAP, qj_all + (warp * 8 + r) * QCAP, lane);
-      const int row = r0 + warp * 8 + r;
+      const int rowl = warp * 8 + r;
+      const int c = sel.qcnt[rowl];
+      if (c > 0) sel.drain(rowl, 0, c, k, lane);
+      __syncwarp();
+      const int row = r0 + rowl;
       if (row < N) {
         int32_t* o = idx + ((size_t)b * N + row) * k;
-#pragma unroll
-        for (int sl = 0; sl < KS; ++sl) {
-          const int pos = sl * 32 + lane;
-          if (pos < k) o[pos] = R[r].j[sl];
-        }
+        for (int pos = lane; pos < k; pos += 32) o[pos] = sel.lj[rowl * KnnSel<KS>::LW + pos];
       }
     }
   }
@@ -349,7 +504,6 @@ __global__ void __launch_bounds__(256) topk_rows_kernel(const float* __restrict_
   }
 }
 
-constexpr size_t KNN_QUEUE_BYTES = (size_t)TM * QCAP * (sizeof(float) + sizeof(int));
 
 static inline int npad_of(int N) { return ((N + TN - 1) / TN) * TN; }
 
@@ -391,7 +545,7 @@ extern "C" int dgcnn_pairwise_distance(const float* x, float* D, int B, int N, i
   int rc = knn_common(x, B, N, C, ws, ws_bytes, st, &xT, &s, &Npad);
   if (rc) return rc;
   dim3 g(cdiv(N, TM), B);
-  knn_tile_kernel<1, true><<<g, KNN_THREADS, 0, st>>>(xT, s, N, Npad, C, 1, nullptr, D);
+  knn_tile_kernel<1, true><<<g, KNN_THREADS, 0, st>>>(xT, s, x, nullptr, N, Npad, C, 1, nullptr, D);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("knn_tile_kernel<D>");
   return DGCNN_OK;
@@ -399,6 +553,11 @@ extern "C" int dgcnn_pairwise_distance(const float* x, float* D, int B, int N, i
 
 extern "C" int dgcnn_knn(const float* x, int32_t* idx, int B, int N, int C, int k, void* ws, size_t ws_bytes,
                          dgcnn_stream_t stream) {
+  return dgcnn_knn_hinted(x, nullptr, idx, B, N, C, k, ws, ws_bytes, stream);
+}
+
+extern "C" int dgcnn_knn_hinted(const float* x, const int32_t* hint, int32_t* idx, int B, int N, int C, int k,
+                                void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DG_REQUIRE(idx, DGCNN_ERR_INVALID, "knn: null output");
   DG_REQUIRE(k >= 1 && k <= N, DGCNN_ERR_INVALID, "knn: need 1 <= k <= N (k=%d, N=%d)", k, N);
@@ -410,14 +569,16 @@ extern "C" int dgcnn_knn(const float* x, int32_t* idx, int B, int N, int C, int 
   dim3 g(cdiv(N, TM), B);
   static bool attr_done = false;  // raise the dynamic-smem cap once (idempotent, benign if raced)
   if (!attr_done) {
-    cudaFuncSetAttribute(knn_tile_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_QUEUE_BYTES);
-    cudaFuncSetAttribute(knn_tile_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_QUEUE_BYTES);
+    cudaFuncSetAttribute(knn_tile_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)KnnSel<1>::bytes());
+    cudaFuncSetAttribute(knn_tile_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)KnnSel<2>::bytes());
     attr_done = true;
   }
   if (k <= 32)
-    knn_tile_kernel<1, false><<<g, KNN_THREADS, KNN_QUEUE_BYTES, st>>>(xT, s, N, Npad, C, k, idx, nullptr);
+    knn_tile_kernel<1, false><<<g, KNN_THREADS, KnnSel<1>::bytes(), st>>>(xT, s, x, hint, N, Npad, C, k, idx, nullptr);
   else
-    knn_tile_kernel<2, false><<<g, KNN_THREADS, KNN_QUEUE_BYTES, st>>>(xT, s, N, Npad, C, k, idx, nullptr);
+    knn_tile_kernel<2, false><<<g, KNN_THREADS, KnnSel<2>::bytes(), st>>>(xT, s, x, hint, N, Npad, C, k, idx, nullptr);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("knn_tile_kernel");
   return DGCNN_OK;

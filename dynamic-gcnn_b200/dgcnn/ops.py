@@ -34,20 +34,23 @@ _knn_forced = None
 _knn_events = None
 
 
-def _layer_knn(x, k):
+def _layer_knn(x, k, hint=None):
     if _knn_forced is not None:
         idx = next(_knn_forced).to(x.device, torch.int32).contiguous()
     else:
-        idx = k_nn(x, k)
+        idx = k_nn(x, k, hint=hint)
     if _knn_trace is not None:
         _knn_trace.append(idx)
     return idx
 
 
 # =============================================================================== raw kernels
-def k_nn(points: torch.Tensor, k: int) -> torch.Tensor:
+def k_nn(points: torch.Tensor, k: int, hint: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ops.py:8-19.  Fused distance + top-k; the [B,N,N] matrix is never written.  Not differentiable
-    (only the indices are used downstream, ops.py:19,34)."""
+    (only the indices are used downstream, ops.py:19,34).
+
+    hint (optional, [B,N,>=k] int32, DISTINCT indices per row -- e.g. the previous layer's result) warm-starts the
+    selection threshold; the result is identical with or without it."""
     x = nv.require_cuda(points.detach(), "points")
     if x.dim() != 3:
         raise ValueError("k_nn: points must be [B,N,C]")
@@ -61,8 +64,12 @@ def k_nn(points: torch.Tensor, k: int) -> torch.Tensor:
     if _knn_events is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-    nv.check(L.dgcnn_knn(x.data_ptr(), idx.data_ptr(), B, N, C, k, ws.data_ptr(), ws.numel(),
-                         nv.stream_ptr(x.device)), "k_nn")
+    hp = 0
+    if hint is not None and hint.shape[-1] >= k and hint.shape[:2] == (B, N):
+        hint = nv.require_cuda(hint if hint.shape[-1] == k else hint[:, :, :k], "hint", torch.int32)
+        hp = hint.data_ptr()
+    nv.check(L.dgcnn_knn_hinted(x.data_ptr(), hp, idx.data_ptr(), B, N, C, k, ws.data_ptr(), ws.numel(),
+                                nv.stream_ptr(x.device)), "k_nn")
     if ev is not None:
         ev[1].record()
         _knn_events.append((B, N, C, k, ev[0], ev[1]))
@@ -285,7 +292,8 @@ def _cur_scope():
 
 
 # =============================================================================== reference API
-def edge_conv(point_cloud, k, num_filters, trainable, activation=relu, debug=False, _residual=None) -> List[torch.Tensor]:
+def edge_conv(point_cloud, k, num_filters, trainable, activation=relu, debug=False, _residual=None,
+              _knn_hint=None, _knn_out=None) -> List[torch.Tensor]:
     """ops.py:42-73 -> [net_max [B,N,1,F], net_mean [B,N,1,F], net [B,N,1,64]].
 
     edges() -> conv0 is evaluated as  [x_i, x_j-x_i].[Wa;Wb] = x_i.(Wa-Wb) + x_j.Wb : one per-point GEMM
@@ -298,7 +306,9 @@ def edge_conv(point_cloud, k, num_filters, trainable, activation=relu, debug=Fal
     B, N, C = x.shape
     k = int(k)
     F = int(num_filters)
-    idx = _layer_knn(x, k)                                                      # ops.py:23
+    idx = _layer_knn(x, k, _knn_hint)                                           # ops.py:23
+    if _knn_out is not None:
+        _knn_out.append(idx)
     if debug: _dbg(debug, torch.empty(B, N, k, 2 * C, device="meta"), _cur_scope() + "/edges (never materialised)")
     w0, b0 = _conv_bn_vars("conv0", 2 * C, F, trainable, x.device)              # ops.py:47-54
     wp = torch.cat([w0[:C] - w0[C:], w0[C:]], dim=1)                            # [C, 2F] = [Wa-Wb | Wb]
@@ -332,9 +342,11 @@ def repeat_edge_conv(point_cloud, repeat, k, num_filters, trainable, debug=False
     num_filters = _listify(num_filters, repeat, "num_filters")
     net = point_cloud
     tensors = []
+    graph = []  # previous layer's neighbour lists warm-start the next layer's selection (same result)
     for i in range(repeat):
         with variable_scope("EdgeConv%d" % i):
-            tensors += edge_conv(net, k[i], num_filters[i], trainable, debug=debug)
+            tensors += edge_conv(net, k[i], num_filters[i], trainable, debug=debug,
+                                 _knn_hint=graph[-1] if graph else None, _knn_out=graph)
             net = tensors[-1].squeeze(-2)
     return tensors
 
@@ -347,10 +359,11 @@ def repeat_residual_edge_conv(point_cloud, repeat, k, num_filters, trainable, de
     net = point_cloud
     tensors = []
     shortcut = None
+    graph = []
     for i in range(repeat):
         with variable_scope("EdgeConv%d" % i):
             if shortcut is None:
-                tensors += edge_conv(net, k[i], num_filters[i], trainable, debug=debug)
+                tensors += edge_conv(net, k[i], num_filters[i], trainable, debug=debug, _knn_out=graph)
             else:
                 if not num_filters[i] == num_filters[i - 1]:            # ops.py:124-133
                     B, N = shortcut.shape[0], shortcut.shape[1]
@@ -362,7 +375,7 @@ def repeat_residual_edge_conv(point_cloud, repeat, k, num_filters, trainable, de
                     shortcut = sc.view(B, N, 1, -1)
                 # conv1 with activation=None, then relu(shortcut + out)  (ops.py:121,134) fused in one epilogue
                 tensors += edge_conv(net, k[i], num_filters[i], trainable, activation=None, debug=debug,
-                                     _residual=shortcut)
+                                     _residual=shortcut, _knn_hint=graph[-1], _knn_out=graph)
             net = tensors[-1]
             shortcut = tensors[-1]
             net = net.squeeze(-2)

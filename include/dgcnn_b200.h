@@ -52,6 +52,13 @@ int dgcnn_pairwise_distance(const float* x, float* D, int B, int N, int C, void*
  * first, self included, equal distances -> lower index first (tf.nn.top_k sorted=True).     */
 int dgcnn_knn(const float* x, int32_t* idx, int B, int N, int C, int k, void* ws, size_t ws_bytes,
               dgcnn_stream_t stream);
+/* Same result as dgcnn_knn, bit for bit, with a warm start: hint [B,N,k] int32 holds, per row, k DISTINCT
+ * in-range column indices (typically the previous EdgeConv layer's neighbours of the same clouds: the reference
+ * recomputes the graph per layer, ops.py:91-96).  Their exact distances bound the k-th smallest from above, so
+ * the threshold filter starts tight instead of at +inf.  hint == NULL is dgcnn_knn.  A hint row with duplicate
+ * indices violates the precondition (the bound would be invalid).                                           */
+int dgcnn_knn_hinted(const float* x, const int32_t* hint, int32_t* idx, int B, int N, int C, int k, void* ws,
+                     size_t ws_bytes, dgcnn_stream_t stream);
 /* ops.py:18 on a materialised matrix: D [rows,N] -> idx [rows,k] (k smallest, same tie rule) */
 int dgcnn_topk_rows(const float* D, int32_t* idx, int64_t rows, int N, int k, dgcnn_stream_t stream);
 

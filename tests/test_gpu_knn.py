@@ -111,3 +111,18 @@ def test_knn_full_size_config2(dg, oracle, cuda):
         assert (D[mask].reshape(2, 2048, -1) >= kth).all()
         # determinism / idempotence
         assert torch.equal(idx, dg.ops.k_nn(xc, 20))
+
+
+def test_knn_hint_never_changes_the_result(dg, oracle, cuda):
+    """dgcnn_knn_hinted: any k distinct in-range indices per row are a valid warm start (good, bad or adversarial)."""
+    rng = np.random.RandomState(5)
+    for B, N, C, k in ((2, 700, 64, 20), (1, 130, 3, 40), (2, 256, 16, 64)):
+        x = torch.from_numpy(rng.randn(B, N, C).astype(np.float32)).cuda()
+        ref = dg.ops.k_nn(x, k)
+        assert torch.equal(ref.cpu(), oracle.k_nn(x.cpu(), k))
+        good = ref                                                           # the answer itself
+        near = dg.ops.k_nn(x + 0.05 * torch.randn_like(x), k)                # a similar graph (previous layer)
+        rnd = torch.stack([torch.stack([torch.randperm(N)[:k] for _ in range(N)]) for _ in range(B)]).int().cuda()
+        far = torch.flip(dg.ops.k_nn(-x, k), dims=[-1])                      # unrelated graph
+        for hint in (good, near, rnd, far):
+            assert torch.equal(dg.ops.k_nn(x, k, hint=hint), ref)
