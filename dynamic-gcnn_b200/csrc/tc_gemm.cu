@@ -1,0 +1,373 @@
+// tcgen05 / TMEM / TMA GEMM with fp32-faithful arithmetic ("bf16x3"):
+//   every fp32 operand x is pre-split into two bf16 planes  hi = bf16(x), lo = bf16(x - hi)   (dgcnn_split_bf16)
+//   C = A.B is accumulated in fp32 TMEM as  hi_a.hi_b + hi_a.lo_b + lo_a.hi_b   (3 tcgen05.mma per k-slice);
+//   the dropped lo.lo term and the lo rounding leave a relative error of ~2^-17 per product, i.e. fp32-class
+//   results (the logits parity bound is 1e-3) at 3/2 of the tensor time of one TF32 pass and 2^-6 of its error.
+// Used for the 1x1 convolutions (slim.conv2d kernel_size=1: /root/reference/dgcnn/ops.py:47-54,62-70,151-160,
+// model.py:65-72) and their gradients.  One kernel covers the three operand layouts that occur, with no
+// transposed copies:   forward  C = X.W      A K-major,  B MN-major (W is [K,N])
+//                      dX       C = g.W^T    A K-major,  B K-major
+//                      dW       C = X^T.g    A MN-major, B MN-major, split over the point dimension
+// Structure (one 128x128 output tile per CTA, 192 threads):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor into a 3-stage ring of 128B-swizzled tiles, mbarrier tx-count
+//   warp 1   : MMA issuer    -- allocates 128 TMEM columns, one elected lane issues tcgen05.mma (M=128,N=128,K=16),
+//                               tcgen05.commit releases ring slots / publishes the accumulator
+//   warps 2-5: epilogue      -- tcgen05.ld 32 lanes x 32 columns, fp32 stores (each warp owns its TMEM sub-partition)
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace dgcnn {
+
+constexpr int GB_M = 128, GB_N = 128, GB_K = 64, G_STAGES = 3, G_THREADS = 192;
+constexpr uint32_t TILE_BYTES = GB_M * GB_K * 2;          // 16 KB: one bf16 plane of one operand tile
+constexpr uint32_t STAGE_BYTES = 4 * TILE_BYTES;          // A_hi, A_lo, B_hi, B_lo
+constexpr size_t G_SMEM = (size_t)G_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 26)) __trap();  // a protocol bug must fail loudly, not hang the GPU
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// 64-bit shared-memory matrix descriptor (sm_100 UMMA): 128B-swizzled tile
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// A_K / B_K: operand is K-major (contraction index contiguous in global memory) or MN-major.
+template <bool A_K, bool B_K>
+__global__ void __launch_bounds__(G_THREADS, 1)
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   float* __restrict__ C, int M, int N, int K, int kblocks_per_split) {
+  extern __shared__ unsigned char g_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)g_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)G_STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + G_STAGES;
+  uint64_t* accum_bar = empty_bar + G_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * GB_M, n0 = blockIdx.y * GB_N;
+  const int kb_total = (K + GB_K - 1) / GB_K;
+  const int kb_begin = blockIdx.z * kblocks_per_split;
+  const int kb_end = min(kb_total, kb_begin + kblocks_per_split);
+  const int nkb = kb_end - kb_begin;
+  float* Cout = C + (size_t)blockIdx.z * M * N;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < G_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: 128 columns x 128 lanes of fp32 accumulator
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && nkb > 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % G_STAGES;
+        const uint32_t ph = (i / G_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        unsigned char* st = smem + (size_t)s * STAGE_BYTES;
+        const int k0 = (kb_begin + i) * GB_K;
+#pragma unroll
+        for (int plane = 0; plane < 2; ++plane) {
+          unsigned char* a_dst = st + plane * TILE_BYTES;
+          unsigned char* b_dst = st + (2 + plane) * TILE_BYTES;
+          if (A_K) {
+            tma_load_3d(a_dst, &tmA, k0, m0, plane, &full_bar[s]);               // box {64 k, 128 m}
+          } else {
+            tma_load_3d(a_dst, &tmA, m0, k0, plane, &full_bar[s]);               // box {64 m, 64 k} x 2
+            tma_load_3d(a_dst + TILE_BYTES / 2, &tmA, m0 + 64, k0, plane, &full_bar[s]);
+          }
+          if (B_K) {
+            tma_load_3d(b_dst, &tmB, k0, n0, plane, &full_bar[s]);
+          } else {
+            tma_load_3d(b_dst, &tmB, n0, k0, plane, &full_bar[s]);
+            tma_load_3d(b_dst + TILE_BYTES / 2, &tmB, n0 + 64, k0, plane, &full_bar[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_K ? 0u : 1u) << 15) | ((B_K ? 0u : 1u) << 16) |
+                           ((uint32_t)(GB_N >> 3) << 17) | ((uint32_t)(GB_M >> 4) << 24);
+    // K-major SW128: 8-row groups 1024 B apart, +32 B per 16-element k-slice
+    // MN-major SW128: 64-wide MN atoms 8192 B apart (LBO), 8-k groups 1024 B apart (SBO), +2048 B per k-slice
+    const uint32_t a_lbo = A_K ? 16u : 8192u, b_lbo = B_K ? 16u : 8192u;
+    const uint32_t a_step = A_K ? 32u : 2048u, b_step = B_K ? 32u : 2048u;
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % G_STAGES;
+      const uint32_t ph = (i / G_STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t a_hi = st, a_lo = st + TILE_BYTES, b_hi = st + 2 * TILE_BYTES, b_lo = st + 3 * TILE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < GB_K / 16; ++ks) {
+          const uint64_t dah = umma_desc(a_hi + ks * a_step, a_lbo, 1024);
+          const uint64_t dal = umma_desc(a_lo + ks * a_step, a_lbo, 1024);
+          const uint64_t dbh = umma_desc(b_hi + ks * b_step, b_lbo, 1024);
+          const uint64_t dbl = umma_desc(b_lo + ks * b_step, b_lbo, 1024);
+          umma_bf16(tmem_base, dal, dbh, idesc, (i | ks) != 0);   // small terms first
+          umma_bf16(tmem_base, dah, dbl, idesc, 1);
+          umma_bf16(tmem_base, dah, dbh, idesc, 1);
+        }
+        umma_commit(&empty_bar[s]);                       // ring slot free once these MMAs retire
+        if (i == nkb - 1) umma_commit(accum_bar);        // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue warps 2..5 -> TMEM sub-partitions (warp % 4)
+    const int sub = warp & 3;
+    const int row = m0 + sub * 32 + lane;
+    if (nkb > 0) {
+      mbar_wait(accum_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+#pragma unroll 1
+    for (int ch = 0; ch < GB_N / 32; ++ch) {
+      uint32_t v[32];
+      if (nkb > 0) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(ch * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
+      if (row < M) {
+        const int c0 = n0 + ch * 32;
+        float* o = Cout + (size_t)row * N + c0;
+        if ((N & 3) == 0 && c0 + 31 < N) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(o + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                                            __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < N) o[i] = __uint_as_float(v[i]);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+// fp32 [n] -> bf16 planes hi[n], lo[n] (plane stride = plane_elems)
+__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ planes, int64_t n,
+                                  int64_t plane_elems) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  if (i4 + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i4);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __float2bfloat16_rn(f[j]);
+      l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+    }
+    *reinterpret_cast<uint2*>(planes + i4) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(planes + plane_elems + i4) = *reinterpret_cast<uint2*>(l);
+  } else {
+    for (int64_t i = i4; i < n; ++i) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(x[i]);
+      planes[i] = h;
+      planes[plane_elems + i] = __float2bfloat16_rn(x[i] - __bfloat162float(h));
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;  // immutable after first successful lookup
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// planes: bf16 [2][rows][cols] row-major.  kmajor: box {64 cols(k), 128 rows};  mn-major: box {64 cols(mn), 64 rows(k)}
+static int make_map(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, bool kmajor) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_err(DGCNN_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * (cuuint64_t)cols * 2};
+  cuuint32_t box[3] = {64, kmajor ? 128u : 64u, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(planes), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(DGCNN_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return DGCNN_OK;
+}
+
+static int tc_splits(int M, int N, int K) {
+  const int64_t tiles = (int64_t)cdiv(M, GB_M) * cdiv(N, GB_N);
+  const int kb = cdiv(K, GB_K);
+  const int sms = num_sms();
+  if (tiles >= sms || kb < 16) return 1;
+  int s = (int)((sms + tiles - 1) / tiles);
+  if (s > kb / 8) s = kb / 8;
+  return s < 1 ? 1 : s;
+}
+
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ C, int64_t MN, int splits) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= MN) return;
+  float s = 0.0f;
+  for (int z = 0; z < splits; ++z) s += part[(size_t)z * MN + i];
+  C[i] = s;
+}
+
+}  // namespace dgcnn
+
+using namespace dgcnn;
+
+extern "C" int dgcnn_split_bf16(const float* x, void* planes, int64_t n, dgcnn_stream_t stream) {
+  DG_REQUIRE(x && planes, DGCNN_ERR_INVALID, "split_bf16: null pointer");
+  DG_REQUIRE(n > 0 && (n & 7) == 0, DGCNN_ERR_INVALID, "split_bf16: n=%lld must be a positive multiple of 8", (long long)n);
+  DG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)planes & 15) == 0, DGCNN_ERR_INVALID, "split_bf16: alignment");
+  const int64_t blocks = (n / 4 + 255) / 256;
+  split_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)planes, n, n);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("split_bf16_kernel");
+  return DGCNN_OK;
+}
+
+extern "C" size_t dgcnn_tc_gemm_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const int s = tc_splits(M, N, K);
+  return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
+}
+
+extern "C" int dgcnn_tc_gemm(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
+                             int transB, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_REQUIRE(a_planes && b_planes && C, DGCNN_ERR_INVALID, "tc_gemm: null pointer");
+  DG_REQUIRE(M > 0 && N > 0 && K > 0, DGCNN_ERR_INVALID, "tc_gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  DG_REQUIRE((M & 7) == 0 && (N & 7) == 0 && (K & 7) == 0, DGCNN_ERR_UNSUPPORTED,
+             "tc_gemm: M, N, K must be multiples of 8 (TMA row pitch), got %d %d %d", M, N, K);
+  DG_REQUIRE(((uintptr_t)a_planes & 15) == 0 && ((uintptr_t)b_planes & 15) == 0 && ((uintptr_t)C & 15) == 0,
+             DGCNN_ERR_INVALID, "tc_gemm: buffers must be 16-byte aligned");
+  // op(A) is [M,K]: stored [M,K] (K-major) or, transA, [K,M] (MN-major).  op(B) is [K,N]: stored [K,N] (MN-major) or,
+  // transB, [N,K] (K-major).
+  const bool a_k = !transA, b_k = transB != 0;
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, a_planes, a_k ? M : K, a_k ? K : M, a_k);
+  if (rc) return rc;
+  rc = make_map(&tmB, b_planes, b_k ? N : K, b_k ? K : N, b_k);
+  if (rc) return rc;
+  const int splits = tc_splits(M, N, K);
+  float* out = C;
+  if (splits > 1) {
+    const size_t need = (size_t)splits * M * N * sizeof(float);
+    DG_REQUIRE(ws && ws_bytes >= need, DGCNN_ERR_WORKSPACE, "tc_gemm: workspace %zu < %zu bytes", ws_bytes, need);
+    out = reinterpret_cast<float*>(ws);
+  }
+  const int kb = cdiv(K, GB_K);
+  const int kper = cdiv(kb, splits);
+  dim3 grid(cdiv(M, GB_M), cdiv(N, GB_N), splits);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+    cudaFuncSetAttribute(tc_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+    cudaFuncSetAttribute(tc_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+    cudaFuncSetAttribute(tc_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
+    attr_done = true;
+  }
+  if (a_k && b_k)
+    tc_gemm_kernel<true, true><<<grid, G_THREADS, G_SMEM, st>>>(tmA, tmB, out, M, N, K, kper);
+  else if (a_k && !b_k)
+    tc_gemm_kernel<true, false><<<grid, G_THREADS, G_SMEM, st>>>(tmA, tmB, out, M, N, K, kper);
+  else if (!a_k && !b_k)
+    tc_gemm_kernel<false, false><<<grid, G_THREADS, G_SMEM, st>>>(tmA, tmB, out, M, N, K, kper);
+  else
+    tc_gemm_kernel<false, true><<<grid, G_THREADS, G_SMEM, st>>>(tmA, tmB, out, M, N, K, kper);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("tc_gemm_kernel");
+  if (splits > 1) {
+    const int64_t MN = (int64_t)M * N;
+    tc_splitk_reduce_kernel<<<cdiv(MN, 256), 256, 0, st>>>(out, C, MN, splits);
+    count_launch();
+    DG_CUDA_LAUNCH_CHECK("tc_splitk_reduce_kernel");
+  }
+  return DGCNN_OK;
+}

@@ -77,6 +77,16 @@ size_t dgcnn_gemm_workspace_bytes(int M, int N, int K, int transA, int transB);
 int dgcnn_gemm(const float* A, const float* B, float* C, int M, int N, int K, int transA, int transB,
                void* ws, size_t ws_bytes, dgcnn_stream_t stream);
 
+/* ---- the same GEMM on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), fp32-faithful ("bf16x3") -----------
+ * Operands are pre-split fp32 -> two bf16 planes, planes[0] = bf16(x), planes[1] = bf16(x - planes[0]), stored
+ * back to back ([2][rows][cols], same row-major layout as the fp32 source); the kernel accumulates
+ * hi.hi + hi.lo + lo.hi in fp32 (relative error ~2^-17 per product).  M, N, K multiples of 8; all pointers
+ * 16-byte aligned.  transA / transB as in dgcnn_gemm; no transposed copies are ever made.                     */
+int dgcnn_split_bf16(const float* x, void* planes, int64_t n, dgcnn_stream_t stream);
+size_t dgcnn_tc_gemm_workspace_bytes(int M, int N, int K);
+int dgcnn_tc_gemm(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA, int transB,
+                  void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+
 /* ---- fused EdgeConv core: ops.py:45-57 (edges -> conv0 -> BN(train) -> ReLU -> max_k, mean_k)
  * Uses [x_i, x_j - x_i].[Wa;Wb] = x_i.(Wa-Wb) + x_j.Wb: the caller first forms
  * uv[P, 2F] = x[P,C] . [Wa-Wb | Wb] with dgcnn_gemm (P = B*N), so that z_ij = u_i + v_{idx(i,j)}

@@ -1,0 +1,80 @@
+"""tcgen05 GEMM (dgcnn_tc_gemm, bf16 hi/lo split, fp32 accumulate) against an fp64 matmul, all three operand
+layouts (forward, dX, dW) and ragged tile edges.  Tolerance: 2^-17-class relative error per product."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _split(dg, x):
+    from dgcnn import _native as nv
+    x = x.contiguous()
+    planes = torch.empty((2,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    nv.check(nv.lib().dgcnn_split_bf16(x.data_ptr(), planes.data_ptr(), x.numel(), nv.stream_ptr(x.device)), "split")
+    return planes
+
+
+def _tc(dg, A, B, M, N, K, tA, tB):
+    from dgcnn import _native as nv
+    L = nv.lib()
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    need = L.dgcnn_tc_gemm_workspace_bytes(M, N, K)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=A.device)
+    pa, pb = _split(dg, A), _split(dg, B)
+    nv.check(L.dgcnn_tc_gemm(pa.data_ptr(), pb.data_ptr(), out.data_ptr(), M, N, K, tA, tB, ws.data_ptr(), ws.numel(),
+                             nv.stream_ptr(A.device)), "tc_gemm")
+    return out
+
+
+def test_split_planes_reconstruct(dg, cuda):
+    x = torch.randn(4096, device=cuda) * 3
+    p = _split(dg, x)
+    rec = p[0].float() + p[1].float()
+    assert (rec - x).abs().max() <= x.abs().max() * 2.0 ** -16
+    assert torch.equal(p[0], x.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 256), (1000, 264, 520), (4096, 512, 1792), (136, 8, 72)])
+@pytest.mark.parametrize("mode", ["fwd", "dx", "dw"])
+def test_tc_gemm_matches_fp64(dg, cuda, M, N, K, mode):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    if mode == "fwd":      # C[M,N] = A[M,K] . B[K,N]
+        A = torch.randn((M, K), generator=g).to(cuda)
+        B = torch.randn((K, N), generator=g).to(cuda)
+        ref = A.double() @ B.double()
+        out = _tc(dg, A, B, M, N, K, 0, 0)
+    elif mode == "dx":     # C[M,N] = A[M,K] . B[N,K]^T
+        A = torch.randn((M, K), generator=g).to(cuda)
+        B = torch.randn((N, K), generator=g).to(cuda)
+        ref = A.double() @ B.double().t()
+        out = _tc(dg, A, B, M, N, K, 0, 1)
+    else:                  # C[M,N] = A[K,M]^T . B[K,N]
+        A = torch.randn((K, M), generator=g).to(cuda)
+        B = torch.randn((K, N), generator=g).to(cuda)
+        ref = A.double().t() @ B.double()
+        out = _tc(dg, A, B, M, N, K, 1, 0)
+    err = (out.double() - ref).abs().max().item()
+    scale = (A.double().abs().max() * B.double().abs().max()).item() * np.sqrt(K)
+    assert err <= 4e-5 * scale, (err, scale)
+    fp32 = (A @ B if mode == "fwd" else (A @ B.t() if mode == "dx" else A.t() @ B)).double()
+    # not worse than 8x the error of a plain fp32 GEMM on the same data (+ floor)
+    assert err <= 8 * (fp32 - ref).abs().max().item() + 1e-5 * scale
+
+
+def test_tc_gemm_weight_gradient_split_k(dg, cuda):
+    """dW shape of the head: small M,N and the 49152 points as contraction dimension (split over the grid)."""
+    g = torch.Generator(device="cpu").manual_seed(0)
+    P, Cin, Cout = 24 * 2048, 256, 512
+    X = torch.randn((P, Cin), generator=g).to(cuda)
+    G = torch.randn((P, Cout), generator=g).to(cuda) * 0.01
+    out = _tc(dg, X, G, Cin, Cout, P, 1, 0)
+    ref = X.double().t() @ G.double()
+    assert (out.double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+def test_tc_gemm_rejects_bad_shapes(dg, cuda):
+    from dgcnn import _native as nv
+    x = torch.zeros(64, device=cuda)
+    assert nv.lib().dgcnn_tc_gemm(x.data_ptr(), x.data_ptr(), x.data_ptr(), 12, 8, 8, 0, 0, None, 0, None) == nv.ERR_UNSUPPORTED
+    assert nv.lib().dgcnn_tc_gemm(None, x.data_ptr(), x.data_ptr(), 8, 8, 8, 0, 0, None, 0, None) == nv.ERR_INVALID
