@@ -223,29 +223,25 @@ __global__ void __launch_bounds__(G_THREADS, 1)
   }
 }
 
-// fp32 [n] -> bf16 planes hi[n], lo[n] (plane stride = plane_elems)
-__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ planes, int64_t n,
-                                  int64_t plane_elems) {
-  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i4 >= n) return;
-  if (i4 + 3 < n) {
-    const float4 v = *reinterpret_cast<const float4*>(x + i4);
-    const float f[4] = {v.x, v.y, v.z, v.w};
-    __nv_bfloat16 h[4], l[4];
+// fp32 [rows, cols] (row pitch ldx) -> bf16 planes hi / lo written at row pitch ldo (so that several sources can
+// fill column slices of one [2][rows][ldo] operand: the reference's tf.concat, model.py:60-63,83-85, by construction)
+__global__ void split_bf16_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ldx,
+                                  __nv_bfloat16* __restrict__ planes, int64_t ldo, int64_t plane_elems) {
+  const int cv = cols >> 2;  // float4 groups per row
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cv) return;
+  const int64_t r = i / cv;
+  const int c = (int)(i - r * cv) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      h[j] = __float2bfloat16_rn(f[j]);
-      l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
-    }
-    *reinterpret_cast<uint2*>(planes + i4) = *reinterpret_cast<uint2*>(h);
-    *reinterpret_cast<uint2*>(planes + plane_elems + i4) = *reinterpret_cast<uint2*>(l);
-  } else {
-    for (int64_t i = i4; i < n; ++i) {
-      const __nv_bfloat16 h = __float2bfloat16_rn(x[i]);
-      planes[i] = h;
-      planes[plane_elems + i] = __float2bfloat16_rn(x[i] - __bfloat162float(h));
-    }
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2bfloat16_rn(f[j]);
+    l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
   }
+  *reinterpret_cast<uint2*>(planes + r * ldo + c) = *reinterpret_cast<uint2*>(h);
+  *reinterpret_cast<uint2*>(planes + plane_elems + r * ldo + c) = *reinterpret_cast<uint2*>(l);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -301,12 +297,18 @@ __global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* _
 
 using namespace dgcnn;
 
-extern "C" int dgcnn_split_bf16(const float* x, void* planes, int64_t n, dgcnn_stream_t stream) {
+extern "C" int dgcnn_split_bf16(const float* x, int64_t rows, int cols, int64_t ldx, void* planes, int64_t ldo,
+                                int64_t plane_elems, dgcnn_stream_t stream) {
   DG_REQUIRE(x && planes, DGCNN_ERR_INVALID, "split_bf16: null pointer");
-  DG_REQUIRE(n > 0 && (n & 7) == 0, DGCNN_ERR_INVALID, "split_bf16: n=%lld must be a positive multiple of 8", (long long)n);
-  DG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)planes & 15) == 0, DGCNN_ERR_INVALID, "split_bf16: alignment");
-  const int64_t blocks = (n / 4 + 255) / 256;
-  split_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)planes, n, n);
+  DG_REQUIRE(rows > 0 && cols > 0 && (cols & 3) == 0, DGCNN_ERR_INVALID,
+             "split_bf16: rows=%lld cols=%d (cols must be a positive multiple of 4)", (long long)rows, cols);
+  DG_REQUIRE(ldx >= cols && ldo >= cols && (ldx & 3) == 0 && (ldo & 3) == 0 && (plane_elems & 3) == 0,
+             DGCNN_ERR_INVALID, "split_bf16: pitches must be multiples of 4 and >= cols");
+  DG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)planes & 7) == 0, DGCNN_ERR_INVALID, "split_bf16: alignment");
+  const int64_t blocks = (rows * (cols >> 2) + 255) / 256;
+  DG_REQUIRE(blocks < (1ll << 31), DGCNN_ERR_UNSUPPORTED, "split_bf16: too many elements");
+  split_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, (__nv_bfloat16*)planes, ldo,
+                                                                        plane_elems);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("split_bf16_kernel");
   return DGCNN_OK;

@@ -33,7 +33,7 @@ SIGNATURES = {
     "dgcnn_edge_feature_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "dgcnn_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "dgcnn_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
-    "dgcnn_split_bf16": (_i, [_vp, _vp, _i64, _vp]),
+    "dgcnn_split_bf16": (_i, [_vp, _i64, _i, _i64, _vp, _i64, _i64, _vp]),
     "dgcnn_tc_gemm_workspace_bytes": (_sz, [_i, _i, _i]),
     "dgcnn_tc_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "dgcnn_edgeconv_workspace_bytes": (_sz, [_i]),

@@ -1,22 +1,41 @@
 """Dense per-point layers of the model head (MergedEdgeConv / FC* / Final): SURVEY.md section 8(f) row N1.
 
-/root/reference/dgcnn/model.py:65-72,94-101 and ops.py:151-160 -- slim.conv2d(kernel 1) + slim.batch_norm +
-ReLU on [B,N,1,C].  The head is outside the EdgeConv hot path; its GEMM is a plain library GEMM
-(torch.matmul -> cuBLAS, true fp32: TF32 stays disabled), while BatchNorm+ReLU reuse the hand-written
-train-mode BN kernels of the hot path so that BN semantics (batch statistics, biased variance, eps=1e-3,
-beta only) are identical everywhere.
+/root/reference/dgcnn/model.py:60-104 and ops.py:151-160 -- tf.concat + slim.conv2d(kernel 1) + slim.batch_norm +
+ReLU on [B,N,1,C].  Here:
+  * the 1x1 convs run on the hand-written tcgen05 GEMM (fp32-faithful bf16 hi/lo split, csrc/tc_gemm.cu);
+  * channel concatenations are never materialised: every source tensor is split straight into its column slice
+    of the GEMM operand (ops._ConcatConvTC);
+  * the global max-pooled feature (model.py:76-81 tiles it over all N points before the concat) enters FC0 as a
+    per-cloud term  g_b . W[:1024]  added to the rows of cloud b -- algebraically the same product, 36 % fewer
+    FLOPs and no [B,N,1024] broadcast;
+  * BatchNorm(train)+ReLU are the hot path's own kernels (ops._BnAct), so BN semantics are identical everywhere.
 """
 from __future__ import annotations
+
+from typing import List, Optional
 
 import torch
 
 from . import ops as _ops
 
 
+def conv_bn_act(srcs: List[torch.Tensor], scope: str, cout: int, trainable: bool, activation=_ops.relu,
+                cloud_feature: Optional[torch.Tensor] = None, points_per_cloud: int = 0) -> torch.Tensor:
+    """srcs: [P, c_i] tensors whose channel concat is the layer input (after the optional per-cloud feature
+    [B, cg] that the reference tiles in front of it).  -> [P, cout]."""
+    cg = cloud_feature.shape[1] if cloud_feature is not None else 0
+    cin = cg + sum(int(t.shape[1]) for t in srcs)
+    w, b = _ops._conv_bn_vars(scope, cin, cout, trainable, srcs[0].device)
+    z = _ops.conv1x1(srcs, w[cg:] if cg else w)
+    if cg:
+        gb = _ops._Conv1x1.apply(cloud_feature, w[:cg])                  # [B, cout]: tiny, SIMT
+        B = cloud_feature.shape[0]
+        z = (z.view(B, points_per_cloud, cout) + gb.view(B, 1, cout)).view(B * points_per_cloud, cout)
+    return _ops._BnAct.apply(z, b, None, activation is not None)
+
+
 def conv_bn_relu_dense(net: torch.Tensor, scope: str, cout: int, trainable: bool, activation=_ops.relu) -> torch.Tensor:
-    """net [B,N,1,Cin] -> [B,N,1,cout]."""
+    """net [B,N,1,Cin] -> [B,N,1,cout] (the reference's tensor shapes)."""
     B, N, one, cin = net.shape
-    w, b = _ops._conv_bn_vars(scope, cin, cout, trainable, net.device)
-    z = torch.matmul(net.reshape(B * N * one, cin), w)
-    y = _ops._BnAct.apply(z, b, None, activation is not None)
+    y = conv_bn_act([net.reshape(B * N * one, cin)], scope, cout, trainable, activation)
     return y.view(B, N, one, cout)

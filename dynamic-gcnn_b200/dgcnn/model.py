@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from .head import conv_bn_relu_dense
+from .head import conv_bn_act, conv_bn_relu_dense
 from .variables import default_store
 
 DROPOUT_KEEP = 0.7  # model.py:91: tf.nn.dropout(net, 0.7, None) -> keep_prob
@@ -50,18 +50,29 @@ def build(point_cloud, flags, dropout_mask=None):
         if debug: print("Shape %s ... Name %s" % (tuple(net.shape), "Final"))
         return net.squeeze(-2)
 
-    concat = torch.cat([tensors[3 * i + 2] for i in range(num_edge_conv)], dim=-1)   # model.py:60-63
-    net = conv_bn_relu_dense(concat, "MergedEdgeConv", 1024, True)                   # model.py:65-72
-    if debug: print("Shape %s ... Name %s" % (tuple(net.shape), "MergedEdgeConv"))
-    tensors = tensors + [net]                                                        # model.py:74
-
-    g = net.amax(dim=1, keepdim=True)                                                # model.py:77 global max pool
-    if debug: print("Shape %s ... Name %s" % (tuple(g.shape), "maxpool0"))
-    g = g.reshape(batch_size, -1, 1, 1024).expand(batch_size, num_point, 1, 1024)    # model.py:80-81
-    net = torch.cat([g] + tensors, dim=3)                                            # model.py:83-85
-    if debug: print("Shape %s ... Name %s" % (tuple(net.shape), "concat"))
-
-    net = ops.fc(net=net, repeat=num_fc, num_filters=num_fc_filters, trainable=is_training, debug=debug)
+    P = batch_size * num_point
+    flat = [x.reshape(P, x.shape[-1]) for x in tensors]
+    # model.py:60-72: concat of every layer's `net` -> MergedEdgeConv (1024) ; the concat is never built
+    merged = conv_bn_act([flat[3 * i + 2] for i in range(num_edge_conv)], "MergedEdgeConv", 1024, True)
+    if debug: print("Shape %s ... Name %s" % ((batch_size, num_point, 1, 1024), "MergedEdgeConv"))
+    g = merged.view(batch_size, num_point, 1024).amax(dim=1)                           # model.py:77 global max pool
+    if debug: print("Shape %s ... Name %s" % ((batch_size, 1, 1, 1024), "maxpool0"))
+    # model.py:80-88: tile(g) ++ tensors ++ merged -> FC stack.  First FC layer: the tiled global feature is a
+    # per-cloud term, the rest a multi-source GEMM; later FC layers are plain.
+    num_fc_filters = ops._listify(num_fc_filters, num_fc, "num_filters")
+    if debug: print("Shape %s ... Name %s" % ((batch_size, num_point, 1, 1024 + sum(x.shape[1] for x in flat) + 1024),
+                                              "concat (never materialised)"))
+    srcs = flat + [merged]
+    if num_fc == 0:
+        net = torch.cat([g.view(batch_size, 1, 1024).expand(batch_size, num_point, 1024).reshape(P, 1024)] + srcs, dim=1)
+    for i in range(num_fc):
+        if i == 0:
+            net = conv_bn_act(srcs, "FC0", int(num_fc_filters[0]), is_training, cloud_feature=g,
+                              points_per_cloud=num_point)
+        else:
+            net = conv_bn_act([net], "FC%d" % i, int(num_fc_filters[i]), is_training)
+        if debug: print("Shape %s ... Name %s" % ((batch_size, num_point, 1, net.shape[1]), "FC%d" % i))
+    net = net.view(batch_size, num_point, 1, net.shape[1])
 
     if is_training:                                                                  # model.py:90-91
         if dropout_mask is None:

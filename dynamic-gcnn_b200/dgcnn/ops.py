@@ -173,6 +173,90 @@ class _Conv1x1(torch.autograd.Function):
         return ga, gw
 
 
+# ---- tensor-core path: tcgen05 GEMM on pre-split bf16 hi/lo planes (fp32-faithful, csrc/tc_gemm.cu) -------------
+TC_MIN_ROWS = 1024  # below this the SIMT kernel wins (launch + split overhead)
+
+
+def _tc_ok(P: int, *dims: int) -> bool:
+    return P >= TC_MIN_ROWS and P % 8 == 0 and all(d % 8 == 0 and d >= 8 for d in dims)
+
+
+def _split_into(x2d: torch.Tensor, planes: torch.Tensor, col: int) -> None:
+    """fp32 [rows, c] -> columns [col, col+c) of the bf16 operand planes [2, rows, ld]."""
+    rows, c = x2d.shape
+    ld = planes.shape[2]
+    dst = planes.data_ptr() + 2 * col
+    nv.check(nv.lib().dgcnn_split_bf16(x2d.data_ptr(), rows, c, x2d.stride(0), dst, ld, planes.shape[1] * ld,
+                                       nv.stream_ptr(x2d.device)), "split_bf16")
+
+
+def _split(x2d: torch.Tensor) -> torch.Tensor:
+    x2d = nv.require_cuda(x2d, "operand")
+    planes = torch.empty((2,) + tuple(x2d.shape), dtype=torch.bfloat16, device=x2d.device)
+    _split_into(x2d, planes, 0)
+    return planes
+
+
+def _tc_gemm_raw(pa, pb, M, N, K, tA, tB):
+    L = nv.lib()
+    out = torch.empty((M, N), dtype=torch.float32, device=pa.device)
+    need = L.dgcnn_tc_gemm_workspace_bytes(M, N, K)
+    ws = nv.workspace(pa.device, need, "gemm") if need else None
+    nv.check(L.dgcnn_tc_gemm(pa.data_ptr(), pb.data_ptr(), out.data_ptr(), M, N, K, tA, tB, nv.ptr(ws),
+                             ws.numel() if ws is not None else 0, nv.stream_ptr(pa.device)), "tc_gemm")
+    return out
+
+
+class _ConcatConvTC(torch.autograd.Function):
+    """1x1 conv of the channel-concatenation of several [P, c_i] tensors with W [sum c_i, Cout], without building
+    the concatenation (model.py:60-63,83-85 + slim.conv2d): each source is split straight into its column slice of
+    one bf16 operand; forward, dX and dW are three tcgen05 GEMMs on the same planes."""
+
+    @staticmethod
+    def forward(ctx, w, *srcs):
+        w = nv.require_cuda(w, "conv weights")
+        srcs = [nv.require_cuda(t, "conv input") for t in srcs]
+        P = srcs[0].shape[0]
+        widths = [int(t.shape[1]) for t in srcs]
+        K, Cout = sum(widths), w.shape[1]
+        planes = torch.empty((2, P, K), dtype=torch.bfloat16, device=w.device)
+        off = 0
+        for t, c in zip(srcs, widths):
+            _split_into(t, planes, off)
+            off += c
+        pw = _split(w)
+        ctx.save_for_backward(planes, pw)
+        ctx.widths = widths
+        return _tc_gemm_raw(planes, pw, P, Cout, K, 0, 0)
+
+    @staticmethod
+    def backward(ctx, g):
+        planes, pw = ctx.saved_tensors
+        _, P, K = planes.shape
+        Cout = pw.shape[2]
+        pg = _split(nv.require_cuda(g, "grad"))
+        gw = _tc_gemm_raw(planes, pg, K, Cout, P, 1, 0) if ctx.needs_input_grad[0] else None   # X^T . g
+        outs = [gw]
+        if any(ctx.needs_input_grad[1:]):
+            gcat = _tc_gemm_raw(pg, pw, P, K, Cout, 0, 1)                                         # g . W^T
+            off = 0
+            for i, c in enumerate(ctx.widths):
+                outs.append(gcat[:, off:off + c] if ctx.needs_input_grad[1 + i] else None)
+                off += c
+        else:
+            outs += [None] * len(ctx.widths)
+        return tuple(outs)
+
+
+def conv1x1(srcs, w) -> torch.Tensor:
+    """[P, sum c_i] x [sum c_i, Cout] on the tensor cores when the shape allows, else the SIMT kernel."""
+    P = srcs[0].shape[0]
+    if _tc_ok(P, w.shape[1], *[t.shape[1] for t in srcs]):
+        return _ConcatConvTC.apply(w, *srcs)
+    a = srcs[0] if len(srcs) == 1 else torch.cat(srcs, dim=1)
+    return _Conv1x1.apply(a, w)
+
+
 class _EdgeConvGather(torch.autograd.Function):
     """ops.py:45-57 after the algebraic split z_ij = u_i + v_idx(i,j): BN(train)+ReLU+max_k/mean_k."""
 

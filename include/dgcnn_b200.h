@@ -82,7 +82,10 @@ int dgcnn_gemm(const float* A, const float* B, float* C, int M, int N, int K, in
  * back to back ([2][rows][cols], same row-major layout as the fp32 source); the kernel accumulates
  * hi.hi + hi.lo + lo.hi in fp32 (relative error ~2^-17 per product).  M, N, K multiples of 8; all pointers
  * 16-byte aligned.  transA / transB as in dgcnn_gemm; no transposed copies are ever made.                     */
-int dgcnn_split_bf16(const float* x, void* planes, int64_t n, dgcnn_stream_t stream);
+/* x [rows, cols] fp32 at row pitch ldx -> planes: hi at planes[r*ldo + c], lo at planes[plane_elems + r*ldo + c].
+ * With ldo > cols several sources fill column slices of one operand (concat by construction).              */
+int dgcnn_split_bf16(const float* x, int64_t rows, int cols, int64_t ldx, void* planes, int64_t ldo,
+                     int64_t plane_elems, dgcnn_stream_t stream);
 size_t dgcnn_tc_gemm_workspace_bytes(int M, int N, int K);
 int dgcnn_tc_gemm(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA, int transB,
                   void* ws, size_t ws_bytes, dgcnn_stream_t stream);
