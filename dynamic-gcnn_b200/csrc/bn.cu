@@ -8,7 +8,7 @@
 namespace dgcnn {
 
 constexpr int BN_THREADS = 256;
-constexpr int BN_BLOCKS_PER_SM = 8;
+constexpr int BN_BLOCKS_PER_SM = 4;
 
 static inline int bn_max_blocks() { return num_sms() * BN_BLOCKS_PER_SM; }
 static inline int bn_blocks(int64_t rows) {

@@ -109,49 +109,59 @@ __global__ void __launch_bounds__(EC_THREADS)
   }
 }
 
-// partial [nblk][2][C] -> per-channel totals.  One warp per channel: lane l adds blocks l, l+32, ... in fp64, then a
-// fixed xor-tree across lanes => deterministic for a given grid.
-__device__ __forceinline__ void warp_channel_totals(const float* __restrict__ partial, int nblk, int C, int c,
-                                                    double& s, double& q) {
-  const int lane = threadIdx.x & 31;
+// partial [nblk][2][C] -> per-channel totals, fp64, fixed summation order (deterministic for a given grid).
+// Block = 64 channels x 16 block-groups: thread (g, c) adds blocks g, g+16, ... with coalesced 256 B reads, then the
+// 16 group sums are combined in a fixed tree through shared memory.
+constexpr int FIN_G = 16;
+__device__ __forceinline__ bool block_channel_totals(const float* __restrict__ partial, int nblk, int C, double& s,
+                                                     double& q, int& c_out) {
+  __shared__ double red[2][FIN_G][64];
+  const int cl = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
+  double a = 0.0, b2 = 0.0;
+  if (c < C) {
+#pragma unroll 4
+    for (int b = g; b < nblk; b += FIN_G) {
+      a += (double)partial[((int64_t)b * 2 + 0) * C + c];
+      b2 += (double)partial[((int64_t)b * 2 + 1) * C + c];
+    }
+  }
+  red[0][g][cl] = a;
+  red[1][g][cl] = b2;
+  __syncthreads();
+  if (g != 0 || c >= C) return false;
   s = 0.0;
   q = 0.0;
-  for (int b = lane; b < nblk; b += 32) {
-    s += (double)partial[((int64_t)b * 2 + 0) * C + c];
-    q += (double)partial[((int64_t)b * 2 + 1) * C + c];
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(FULL, s, o);
-    q += __shfl_xor_sync(FULL, q, o);
+  for (int i = 0; i < FIN_G; ++i) {
+    s += red[0][i][cl];
+    q += red[1][i][cl];
   }
+  c_out = c;
+  return true;
 }
 
-__global__ void finalize_stats_kernel(const float* __restrict__ partial, int nblk, int C, double count, float eps,
-                                      float* __restrict__ mean, float* __restrict__ rstd) {
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (c >= C) return;
+__global__ void __launch_bounds__(64 * FIN_G)
+    finalize_stats_kernel(const float* __restrict__ partial, int nblk, int C, double count, float eps,
+                          float* __restrict__ mean, float* __restrict__ rstd) {
   double s, q;
-  warp_channel_totals(partial, nblk, C, c, s, q);
+  int c;
+  if (!block_channel_totals(partial, nblk, C, s, q, c)) return;
   const double m = s / count;
   double var = q / count - m * m;
   if (var < 0.0) var = 0.0;
-  if ((threadIdx.x & 31) == 0) {
-    mean[c] = (float)m;
-    rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  }
+  mean[c] = (float)m;
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-__global__ void finalize_sums_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ s1,
-                                     float* __restrict__ s2) {
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (c >= C) return;
+__global__ void __launch_bounds__(64 * FIN_G)
+    finalize_sums_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ s1,
+                         float* __restrict__ s2) {
   double a, b2;
-  warp_channel_totals(partial, nblk, C, c, a, b2);
-  if ((threadIdx.x & 31) == 0) {
-    s1[c] = (float)a;
-    s2[c] = (float)b2;
-  }
+  int c;
+  if (!block_channel_totals(partial, nblk, C, a, b2, c)) return;
+  s1[c] = (float)a;
+  s2[c] = (float)b2;
 }
 
 // pass 2 forward: out_max, out_mean
@@ -277,13 +287,13 @@ __global__ void zero_vhalf_kernel(float* __restrict__ guv, int64_t P, int F) {
 
 int launch_finalize_stats(const float* partial, int nblk, int C, double count, float eps, float* mean, float* rstd,
                           cudaStream_t st) {
-  finalize_stats_kernel<<<cdiv(C, 4), 128, 0, st>>>(partial, nblk, C, count, eps, mean, rstd);
+  finalize_stats_kernel<<<cdiv(C, 64), 64 * FIN_G, 0, st>>>(partial, nblk, C, count, eps, mean, rstd);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("finalize_stats_kernel");
   return DGCNN_OK;
 }
 int launch_finalize_sums(const float* partial, int nblk, int C, float* s1, float* s2, cudaStream_t st) {
-  finalize_sums_kernel<<<cdiv(C, 4), 128, 0, st>>>(partial, nblk, C, s1, s2);
+  finalize_sums_kernel<<<cdiv(C, 64), 64 * FIN_G, 0, st>>>(partial, nblk, C, s1, s2);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("finalize_sums_kernel");
   return DGCNN_OK;

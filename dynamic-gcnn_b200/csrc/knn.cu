@@ -197,12 +197,14 @@ struct RowSel {
 //   queue  [TM][TQ]      candidates that passed the filter, (d, j) split in two planes
 //   list   [TM][32*KS]   ascending best-so-far list
 //   tau    [TM]          admission threshold (list entry k-1), count [TM] queued candidates
-//   dst    [TM][TN]      the tile's distances, staged so that the per-row selection loop can index rows
-//                        dynamically (each lane reads back exactly the float4 it wrote: conflict-free)
+//   dst    [TM][DLD]     the tile's distances, staged so that the scan can re-map threads: the FMA micro-tile is
+//                        8 rows x 4 columns per lane, the scan gives every row to 4 lanes (columns q, q+4, ...);
+//                        row pitch 132 floats makes both the float4 writes and the strided reads conflict-free
 // Keeping this state out of registers lets the drain (sort + merge, ~200 instructions) exist ONCE in the
 // instruction stream: a first version that kept the lists in registers had to unroll it per row and ran
 // instruction-cache bound (ncu: stall_no_instruction 7 of 14.9 cycles per issue).
-constexpr int TQ = 64;  // 31 left over + 32 appended per ballot
+constexpr int TQ = 64;   // 31 left over + at most 32 appended per 32-column chunk
+constexpr int DLD = TN + 4;
 
 template <int KS>
 struct KnnSel {
@@ -213,12 +215,12 @@ struct KnnSel {
   float* taud;
   int* tauj;
   int* qcnt;
-  float4* dst;
+  float* dst;
   static constexpr int LW = 32 * KS;
-  static constexpr size_t bytes() { return (size_t)TM * (TN * 4 + TQ * 8 + LW * 8 + 12); }
+  static constexpr size_t bytes() { return (size_t)TM * (DLD * 4 + TQ * 8 + LW * 8 + 12); }
   __device__ __forceinline__ void carve(unsigned char* base) {
-    dst = reinterpret_cast<float4*>(base);
-    qd = reinterpret_cast<float*>(base + (size_t)TM * TN * 4);
+    dst = reinterpret_cast<float*>(base);
+    qd = reinterpret_cast<float*>(base + (size_t)TM * DLD * 4);
     qj = reinterpret_cast<int*>(qd + TM * TQ);
     ld = reinterpret_cast<float*>(qj + TM * TQ);
     lj = reinterpret_cast<int*>(ld + TM * LW);
@@ -312,7 +314,6 @@ __global__ void __launch_bounds__(KNN_THREADS, 2)
   const int T = Npad / TN;
   const int Q = (C + CK - 1) / CK;
   const int S = T * Q;
-  const unsigned lt = (1u << lane) - 1u;
 
   if (tid < TM) sAs[tid] = sb[r0 + tid];
 
@@ -411,47 +412,49 @@ __global__ void __launch_bounds__(KNN_THREADS, 2)
             for (int c = 0; c < 4; ++c)
               if (col0 + c >= N) acc[r][c] = __int_as_float(0x7fc00000);
         }
-        // stage the warp's 8x128 distances, then ONE (not unrolled) per-row loop: filter against the row's
-        // threshold, ballot-compacted append to its queue, drain (sort+merge) whenever 32 are queued.
+        // stage the warp's 8x128 distances, then scan them with a different thread mapping: lane = (row, quarter),
+        // each lane filters ITS OWN elements against its row's threshold (one compare per element, no collectives);
+        // survivors go to the row's queue through a shared counter; the warp drains a row (sort + merge) only when
+        // 32 candidates are queued.  Chunks of 32 columns bound the queue at 31 + 32 entries.
 #pragma unroll
         for (int r = 0; r < 8; ++r)
-          sel.dst[(warp * 8 + r) * 32 + lane] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+          *reinterpret_cast<float4*>(&sel.dst[(warp * 8 + r) * DLD + lane * 4]) =
+              make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
         __syncwarp();
+        const int srow = warp * 8 + (lane >> 2);   // the row this lane scans
+        const int sq = lane & 3;
+        const float* drow = sel.dst + srow * DLD + sq;
 #pragma unroll 1
-        for (int r = 0; r < 8; ++r) {
-          const int row = warp * 8 + r;
-          const float4 d4 = sel.dst[row * 32 + lane];
-          const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
-          float td = sel.taud[row];
-          int tj = sel.tauj[row];
-          // cheap superset test first (one compare per element); the exact (d, j) order only on the rare pass path
-          const bool anyp = (dv[0] <= td) || (dv[1] <= td) || (dv[2] <= td) || (dv[3] <= td);
-          if (__ballot_sync(FULL, anyp) == 0) continue;
-          int cnt = sel.qcnt[row];
+        for (int ch = 0; ch < TN / 32; ++ch) {
+          const float td = sel.taud[srow];
+          const int tj = sel.tauj[srow];
+          float dv[8];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int col = col0 + c;
-            const bool p = lex_less(dv[c], col, td, tj);
-            const unsigned m = __ballot_sync(FULL, p);
-            if (m == 0) continue;
-            if (p) {
-              const int pos = cnt + __popc(m & lt);
-              sel.qd[row * TQ + pos] = dv[c];
-              sel.qj[row * TQ + pos] = col;
-            }
-            cnt += __popc(m);
-            if (cnt >= 32) {
-              __syncwarp();
-              cnt -= 32;
-              sel.drain(row, cnt, 32, k, lane);
-              __syncwarp();
-              td = sel.taud[row];
-              tj = sel.tauj[row];
+          for (int i = 0; i < 8; ++i) dv[i] = drow[ch * 32 + 4 * i];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (dv[i] <= td) {                                   // superset test; NaN (ragged columns) fails
+              const int col = t * TN + ch * 32 + 4 * i + sq;
+              if (lex_less(dv[i], col, td, tj)) {
+                const int pos = atomicAdd(&sel.qcnt[srow], 1);
+                sel.qd[srow * TQ + pos] = dv[i];
+                sel.qj[srow * TQ + pos] = col;
+              }
             }
           }
-          if (lane == 0) sel.qcnt[row] = cnt;
+          __syncwarp();
+          const int cnt = sel.qcnt[srow];
+          unsigned need = __ballot_sync(FULL, cnt >= 32 && sq == 0);
+          while (need) {                                         // warp-uniform
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const int c = __shfl_sync(FULL, cnt, src) - 32;
+            const int row = warp * 8 + (src >> 2);
+            sel.drain(row, c, 32, k, lane);
+            if (lane == 0) sel.qcnt[row] = c;
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
     __syncthreads();

@@ -396,7 +396,7 @@ def edge_conv(point_cloud, k, num_filters, trainable, activation=relu, debug=Fal
     if debug: _dbg(debug, torch.empty(B, N, k, 2 * C, device="meta"), _cur_scope() + "/edges (never materialised)")
     w0, b0 = _conv_bn_vars("conv0", 2 * C, F, trainable, x.device)              # ops.py:47-54
     wp = torch.cat([w0[:C] - w0[C:], w0[C:]], dim=1)                            # [C, 2F] = [Wa-Wb | Wb]
-    uv = _Conv1x1.apply(x.reshape(B * N, C), wp)
+    uv = _Conv1x1.apply(x.reshape(B * N, C), wp)   # exact fp32 SIMT: the next layer's kNN is built on these features
     net_max, net_mean = _EdgeConvGather.apply(uv, idx, b0, B, N, k)             # ops.py:53-57
     if debug: _dbg(debug, torch.empty(B, N, k, F, device="meta"), _cur_scope() + "/conv0 (never materialised)")
     net = torch.cat([net_max, net_mean], dim=-1)                                # ops.py:58
