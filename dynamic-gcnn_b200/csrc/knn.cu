@@ -3,6 +3,7 @@
 // Neg, TopKV2).  fp32 SIMT formulation: every p_ij is ONE sequential-in-c fmaf chain (the oracle's order),
 // the [B,N,N] matrix lives only in registers, selection is a warp-resident sorted list.
 #include "common.cuh"
+#include "knn_select.cuh"
 
 namespace dgcnn {
 
@@ -33,164 +34,6 @@ __global__ void knn_prep_kernel(const float* __restrict__ x, float* __restrict__
   }
   s[(size_t)b * Npad + n] = acc;
 }
-
-// ---------------------------------------------------------------------------------------------
-// Per-row selection state, owned by one warp.
-//   * an ascending list of the best 32*KS (distance, index) pairs: slot p lives in lane p&31, register p>>5.
-//     Order is lexicographic (d, j): equal distances keep the lower index first = tf.nn.top_k's tie rule
-//     (ops.py:18).  Empty slots hold (+inf, INT_MAX).
-//   * a 64-entry shared-memory queue of candidates that passed the threshold filter.  Whenever 32 are
-//     queued the warp sorts them with a 32-lane bitonic network and bitonic-merges them into the list
-//     (one ~200-instruction dependent chain per 32 candidates instead of one per candidate).
-// The threshold (td, tj) = list entry k-1 only tightens at drains; stale entries are merely merged and drop off.
-constexpr int QCAP = 64;
-
-__device__ __forceinline__ bool lex_less(float ad, int aj, float bd, int bj) {
-  return (ad < bd) || (ad == bd && aj < bj);
-}
-
-// ascending bitonic sort of one (d, j) pair per lane
-__device__ __forceinline__ void warp_sort32(float& d, int& j, int lane) {
-#pragma unroll
-  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
-#pragma unroll
-    for (int jm = k2 >> 1; jm > 0; jm >>= 1) {
-      const float od = __shfl_xor_sync(FULL, d, jm);
-      const int oj = __shfl_xor_sync(FULL, j, jm);
-      const bool up = (lane & k2) == 0;
-      const bool lower = (lane & jm) == 0;
-      const bool other_less = lex_less(od, oj, d, j);
-      const bool take = (lower == up) ? other_less : !other_less;
-      if (take) {
-        d = od;
-        j = oj;
-      }
-    }
-  }
-}
-
-// d,j hold a bitonic sequence across the 32 lanes -> ascending
-__device__ __forceinline__ void warp_bitonic_merge32(float& d, int& j, int lane) {
-#pragma unroll
-  for (int jm = 16; jm > 0; jm >>= 1) {
-    const float od = __shfl_xor_sync(FULL, d, jm);
-    const int oj = __shfl_xor_sync(FULL, j, jm);
-    const bool lower = (lane & jm) == 0;
-    const bool other_less = lex_less(od, oj, d, j);
-    if (lower ? other_less : !other_less) {
-      d = od;
-      j = oj;
-    }
-  }
-}
-
-template <int KS>
-struct RowSel {
-  float d[KS];
-  int j[KS];
-  float td;  // admission threshold = entry k-1 of the list
-  int tj;
-  int cnt;   // queued candidates (warp-uniform)
-
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int s = 0; s < KS; ++s) {
-      d[s] = __int_as_float(0x7f800000);
-      j[s] = 0x7fffffff;
-    }
-    td = __int_as_float(0x7f800000);
-    tj = 0x7fffffff;
-    cnt = 0;
-  }
-
-  // merge one candidate per lane (bd, bj; +inf pads) into the list and refresh the threshold
-  __device__ __forceinline__ void merge_batch(float bd, int bj, int k, int lane) {
-    warp_sort32(bd, bj, lane);
-    const float rd = __shfl_sync(FULL, bd, 31 - lane);  // reversed batch
-    const int rj = __shfl_sync(FULL, bj, 31 - lane);
-    if (KS == 1) {
-      if (lex_less(rd, rj, d[0], j[0])) {
-        d[0] = rd;
-        j[0] = rj;
-      }
-      warp_bitonic_merge32(d[0], j[0], lane);
-    } else {
-      // 64 smallest of list(64) U batch(32): C = [L0, min(L1, rev(batch))] is bitonic; merge network over 64
-      if (lex_less(rd, rj, d[KS - 1], j[KS - 1])) {
-        d[KS - 1] = rd;
-        j[KS - 1] = rj;
-      }
-      if (lex_less(d[KS - 1], j[KS - 1], d[0], j[0])) {
-        const float t = d[0];
-        d[0] = d[KS - 1];
-        d[KS - 1] = t;
-        const int u = j[0];
-        j[0] = j[KS - 1];
-        j[KS - 1] = u;
-      }
-      warp_bitonic_merge32(d[0], j[0], lane);
-      warp_bitonic_merge32(d[KS - 1], j[KS - 1], lane);
-    }
-    const int src = (k - 1) & 31;
-    float a = __shfl_sync(FULL, d[0], src);
-    int bjj = __shfl_sync(FULL, j[0], src);
-    if (KS == 2) {
-      const float a1 = __shfl_sync(FULL, d[KS - 1], src);
-      const int b1 = __shfl_sync(FULL, j[KS - 1], src);
-      if (k > 32) {
-        a = a1;
-        bjj = b1;
-      }
-    }
-    td = a;
-    tj = bjj;
-  }
-
-  // offer 4 candidates per lane; qd/qj = this row's queue (QCAP entries)
-  __device__ __forceinline__ void offer4(const float (&dv)[4], const int (&cj)[4], int N, int k,
-                                         float* __restrict__ qd, int* __restrict__ qj, int lane) {
-    bool p[4];
-    bool anyp = false;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      p[q] = (cj[q] < N) && lex_less(dv[q], cj[q], td, tj);
-      anyp |= p[q];
-    }
-    if (__ballot_sync(FULL, anyp) == 0) return;
-    const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const unsigned m = __ballot_sync(FULL, p[q]);
-      if (m == 0) continue;  // warp-uniform
-      if (p[q]) {
-        const int pos = cnt + __popc(m & lt);
-        qd[pos] = dv[q];
-        qj[pos] = cj[q];
-      }
-      cnt += __popc(m);
-      if (cnt >= 32) {
-        __syncwarp();
-        cnt -= 32;
-        const float bd = qd[cnt + lane];
-        const int bj = qj[cnt + lane];
-        __syncwarp();
-        merge_batch(bd, bj, k, lane);
-      }
-    }
-  }
-
-  // drain what is left in the queue
-  __device__ __forceinline__ void finish(int k, const float* __restrict__ qd, const int* __restrict__ qj, int lane) {
-    if (cnt > 0) {
-      __syncwarp();
-      const float bd = lane < cnt ? qd[lane] : __int_as_float(0x7f800000);
-      const int bj = lane < cnt ? qj[lane] : 0x7fffffff;
-      cnt = 0;
-      __syncwarp();
-      merge_batch(bd, bj, k, lane);
-    }
-  }
-};
 
 // ---------------------------------------------------------------------------------------------
 // Shared-memory selection state of the tile kernel (one row = one warp-owned record):
@@ -298,8 +141,8 @@ struct KnnSel {
 template <int KS, bool WRITE_D>
 __global__ void __launch_bounds__(KNN_THREADS, 2)
     knn_tile_kernel(const float* __restrict__ xT, const float* __restrict__ s, const float* __restrict__ x,
-                    const int32_t* __restrict__ hint, int N, int Npad, int C, int k, int32_t* __restrict__ idx,
-                    float* __restrict__ D) {
+                    const int32_t* __restrict__ hint, const int32_t* __restrict__ rowflags, int N, int Npad, int C,
+                    int k, int32_t* __restrict__ idx, float* __restrict__ D) {
   __shared__ __align__(16) float As[2][CK][TM];
   __shared__ __align__(16) float Bs[2][CK][TN];
   __shared__ __align__(16) float sBs[2][TN];
@@ -315,6 +158,12 @@ __global__ void __launch_bounds__(KNN_THREADS, 2)
   const int Q = (C + CK - 1) / CK;
   const int S = T * Q;
 
+  if (!WRITE_D && rowflags != nullptr) {
+    // fallback mode behind the tensor-core filter: only CTAs that own an uncertified row do any work
+    int f = 0;
+    if (tid < TM && r0 + tid < N) f = rowflags[(size_t)b * N + r0 + tid];
+    if (!__syncthreads_or(f)) return;
+  }
   if (tid < TM) sAs[tid] = sb[r0 + tid];
 
   KnnSel<KS> sel;
@@ -532,10 +381,25 @@ static int knn_common(const float* x, int B, int N, int C, void* ws, size_t ws_b
 
 using namespace dgcnn;
 
+namespace dgcnn {
+int knn_tc_run(const float* x, const float* s, const int32_t* hint, int32_t* idx, int B, int N, int Npad, int C, int k,
+               void* extra, int32_t** flags_out, cudaStream_t st);
+size_t knn_tc_extra_bytes(int B, int N, int C);
+static inline size_t knn_base_bytes(int B, int N, int C) {
+  const size_t Npad = npad_of(N);
+  return ((((size_t)B * C * Npad + (size_t)B * Npad) * sizeof(float)) + 255) & ~(size_t)255;
+}
+// the tensor-core filter needs a warm start, 16-byte rows of at most one 64-wide k-block, and list slack over k
+static inline bool knn_tc_eligible(const int32_t* hint, int N, int C, int k) {
+  return hint != nullptr && (C & 7) == 0 && C >= 8 && C <= 64 && k <= 24 && N >= 128;
+}
+}  // namespace dgcnn
+
 extern "C" size_t dgcnn_knn_workspace_bytes(int B, int N, int C) {
   if (B <= 0 || N <= 0 || C <= 0) return 0;
-  const size_t Npad = npad_of(N);
-  return ((size_t)B * C * Npad + (size_t)B * Npad) * sizeof(float);
+  size_t n = knn_base_bytes(B, N, C);
+  if ((C & 7) == 0 && C >= 8 && C <= 64 && N >= 128) n += knn_tc_extra_bytes(B, N, C);
+  return n;
 }
 
 extern "C" int dgcnn_pairwise_distance(const float* x, float* D, int B, int N, int C, void* ws, size_t ws_bytes,
@@ -548,7 +412,7 @@ extern "C" int dgcnn_pairwise_distance(const float* x, float* D, int B, int N, i
   int rc = knn_common(x, B, N, C, ws, ws_bytes, st, &xT, &s, &Npad);
   if (rc) return rc;
   dim3 g(cdiv(N, TM), B);
-  knn_tile_kernel<1, true><<<g, KNN_THREADS, 0, st>>>(xT, s, x, nullptr, N, Npad, C, 1, nullptr, D);
+  knn_tile_kernel<1, true><<<g, KNN_THREADS, 0, st>>>(xT, s, x, nullptr, nullptr, N, Npad, C, 1, nullptr, D);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("knn_tile_kernel<D>");
   return DGCNN_OK;
@@ -569,6 +433,16 @@ extern "C" int dgcnn_knn_hinted(const float* x, const int32_t* hint, int32_t* id
   int Npad = 0;
   int rc = knn_common(x, B, N, C, ws, ws_bytes, st, &xT, &s, &Npad);
   if (rc) return rc;
+  const int32_t* rowflags = nullptr;
+  if (knn_tc_eligible(hint, N, C, k)) {
+    // tensor-core filter + exact refinement; the SIMT kernel below then only redoes uncertified rows
+    int32_t* fl = nullptr;
+    rc = knn_tc_run(x, s, hint, idx, B, N, Npad, C, k, reinterpret_cast<unsigned char*>(ws) + knn_base_bytes(B, N, C),
+                    &fl, st);
+    if (rc) return rc;
+    (void)fl;       // uncertified rows were already recomputed exactly by knn_row_fallback_kernel
+    return DGCNN_OK;
+  }
   dim3 g(cdiv(N, TM), B);
   static bool attr_done = false;  // raise the dynamic-smem cap once (idempotent, benign if raced)
   if (!attr_done) {
@@ -579,9 +453,9 @@ extern "C" int dgcnn_knn_hinted(const float* x, const int32_t* hint, int32_t* id
     attr_done = true;
   }
   if (k <= 32)
-    knn_tile_kernel<1, false><<<g, KNN_THREADS, KnnSel<1>::bytes(), st>>>(xT, s, x, hint, N, Npad, C, k, idx, nullptr);
+    knn_tile_kernel<1, false><<<g, KNN_THREADS, KnnSel<1>::bytes(), st>>>(xT, s, x, hint, rowflags, N, Npad, C, k, idx, nullptr);
   else
-    knn_tile_kernel<2, false><<<g, KNN_THREADS, KnnSel<2>::bytes(), st>>>(xT, s, x, hint, N, Npad, C, k, idx, nullptr);
+    knn_tile_kernel<2, false><<<g, KNN_THREADS, KnnSel<2>::bytes(), st>>>(xT, s, x, hint, rowflags, N, Npad, C, k, idx, nullptr);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("knn_tile_kernel");
   return DGCNN_OK;

@@ -13,10 +13,7 @@
 //   warp 1   : MMA issuer    -- allocates 128 TMEM columns, one elected lane issues tcgen05.mma (M=128,N=128,K=16),
 //                               tcgen05.commit releases ring slots / publishes the accumulator
 //   warps 2-5: epilogue      -- tcgen05.ld 32 lanes x 32 columns, fp32 stores (each warp owns its TMEM sub-partition)
-#include <cuda.h>
-#include <cuda_bf16.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dgcnn {
 
@@ -24,57 +21,6 @@ constexpr int GB_M = 128, GB_N = 128, GB_K = 64, G_STAGES = 3, G_THREADS = 192;
 constexpr uint32_t TILE_BYTES = GB_M * GB_K * 2;          // 16 KB: one bf16 plane of one operand tile
 constexpr uint32_t STAGE_BYTES = 4 * TILE_BYTES;          // A_hi, A_lo, B_hi, B_lo
 constexpr size_t G_SMEM = (size_t)G_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  uint32_t spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > (1u << 26)) __trap();  // a protocol bug must fail loudly, not hang the GPU
-  }
-}
-
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-      : "memory");
-}
-
-// 64-bit shared-memory matrix descriptor (sm_100 UMMA): 128B-swizzled tile
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
-  return d;
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // A_K / B_K: operand is K-major (contraction index contiguous in global memory) or MN-major.
 template <bool A_K, bool B_K>
@@ -244,11 +190,7 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int64_t rows, int
   *reinterpret_cast<uint2*>(planes + plane_elems + r * ldo + c) = *reinterpret_cast<uint2*>(l);
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
+EncodeTiledFn tensor_map_encoder() {
   static EncodeTiledFn fn = nullptr;  // immutable after first successful lookup
   if (!fn) {
     void* p = nullptr;
@@ -260,19 +202,23 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// planes: bf16 [2][rows][cols] row-major.  kmajor: box {64 cols(k), 128 rows};  mn-major: box {64 cols(mn), 64 rows(k)}
-static int make_map(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, bool kmajor) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return set_err(DGCNN_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled unavailable");
+int make_plane_map(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = tensor_map_encoder();
+  if (!fn) return set_err(DGCNN_ERR_CUDA, "tensor map: cuTensorMapEncodeTiled unavailable");
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
   cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * (cuuint64_t)cols * 2};
-  cuuint32_t box[3] = {64, kmajor ? 128u : 64u, 1};
+  cuuint32_t box[3] = {64, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(planes), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_err(DGCNN_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  if (r != CUDA_SUCCESS) return set_err(DGCNN_ERR_CUDA, "tensor map: cuTensorMapEncodeTiled failed (%d)", (int)r);
   return DGCNN_OK;
+}
+
+// kmajor: box {64 cols(k), 128 rows};  mn-major: box {64 cols(mn), 64 rows(k)}
+static int make_map(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, bool kmajor) {
+  return make_plane_map(tm, planes, rows, cols, kmajor ? 128u : 64u);
 }
 
 static int tc_splits(int M, int N, int K) {
@@ -293,6 +239,16 @@ __global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* _
   C[i] = s;
 }
 
+int launch_split_bf16(const float* x, int64_t rows, int cols, int64_t ldx, void* planes, int64_t ldo,
+                      int64_t plane_elems, cudaStream_t st) {
+  const int64_t blocks = (rows * (cols >> 2) + 255) / 256;
+  DG_REQUIRE(blocks > 0 && blocks < (1ll << 31), DGCNN_ERR_UNSUPPORTED, "split_bf16: bad element count");
+  split_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, rows, cols, ldx, (__nv_bfloat16*)planes, ldo, plane_elems);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("split_bf16_kernel");
+  return DGCNN_OK;
+}
+
 }  // namespace dgcnn
 
 using namespace dgcnn;
@@ -305,13 +261,7 @@ extern "C" int dgcnn_split_bf16(const float* x, int64_t rows, int cols, int64_t 
   DG_REQUIRE(ldx >= cols && ldo >= cols && (ldx & 3) == 0 && (ldo & 3) == 0 && (plane_elems & 3) == 0,
              DGCNN_ERR_INVALID, "split_bf16: pitches must be multiples of 4 and >= cols");
   DG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)planes & 7) == 0, DGCNN_ERR_INVALID, "split_bf16: alignment");
-  const int64_t blocks = (rows * (cols >> 2) + 255) / 256;
-  DG_REQUIRE(blocks < (1ll << 31), DGCNN_ERR_UNSUPPORTED, "split_bf16: too many elements");
-  split_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, (__nv_bfloat16*)planes, ldo,
-                                                                        plane_elems);
-  count_launch();
-  DG_CUDA_LAUNCH_CHECK("split_bf16_kernel");
-  return DGCNN_OK;
+  return launch_split_bf16(x, rows, cols, ldx, planes, ldo, plane_elems, (cudaStream_t)stream);
 }
 
 extern "C" size_t dgcnn_tc_gemm_workspace_bytes(int M, int N, int K) {

@@ -126,3 +126,34 @@ def test_knn_hint_never_changes_the_result(dg, oracle, cuda):
         far = torch.flip(dg.ops.k_nn(-x, k), dims=[-1])                      # unrelated graph
         for hint in (good, near, rnd, far):
             assert torch.equal(dg.ops.k_nn(x, k, hint=hint), ref)
+
+
+@pytest.mark.parametrize("B,N,C,k", [(2, 700, 64, 20), (3, 2048, 64, 20), (2, 384, 64, 40), (1, 130, 8, 5),
+                                      (2, 1000, 32, 24), (2, 256, 64, 56), (1, 128, 16, 1)])
+def test_knn_tensor_core_path_bit_exact(dg, oracle, cuda, B, N, C, k):
+    """The tcgen05 filter + exact refinement (taken when a hint is given, C % 8 == 0, C <= 64) must reproduce the
+    oracle bit for bit for every kind of hint, including useless ones."""
+    rng = np.random.RandomState(N + C + k)
+    x = torch.from_numpy((rng.randn(B, N, C) * rng.uniform(0.2, 3.0, size=(1, 1, C))).astype(np.float32)).cuda()
+    ref = oracle.k_nn(x.cpu(), k).cuda()
+    near = dg.ops.k_nn(x + 0.05 * torch.randn_like(x), k)
+    rnd = torch.stack([torch.stack([torch.randperm(N)[:k] for _ in range(N)]) for _ in range(B)]).int().cuda()
+    for name, hint in (("exact", ref), ("near", near), ("random", rnd)):
+        got = dg.ops.k_nn(x, k, hint=hint)
+        bad = int((got != ref).sum())
+        assert bad == 0, "%s hint: %d / %d indices differ" % (name, bad, ref.numel())
+
+
+def test_knn_tensor_core_path_ties_fall_back_exactly(dg, oracle, cuda):
+    """Voxel-lattice features and duplicated points: distance ties far beyond the filter's resolution.  Rows that
+    cannot be certified are recomputed by the exact SIMT kernel; the result is still the oracle's."""
+    rng = np.random.RandomState(3)
+    for x in (rng.randint(0, 3, size=(2, 512, 64)).astype(np.float32),          # lattice in 64-d
+              np.repeat(rng.rand(2, 64, 64).astype(np.float32), 8, axis=1),      # every point 8 times
+              np.zeros((1, 300, 64), np.float32)):                              # all identical
+        xc = torch.from_numpy(x).cuda()
+        ref = oracle.k_nn(x, 20).cuda()
+        hint = torch.stack([torch.stack([torch.randperm(x.shape[1])[:20] for _ in range(x.shape[1])])
+                            for _ in range(x.shape[0])]).int().cuda()
+        assert torch.equal(dg.ops.k_nn(xc, 20, hint=ref), ref)
+        assert torch.equal(dg.ops.k_nn(xc, 20, hint=hint), ref)
