@@ -8,7 +8,7 @@
 namespace dgcnn {
 
 constexpr int BN_THREADS = 256;
-constexpr int BN_BLOCKS_PER_SM = 4;
+constexpr int BN_BLOCKS_PER_SM = 2;
 
 static inline int bn_max_blocks() { return num_sms() * BN_BLOCKS_PER_SM; }
 static inline int bn_blocks(int64_t rows) {
@@ -22,7 +22,7 @@ template <int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
     bn_colsum_kernel(const float* __restrict__ z, const float* __restrict__ out, const float* __restrict__ gout,
                      const float* __restrict__ mean, const float* __restrict__ rstd, int relu, int64_t rows, int C,
-                     float* __restrict__ partial) {
+                     float* __restrict__ partial, const float* __restrict__ gbias, int grows) {
   __shared__ float red[2][4][64];
   const int cl = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int c = blockIdx.y * 64 + cl;
@@ -40,14 +40,17 @@ __global__ void __launch_bounds__(BN_THREADS)
     for (int64_t r = rbeg + rg; r < rend; r += 4) {
       const int64_t o = r * C + c;
       if (MODE == 0) {
-        const float v = z[o];
+        float v = z[o];
+        if (gbias) v += gbias[(r / grows) * C + c];
         a += v;
         q = fmaf(v, v, q);
       } else {
         float gp = gout[o];
         if (relu && !(out[o] > 0.f)) gp = 0.f;
         a += gp;
-        q = fmaf(gp, (z[o] - mu) * rs, q);
+        float zv = z[o];
+        if (gbias) zv += gbias[(r / grows) * C + c];
+        q = fmaf(gp, (zv - mu) * rs, q);
       }
     }
   }
@@ -61,32 +64,84 @@ __global__ void __launch_bounds__(BN_THREADS)
   }
 }
 
-__global__ void bn_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mean,
-                                  const float* __restrict__ rstd, const float* __restrict__ beta,
-                                  const float* __restrict__ res, int relu, int64_t total, int C,
-                                  float* __restrict__ out) {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(e % C);
-    float y = fmaf(z[e] - mean[c], rstd[c], beta[c]);
-    if (res) y += res[e];
-    if (relu) y = fmaxf(y, 0.f);
-    out[e] = y;
+// Element-wise passes.  VEC = 4: one thread handles 4 consecutive channels of one row (float4 traffic, one 32-bit
+// division per 4 elements); VEC = 1 is the fallback for C % 4 != 0.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+    bn_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ rstd,
+                      const float* __restrict__ beta, const float* __restrict__ res, int relu, uint32_t nvec, int C,
+                      float* __restrict__ out, const float* __restrict__ gbias, int grows) {
+  const uint32_t cv = (uint32_t)C / VEC;
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
+    const uint32_t r = v / cv;
+    const uint32_t c = (v - r * cv) * VEC;
+    const size_t e = (size_t)r * C + c;
+    float zz[VEC], rr[VEC], gb[VEC], y[VEC];
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(zz) = *reinterpret_cast<const float4*>(z + e);
+      if (res) *reinterpret_cast<float4*>(rr) = *reinterpret_cast<const float4*>(res + e);
+      if (gbias) *reinterpret_cast<float4*>(gb) = *reinterpret_cast<const float4*>(gbias + (size_t)(r / grows) * C + c);
+    } else {
+      zz[0] = z[e];
+      if (res) rr[0] = res[e];
+      if (gbias) gb[0] = gbias[(size_t)(r / grows) * C + c];
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float zv = zz[i];
+      if (gbias) zv += gb[i];
+      float t = fmaf(zv - mean[c + i], rstd[c + i], beta[c + i]);
+      if (res) t += rr[i];
+      y[i] = relu ? fmaxf(t, 0.f) : t;
+    }
+    if (VEC == 4)
+      *reinterpret_cast<float4*>(out + e) = *reinterpret_cast<float4*>(y);
+    else
+      out[e] = y[0];
   }
 }
 
-__global__ void bn_act_bwd_kernel(const float* __restrict__ z, const float* __restrict__ out,
-                                  const float* __restrict__ gout, const float* __restrict__ mean,
-                                  const float* __restrict__ rstd, const float* __restrict__ s1,
-                                  const float* __restrict__ s2, int relu, int64_t total, int C, float inv_rows,
-                                  float* __restrict__ gz, float* __restrict__ gpre) {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(e % C);
-    float gp = gout[e];
-    if (relu && !(out[e] > 0.f)) gp = 0.f;
-    const float rs = rstd[c];
-    const float zh = (z[e] - mean[c]) * rs;
-    gz[e] = rs * (gp - s1[c] * inv_rows - zh * (s2[c] * inv_rows));
-    if (gpre) gpre[e] = gp;
+template <int VEC>
+__global__ void __launch_bounds__(256)
+    bn_act_bwd_kernel(const float* __restrict__ z, const float* __restrict__ out, const float* __restrict__ gout,
+                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ s1,
+                      const float* __restrict__ s2, int relu, uint32_t nvec, int C, float inv_rows,
+                      float* __restrict__ gz, float* __restrict__ gpre, const float* __restrict__ gbias, int grows) {
+  const uint32_t cv = (uint32_t)C / VEC;
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
+    const uint32_t r = v / cv;
+    const uint32_t c = (v - r * cv) * VEC;
+    const size_t e = (size_t)r * C + c;
+    float zz[VEC], oo[VEC], gg[VEC], gb[VEC], gzv[VEC], gpv[VEC];
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(zz) = *reinterpret_cast<const float4*>(z + e);
+      *reinterpret_cast<float4*>(gg) = *reinterpret_cast<const float4*>(gout + e);
+      if (relu) *reinterpret_cast<float4*>(oo) = *reinterpret_cast<const float4*>(out + e);
+      if (gbias) *reinterpret_cast<float4*>(gb) = *reinterpret_cast<const float4*>(gbias + (size_t)(r / grows) * C + c);
+    } else {
+      zz[0] = z[e];
+      gg[0] = gout[e];
+      if (relu) oo[0] = out[e];
+      if (gbias) gb[0] = gbias[(size_t)(r / grows) * C + c];
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float gp = gg[i];
+      if (relu && !(oo[i] > 0.f)) gp = 0.f;
+      const float rs = rstd[c + i];
+      float zv = zz[i];
+      if (gbias) zv += gb[i];
+      const float zh = (zv - mean[c + i]) * rs;
+      gzv[i] = rs * (gp - s1[c + i] * inv_rows - zh * (s2[c + i] * inv_rows));
+      gpv[i] = gp;
+    }
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(gz + e) = *reinterpret_cast<float4*>(gzv);
+      if (gpre) *reinterpret_cast<float4*>(gpre + e) = *reinterpret_cast<float4*>(gpv);
+    } else {
+      gz[e] = gzv[0];
+      if (gpre) gpre[e] = gpv[0];
+    }
   }
 }
 
@@ -121,19 +176,35 @@ extern "C" size_t dgcnn_bn_workspace_bytes(int C) {
 extern "C" int dgcnn_bn_act_fwd(const float* z, int64_t rows, int C, const float* beta, const float* residual,
                                 int relu, float* out, float* mean, float* rstd, void* ws, size_t ws_bytes,
                                 dgcnn_stream_t stream) {
+  return dgcnn_bn_act_fwd_gb(z, rows, C, beta, residual, nullptr, 0, relu, out, mean, rstd, ws, ws_bytes, stream);
+}
+
+extern "C" int dgcnn_bn_act_fwd_gb(const float* z, int64_t rows, int C, const float* beta, const float* residual,
+                                   const float* group_bias, int group_rows, int relu, float* out, float* mean,
+                                   float* rstd, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
+  DG_REQUIRE(!group_bias || (group_rows > 0 && rows % group_rows == 0), DGCNN_ERR_INVALID,
+             "bn_act_fwd: rows=%lld is not a multiple of group_rows=%d", (long long)rows, group_rows);
   DG_REQUIRE(z && beta && out && mean && rstd && ws, DGCNN_ERR_INVALID, "bn_act_fwd: null pointer");
   DG_REQUIRE(rows > 0 && C > 0, DGCNN_ERR_INVALID, "bn_act_fwd: bad shape rows=%lld C=%d", (long long)rows, C);
   DG_REQUIRE(ws_bytes >= dgcnn_bn_workspace_bytes(C), DGCNN_ERR_WORKSPACE, "bn_act_fwd: workspace");
   cudaStream_t st = (cudaStream_t)stream;
   const int nb = bn_blocks(rows);
   dim3 grid(nb, cdiv(C, 64));
-  bn_colsum_kernel<0><<<grid, BN_THREADS, 0, st>>>(z, nullptr, nullptr, nullptr, nullptr, 0, rows, C, (float*)ws);
+  bn_colsum_kernel<0><<<grid, BN_THREADS, 0, st>>>(z, nullptr, nullptr, nullptr, nullptr, 0, rows, C, (float*)ws,
+                                                   group_bias, group_rows);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_colsum_kernel<0>");
   int rc = launch_finalize_stats((const float*)ws, nb, C, (double)rows, 1e-3f, mean, rstd, st);
   if (rc) return rc;
   const int64_t total = rows * C;
-  bn_act_fwd_kernel<<<ew_blocks(total), 256, 0, st>>>(z, mean, rstd, beta, residual, relu, total, C, out);
+  DG_REQUIRE(total < (1ll << 32), DGCNN_ERR_UNSUPPORTED, "bn_act_fwd: more than 2^32 elements");
+  const bool vec = (C & 3) == 0 && (((uintptr_t)z | (uintptr_t)out | (uintptr_t)residual | (uintptr_t)group_bias) & 15) == 0;
+  if (vec)
+    bn_act_fwd_kernel<4><<<ew_blocks(total / 4), 256, 0, st>>>(z, mean, rstd, beta, residual, relu, (uint32_t)(total / 4), C,
+                                                               out, group_bias, group_rows);
+  else
+    bn_act_fwd_kernel<1><<<ew_blocks(total), 256, 0, st>>>(z, mean, rstd, beta, residual, relu, (uint32_t)total, C, out,
+                                                           group_bias, group_rows);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_act_fwd_kernel");
   return DGCNN_OK;
@@ -142,6 +213,16 @@ extern "C" int dgcnn_bn_act_fwd(const float* z, int64_t rows, int C, const float
 extern "C" int dgcnn_bn_act_bwd(const float* z, const float* out, const float* g_out, int64_t rows, int C,
                                 const float* mean, const float* rstd, int relu, float* g_z, float* g_beta,
                                 float* g_pre, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
+  return dgcnn_bn_act_bwd_gb(z, out, g_out, rows, C, mean, rstd, nullptr, 0, relu, g_z, g_beta, g_pre, ws, ws_bytes,
+                             stream);
+}
+
+extern "C" int dgcnn_bn_act_bwd_gb(const float* z, const float* out, const float* g_out, int64_t rows, int C,
+                                   const float* mean, const float* rstd, const float* group_bias, int group_rows,
+                                   int relu, float* g_z, float* g_beta, float* g_pre, void* ws, size_t ws_bytes,
+                                   dgcnn_stream_t stream) {
+  DG_REQUIRE(!group_bias || (group_rows > 0 && rows % group_rows == 0), DGCNN_ERR_INVALID,
+             "bn_act_bwd: rows=%lld is not a multiple of group_rows=%d", (long long)rows, group_rows);
   DG_REQUIRE(z && g_out && mean && rstd && g_z && g_beta && ws, DGCNN_ERR_INVALID, "bn_act_bwd: null pointer");
   DG_REQUIRE(!relu || out, DGCNN_ERR_INVALID, "bn_act_bwd: relu backward needs the forward output");
   DG_REQUIRE(rows > 0 && C > 0, DGCNN_ERR_INVALID, "bn_act_bwd: bad shape rows=%lld C=%d", (long long)rows, C);
@@ -151,14 +232,23 @@ extern "C" int dgcnn_bn_act_bwd(const float* z, const float* out, const float* g
   float* partial = (float*)ws;
   float* s2 = partial + (size_t)bn_max_blocks() * 2 * C;
   dim3 grid(nb, cdiv(C, 64));
-  bn_colsum_kernel<1><<<grid, BN_THREADS, 0, st>>>(z, out, g_out, mean, rstd, relu, rows, C, partial);
+  bn_colsum_kernel<1><<<grid, BN_THREADS, 0, st>>>(z, out, g_out, mean, rstd, relu, rows, C, partial, group_bias,
+                                                   group_rows);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_colsum_kernel<1>");
   int rc = launch_finalize_sums(partial, nb, C, g_beta, s2, st);
   if (rc) return rc;
   const int64_t total = rows * C;
-  bn_act_bwd_kernel<<<ew_blocks(total), 256, 0, st>>>(z, out, g_out, mean, rstd, g_beta, s2, relu, total, C,
-                                                      1.0f / (float)rows, g_z, g_pre);
+  DG_REQUIRE(total < (1ll << 32), DGCNN_ERR_UNSUPPORTED, "bn_act_bwd: more than 2^32 elements");
+  const bool vec = (C & 3) == 0 && (((uintptr_t)z | (uintptr_t)out | (uintptr_t)g_out | (uintptr_t)g_z | (uintptr_t)g_pre |
+                                     (uintptr_t)group_bias) & 15) == 0;
+  if (vec)
+    bn_act_bwd_kernel<4><<<ew_blocks(total / 4), 256, 0, st>>>(z, out, g_out, mean, rstd, g_beta, s2, relu,
+                                                               (uint32_t)(total / 4), C, 1.0f / (float)rows, g_z, g_pre,
+                                                               group_bias, group_rows);
+  else
+    bn_act_bwd_kernel<1><<<ew_blocks(total), 256, 0, st>>>(z, out, g_out, mean, rstd, g_beta, s2, relu, (uint32_t)total, C,
+                                                           1.0f / (float)rows, g_z, g_pre, group_bias, group_rows);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_act_bwd_kernel");
   return DGCNN_OK;

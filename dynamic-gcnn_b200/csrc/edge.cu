@@ -12,7 +12,7 @@ namespace dgcnn {
 
 constexpr int EC_THREADS = 256;          // 8 warps
 constexpr int EC_WARPS = EC_THREADS / 32;
-constexpr int STAT_BLOCKS_PER_SM = 8;
+constexpr int STAT_BLOCKS_PER_SM = 4;
 
 // ------------------------------------------------------------------------------------------ edges()
 __global__ void edge_feature_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx,

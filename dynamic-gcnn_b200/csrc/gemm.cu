@@ -10,7 +10,10 @@ namespace dgcnn {
 
 constexpr int BM = 128, BN = 64, BK = 16, GEMM_THREADS = 256, PADA = 4, PADB = 4;
 
-template <bool TA, bool TB>
+// Global -> register staging of one (BM x BK) A tile and one (BK x BN) B tile.  VEC: 16-byte loads along the
+// contiguous dimension (needs that dimension and the base pointers 4-float aligned); otherwise scalar, fully guarded.
+// Register prefetch: the next k-tile is fetched while the current one is multiplied (one __syncthreads pair per step).
+template <bool TA, bool TB, bool VEC>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
     sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ Cout, int M, int N,
                  int K, int kper) {
@@ -22,46 +25,104 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
   const int kend = min(K, kbeg + kper);
   float* Cp = Cout + (size_t)blockIdx.z * M * N;
 
+  constexpr int A_PER = (BM * BK) / GEMM_THREADS;   // 8 floats per thread
+  constexpr int B_PER = (BN * BK) / GEMM_THREADS;   // 4 floats per thread
+  float ra[A_PER], rb[B_PER];
+
+  auto fetch = [&](int k0) {
+    if (VEC) {
+#pragma unroll
+      for (int i = 0; i < A_PER / 4; ++i) {
+        const int e = tid + i * GEMM_THREADS;            // float4 index
+        int m, k;
+        if (TA) { m = (e % (BM / 4)) * 4; k = e / (BM / 4); } else { k = (e % (BK / 4)) * 4; m = e / (BK / 4); }
+        const int gm = m0 + m, gk = k0 + k;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (TA) { if (gk < kend && gm < M) v = __ldg(reinterpret_cast<const float4*>(A + (size_t)gk * M + gm)); }
+        else    { if (gm < M && gk < kend) v = __ldg(reinterpret_cast<const float4*>(A + (size_t)gm * K + gk)); }
+        ra[i * 4 + 0] = v.x; ra[i * 4 + 1] = v.y; ra[i * 4 + 2] = v.z; ra[i * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < B_PER / 4; ++i) {
+        const int e = tid + i * GEMM_THREADS;
+        int n, k;
+        if (TB) { k = (e % (BK / 4)) * 4; n = e / (BK / 4); } else { n = (e % (BN / 4)) * 4; k = e / (BN / 4); }
+        const int gn = n0 + n, gk = k0 + k;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (TB) { if (gn < N && gk < kend) v = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)gn * K + gk)); }
+        else    { if (gk < kend && gn < N) v = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)gk * N + gn)); }
+        rb[i * 4 + 0] = v.x; rb[i * 4 + 1] = v.y; rb[i * 4 + 2] = v.z; rb[i * 4 + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < A_PER; ++i) {
+        const int e = tid + i * GEMM_THREADS;
+        int m, k;
+        if (TA) { m = e & (BM - 1); k = e / BM; } else { k = e & (BK - 1); m = e / BK; }
+        const int gm = m0 + m, gk = k0 + k;
+        ra[i] = (gm < M && gk < kend) ? (TA ? __ldg(A + (size_t)gk * M + gm) : __ldg(A + (size_t)gm * K + gk)) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < B_PER; ++i) {
+        const int e = tid + i * GEMM_THREADS;
+        int n, k;
+        if (TB) { k = e & (BK - 1); n = e / BK; } else { n = e & (BN - 1); k = e / BN; }
+        const int gn = n0 + n, gk = k0 + k;
+        rb[i] = (gn < N && gk < kend) ? (TB ? __ldg(Bm + (size_t)gn * K + gk) : __ldg(Bm + (size_t)gk * N + gn)) : 0.f;
+      }
+    }
+  };
+  auto stash = [&]() {
+    if (VEC) {
+#pragma unroll
+      for (int i = 0; i < A_PER / 4; ++i) {
+        const int e = tid + i * GEMM_THREADS;
+        if (TA) {
+          const int m = (e % (BM / 4)) * 4, k = e / (BM / 4);
+          *reinterpret_cast<float4*>(&As[k][m]) = make_float4(ra[i * 4], ra[i * 4 + 1], ra[i * 4 + 2], ra[i * 4 + 3]);
+        } else {
+          const int k = (e % (BK / 4)) * 4, m = e / (BK / 4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) As[k + j][m] = ra[i * 4 + j];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < B_PER / 4; ++i) {
+        const int e = tid + i * GEMM_THREADS;
+        if (TB) {
+          const int k = (e % (BK / 4)) * 4, n = e / (BK / 4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) Bs[k + j][n] = rb[i * 4 + j];
+        } else {
+          const int n = (e % (BN / 4)) * 4, k = e / (BN / 4);
+          *reinterpret_cast<float4*>(&Bs[k][n]) = make_float4(rb[i * 4], rb[i * 4 + 1], rb[i * 4 + 2], rb[i * 4 + 3]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < A_PER; ++i) {
+        const int e = tid + i * GEMM_THREADS;
+        if (TA) As[e / BM][e & (BM - 1)] = ra[i]; else As[e & (BK - 1)][e / BK] = ra[i];
+      }
+#pragma unroll
+      for (int i = 0; i < B_PER; ++i) {
+        const int e = tid + i * GEMM_THREADS;
+        if (TB) Bs[e & (BK - 1)][e / BK] = rb[i]; else Bs[e / BN][e & (BN - 1)] = rb[i];
+      }
+    }
+  };
+
   float acc[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
+  if (kbeg < kend) fetch(kbeg);
   for (int k0 = kbeg; k0 < kend; k0 += BK) {
-#pragma unroll
-    for (int i = 0; i < (BM * BK) / GEMM_THREADS; ++i) {
-      const int e = tid + i * GEMM_THREADS;
-      int m, k;
-      if (TA) {
-        m = e & (BM - 1);
-        k = e / BM;
-      } else {
-        k = e & (BK - 1);
-        m = e / BK;
-      }
-      const int gm = m0 + m, gk = k0 + k;
-      float v = 0.0f;
-      if (gm < M && gk < kend) v = TA ? __ldg(A + (size_t)gk * M + gm) : __ldg(A + (size_t)gm * K + gk);
-      As[k][m] = v;
-    }
-#pragma unroll
-    for (int i = 0; i < (BN * BK) / GEMM_THREADS; ++i) {
-      const int e = tid + i * GEMM_THREADS;
-      int n, k;
-      if (TB) {
-        k = e & (BK - 1);
-        n = e / BK;
-      } else {
-        n = e & (BN - 1);
-        k = e / BN;
-      }
-      const int gn = n0 + n, gk = k0 + k;
-      float v = 0.0f;
-      if (gn < N && gk < kend) v = TB ? __ldg(Bm + (size_t)gn * K + gk) : __ldg(Bm + (size_t)gk * N + gn);
-      Bs[k][n] = v;
-    }
+    stash();
     __syncthreads();
+    if (k0 + BK < kend) fetch(k0 + BK);          // overlaps with the FMAs below
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
@@ -141,14 +202,20 @@ extern "C" int dgcnn_gemm(const float* A, const float* B, float* C, int M, int N
   kper = cdiv(kper, BK) * BK;
   dim3 grid(cdiv(N, BN), cdiv(M, BM), splits);
   DG_REQUIRE(grid.y <= 65535, DGCNN_ERR_UNSUPPORTED, "gemm: M=%d too large for grid.y", M);
-  if (transA && transB)
-    sgemm_kernel<true, true><<<grid, GEMM_THREADS, 0, st>>>(A, B, out, M, N, K, kper);
-  else if (transA)
-    sgemm_kernel<true, false><<<grid, GEMM_THREADS, 0, st>>>(A, B, out, M, N, K, kper);
-  else if (transB)
-    sgemm_kernel<false, true><<<grid, GEMM_THREADS, 0, st>>>(A, B, out, M, N, K, kper);
-  else
-    sgemm_kernel<false, false><<<grid, GEMM_THREADS, 0, st>>>(A, B, out, M, N, K, kper);
+  // 16-byte loads need the contiguous dimension of each operand (and kper for k-contiguous ones) 4-float aligned
+  const bool a_ok = transA ? (M & 3) == 0 : ((K & 3) == 0 && (kper & 3) == 0);
+  const bool b_ok = transB ? ((K & 3) == 0 && (kper & 3) == 0) : (N & 3) == 0;
+  const bool vec = a_ok && b_ok && (((uintptr_t)A | (uintptr_t)B) & 15) == 0;
+#define DG_LAUNCH_SGEMM(TA_, TB_)                                                                     \
+  do {                                                                                                \
+    if (vec) sgemm_kernel<TA_, TB_, true><<<grid, GEMM_THREADS, 0, st>>>(A, B, out, M, N, K, kper);   \
+    else sgemm_kernel<TA_, TB_, false><<<grid, GEMM_THREADS, 0, st>>>(A, B, out, M, N, K, kper);      \
+  } while (0)
+  if (transA && transB) DG_LAUNCH_SGEMM(true, true);
+  else if (transA) DG_LAUNCH_SGEMM(true, false);
+  else if (transB) DG_LAUNCH_SGEMM(false, true);
+  else DG_LAUNCH_SGEMM(false, false);
+#undef DG_LAUNCH_SGEMM
   count_launch();
   DG_CUDA_LAUNCH_CHECK("sgemm_kernel");
   if (splits > 1) {

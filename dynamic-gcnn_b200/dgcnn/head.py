@@ -27,11 +27,8 @@ def conv_bn_act(srcs: List[torch.Tensor], scope: str, cout: int, trainable: bool
     cin = cg + sum(int(t.shape[1]) for t in srcs)
     w, b = _ops._conv_bn_vars(scope, cin, cout, trainable, srcs[0].device)
     z = _ops.conv1x1(srcs, w[cg:] if cg else w)
-    if cg:
-        gb = _ops._Conv1x1.apply(cloud_feature, w[:cg])                  # [B, cout]: tiny, SIMT
-        B = cloud_feature.shape[0]
-        z = (z.view(B, points_per_cloud, cout) + gb.view(B, 1, cout)).view(B * points_per_cloud, cout)
-    return _ops._BnAct.apply(z, b, None, activation is not None)
+    gb = _ops._Conv1x1.apply(cloud_feature, w[:cg]) if cg else None      # [B, cout]: tiny, SIMT; added inside BN
+    return _ops._BnAct.apply(z, b, None, activation is not None, gb)
 
 
 def conv_bn_relu_dense(net: torch.Tensor, scope: str, cout: int, trainable: bool, activation=_ops.relu) -> torch.Tensor:

@@ -308,31 +308,35 @@ class _EdgeConvGather(torch.autograd.Function):
 
 
 class _BnAct(torch.autograd.Function):
-    """slim.batch_norm (train mode, beta only, eps 1e-3) [+ residual] [+ ReLU] on a [P,C] tensor."""
+    """slim.batch_norm (train mode, beta only, eps 1e-3) [+ residual] [+ ReLU] on a [P,C] tensor.
+    group_bias [G,C] (optional) is added to the rows of group r // (P/G) before the statistics."""
 
     @staticmethod
-    def forward(ctx, z, beta, residual, relu_flag):
+    def forward(ctx, z, beta, residual, relu_flag, group_bias=None):
         z = nv.require_cuda(z, "z")
         beta = nv.require_cuda(beta, "beta")
         res = nv.require_cuda(residual, "residual") if residual is not None else None
+        gb = nv.require_cuda(group_bias, "group_bias") if group_bias is not None else None
         P, C = z.shape
+        grows = P // gb.shape[0] if gb is not None else 0
         dev = z.device
         L = nv.lib()
         ws = nv.workspace(dev, L.dgcnn_bn_workspace_bytes(C), "stats")
         out = torch.empty_like(z)
         mean = torch.empty(C, dtype=torch.float32, device=dev)
         rstd = torch.empty(C, dtype=torch.float32, device=dev)
-        nv.check(L.dgcnn_bn_act_fwd(z.data_ptr(), P, C, beta.data_ptr(), nv.ptr(res), int(bool(relu_flag)),
-                                    out.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(), ws.numel(),
-                                    nv.stream_ptr(dev)), "bn_act_fwd")
-        ctx.save_for_backward(z, out, mean, rstd)
+        nv.check(L.dgcnn_bn_act_fwd_gb(z.data_ptr(), P, C, beta.data_ptr(), nv.ptr(res), nv.ptr(gb), grows,
+                                       int(bool(relu_flag)), out.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), nv.stream_ptr(dev)), "bn_act_fwd")
+        ctx.save_for_backward(z, out, mean, rstd, gb)
         ctx.relu = bool(relu_flag)
         ctx.has_res = res is not None
+        ctx.grows = grows
         return out
 
     @staticmethod
     def backward(ctx, g):
-        z, out, mean, rstd = ctx.saved_tensors
+        z, out, mean, rstd, gb = ctx.saved_tensors
         g = nv.require_cuda(g, "grad")
         P, C = z.shape
         dev = z.device
@@ -341,10 +345,12 @@ class _BnAct(torch.autograd.Function):
         gz = torch.empty_like(z)
         gbeta = torch.empty(C, dtype=torch.float32, device=dev)
         gpre = torch.empty_like(z) if ctx.has_res else None
-        nv.check(L.dgcnn_bn_act_bwd(z.data_ptr(), out.data_ptr(), g.data_ptr(), P, C, mean.data_ptr(),
-                                    rstd.data_ptr(), int(ctx.relu), gz.data_ptr(), gbeta.data_ptr(), nv.ptr(gpre),
-                                    ws.data_ptr(), ws.numel(), nv.stream_ptr(dev)), "bn_act_bwd")
-        return gz, gbeta, gpre, None
+        nv.check(L.dgcnn_bn_act_bwd_gb(z.data_ptr(), out.data_ptr(), g.data_ptr(), P, C, mean.data_ptr(),
+                                       rstd.data_ptr(), nv.ptr(gb), ctx.grows, int(ctx.relu), gz.data_ptr(),
+                                       gbeta.data_ptr(), nv.ptr(gpre), ws.data_ptr(), ws.numel(), nv.stream_ptr(dev)),
+                 "bn_act_bwd")
+        ggb = gz.view(gb.shape[0], ctx.grows, C).sum(dim=1) if gb is not None else None
+        return gz, gbeta, gpre, None, ggb
 
 
 # =============================================================================== variables (slim.conv2d)

@@ -129,6 +129,17 @@ int dgcnn_bn_act_bwd(const float* z, const float* out, const float* g_out, int64
                      const float* mean, const float* rstd, int relu, float* g_z, float* g_beta, float* g_pre,
                      void* ws, size_t ws_bytes, dgcnn_stream_t stream);
 
+/* Same with a per-group additive term: row r gets group_bias[(r / group_rows), :] added to z before the statistics
+ * (the model head's global max-pooled feature, tiled over the N points of each cloud by model.py:80-81, enters the
+ * first FC layer as one [B, C] term instead of a [B*N, 1024] operand).  The gradient of the bias is the per-group
+ * row sum of g_z (done by the caller).                                                                        */
+int dgcnn_bn_act_fwd_gb(const float* z, int64_t rows, int C, const float* beta, const float* residual,
+                        const float* group_bias, int group_rows, int relu, float* out, float* mean, float* rstd,
+                        void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+int dgcnn_bn_act_bwd_gb(const float* z, const float* out, const float* g_out, int64_t rows, int C, const float* mean,
+                        const float* rstd, const float* group_bias, int group_rows, int relu, float* g_z,
+                        float* g_beta, float* g_pre, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+
 /* ---- tf.train.AdamOptimizer update on a flat buffer: trainval.py:17,80 --------------------
  * g' = g*grad_scale; m = b1*m+(1-b1)g'; v = b2*v+(1-b2)g'^2; p -= lr_t*m/(sqrt(v)+eps),
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller (epsilon outside the bias correction). */

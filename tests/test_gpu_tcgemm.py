@@ -80,3 +80,16 @@ def test_tc_gemm_rejects_bad_shapes(dg, cuda):
     x = torch.zeros(64, device=cuda)
     assert nv.lib().dgcnn_tc_gemm(x.data_ptr(), x.data_ptr(), x.data_ptr(), 12, 8, 8, 0, 0, None, 0, None) == nv.ERR_UNSUPPORTED
     assert nv.lib().dgcnn_tc_gemm(None, x.data_ptr(), x.data_ptr(), 8, 8, 8, 0, 0, None, 0, None) == nv.ERR_INVALID
+
+
+@pytest.mark.parametrize("M,N,K", [(130, 70, 33), (256, 128, 64), (49, 8, 1030), (64, 128, 4096), (1000, 64, 128)])
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_simt_gemm_exact_fp32(dg, cuda, M, N, K, tA, tB):
+    """dgcnn_gemm (exact fp32 SIMT, vectorised and scalar paths, split-K) against fp64."""
+    from dgcnn import ops
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn((K, M) if tA else (M, K), generator=g).to(cuda)
+    B = torch.randn((N, K) if tB else (K, N), generator=g).to(cuda)
+    out = ops._gemm_raw(A, B, M, N, K, tA, tB)
+    ref = (A.double().t() if tA else A.double()) @ (B.double().t() if tB else B.double())
+    assert (out.double() - ref).abs().max().item() <= 2e-6 * np.sqrt(K) * max(1.0, ref.abs().max().item())
