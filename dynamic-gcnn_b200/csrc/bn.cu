@@ -158,6 +158,58 @@ __global__ void adam_tf_kernel(float* __restrict__ p, const float* __restrict__ 
   }
 }
 
+// Global max over the points of each cloud (gen_nn_ops.max_pool_v2 with ksize [1,N,1,1], model.py:77) and its
+// gradient (MaxPoolGrad routes to the arg-max; exact ties share the gradient like tf.reduce_max / torch.amax).
+// x [G, rows, C] -> out [G, C], cnt [G, C] = number of points attaining the maximum.
+__global__ void __launch_bounds__(256)
+    group_max_fwd_kernel(const float* __restrict__ x, int rows, int C, float* __restrict__ out, float* __restrict__ cnt) {
+  __shared__ float rm[4][64];
+  __shared__ float rc[4][64];
+  const int cl = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
+  const int g = blockIdx.y;
+  float m = -INFINITY, n = 0.f;
+  if (c < C) {
+    const float* xg = x + (size_t)g * rows * C + c;
+    for (int r = rg; r < rows; r += 4) {
+      const float v = xg[(size_t)r * C];
+      if (v > m) { m = v; n = 1.f; } else if (v == m) n += 1.f;
+    }
+  }
+  rm[rg][cl] = m;
+  rc[rg][cl] = n;
+  __syncthreads();
+  if (rg == 0 && c < C) {
+    for (int i = 1; i < 4; ++i) {
+      const float mi = rm[i][cl], ni = rc[i][cl];
+      if (mi > m) { m = mi; n = ni; } else if (mi == m) n += ni;
+    }
+    out[(size_t)g * C + c] = m;
+    cnt[(size_t)g * C + c] = n;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    group_max_bwd_kernel(const float* __restrict__ x, const float* __restrict__ out, const float* __restrict__ cnt,
+                         const float* __restrict__ gout, int rows, int C, uint32_t nvec, float* __restrict__ gx) {
+  const uint32_t cv = (uint32_t)C / 4;
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
+    const uint32_t r = v / cv;
+    const uint32_t c = (v - r * cv) * 4;
+    const size_t go = (size_t)(r / rows) * C + c;
+    const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)r * C + c);
+    const float4 mv = *reinterpret_cast<const float4*>(out + go);
+    const float4 nv = *reinterpret_cast<const float4*>(cnt + go);
+    const float4 gv = *reinterpret_cast<const float4*>(gout + go);
+    float4 o;
+    o.x = xv.x == mv.x ? gv.x / nv.x : 0.f;
+    o.y = xv.y == mv.y ? gv.y / nv.y : 0.f;
+    o.z = xv.z == mv.z ? gv.z / nv.z : 0.f;
+    o.w = xv.w == mv.w ? gv.w / nv.w : 0.f;
+    *reinterpret_cast<float4*>(gx + (size_t)r * C + c) = o;
+  }
+}
+
 static inline int ew_blocks(int64_t total) {
   int64_t b = (total + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 16;
@@ -261,5 +313,29 @@ extern "C" int dgcnn_adam_tf_step(float* p, const float* g, float* m, float* v, 
   adam_tf_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_t, b1, b2, eps, grad_scale);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("adam_tf_kernel");
+  return DGCNN_OK;
+}
+
+extern "C" int dgcnn_group_max_fwd(const float* x, int groups, int rows, int C, float* out, float* cnt,
+                                   dgcnn_stream_t stream) {
+  DG_REQUIRE(x && out && cnt, DGCNN_ERR_INVALID, "group_max_fwd: null pointer");
+  DG_REQUIRE(groups > 0 && rows > 0 && C > 0 && groups <= 65535, DGCNN_ERR_INVALID, "group_max_fwd: bad shape");
+  dim3 grid(cdiv(C, 64), groups);
+  group_max_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, C, out, cnt);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("group_max_fwd_kernel");
+  return DGCNN_OK;
+}
+
+extern "C" int dgcnn_group_max_bwd(const float* x, const float* out, const float* cnt, const float* g_out, int groups,
+                                   int rows, int C, float* g_x, dgcnn_stream_t stream) {
+  DG_REQUIRE(x && out && cnt && g_out && g_x, DGCNN_ERR_INVALID, "group_max_bwd: null pointer");
+  DG_REQUIRE(groups > 0 && rows > 0 && C > 0 && (C & 3) == 0, DGCNN_ERR_INVALID, "group_max_bwd: bad shape (C %% 4)");
+  const int64_t total = (int64_t)groups * rows * C;
+  DG_REQUIRE(total < (1ll << 32), DGCNN_ERR_UNSUPPORTED, "group_max_bwd: more than 2^32 elements");
+  group_max_bwd_kernel<<<ew_blocks(total / 4), 256, 0, (cudaStream_t)stream>>>(x, out, cnt, g_out, rows, C,
+                                                                               (uint32_t)(total / 4), g_x);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("group_max_bwd_kernel");
   return DGCNN_OK;
 }

@@ -13,20 +13,34 @@
 //   warp 1   : MMA issuer    -- allocates 128 TMEM columns, one elected lane issues tcgen05.mma (M=128,N=128,K=16),
 //                               tcgen05.commit releases ring slots / publishes the accumulator
 //   warps 2-5: epilogue      -- tcgen05.ld 32 lanes x 32 columns, fp32 stores (each warp owns its TMEM sub-partition)
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace dgcnn {
 
-constexpr int GB_M = 128, GB_N = 128, GB_K = 64, G_STAGES = 3, G_THREADS = 192;
+constexpr int GB_M = 128, GB_N = 128, GB_K = 64, G_THREADS = 192;
 constexpr uint32_t TILE_BYTES = GB_M * GB_K * 2;          // 16 KB: one bf16 plane of one operand tile
 constexpr uint32_t STAGE_BYTES = 4 * TILE_BYTES;          // A_hi, A_lo, B_hi, B_lo
-constexpr size_t G_SMEM = (size_t)G_STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr size_t g_smem(int stages) { return (size_t)stages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
 
 // A_K / B_K: operand is K-major (contraction index contiguous in global memory) or MN-major.
-template <bool A_K, bool B_K>
+// Column groups of the output written to separate contiguous buffers (gradients of a multi-source concat operand:
+// each source gets its own [M, width] tensor instead of a strided slice).  Widths are multiples of 32.
+struct OutGroups {
+  int n;
+  int start[32];
+  int width[32];
+  float* ptr[32];
+};
+
+// G_STAGES = 3: deep TMA ring, one CTA per SM (long K).  G_STAGES = 1: 64 KB per CTA so that three CTAs share an SM and
+// overlap each other's load / MMA / epilogue phases (short K, where the epilogue dominates).
+template <bool A_K, bool B_K, int G_STAGES>
 __global__ void __launch_bounds__(G_THREADS, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   float* __restrict__ C, int M, int N, int K, int kblocks_per_split) {
+                   float* __restrict__ C, int M, int N, int K, int kblocks_per_split,
+                   const __grid_constant__ OutGroups og) {
   extern __shared__ unsigned char g_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)g_smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)G_STAGES * STAGE_BYTES);
@@ -149,7 +163,17 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       if (row < M) {
         const int c0 = n0 + ch * 32;
         float* o = Cout + (size_t)row * N + c0;
-        if ((N & 3) == 0 && c0 + 31 < N) {
+        if (og.n > 0) {
+          o = nullptr;
+          for (int g = 0; g < og.n; ++g)
+            if (c0 >= og.start[g] && c0 < og.start[g] + og.width[g])
+              o = og.ptr[g] + (size_t)row * og.width[g] + (c0 - og.start[g]);
+          if (o == nullptr) continue;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(o + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                                            __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        } else if ((N & 3) == 0 && c0 + 31 < N) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
             *reinterpret_cast<float4*>(o + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
@@ -270,8 +294,41 @@ extern "C" size_t dgcnn_tc_gemm_workspace_bytes(int M, int N, int K) {
   return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
 }
 
+static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
+                        int transB, void* ws, size_t ws_bytes, const OutGroups& og, dgcnn_stream_t stream);
+
 extern "C" int dgcnn_tc_gemm(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
                              int transB, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
+  DG_REQUIRE(C, DGCNN_ERR_INVALID, "tc_gemm: null output");
+  OutGroups og;
+  og.n = 0;
+  return tc_gemm_impl(a_planes, b_planes, C, M, N, K, transA, transB, ws, ws_bytes, og, stream);
+}
+
+extern "C" int dgcnn_tc_gemm_grouped(const void* a_planes, const void* b_planes, int M, int N, int K, int transA,
+                                     int transB, int n_groups, const int* starts, const int* widths,
+                                     float* const* outs, dgcnn_stream_t stream) {
+  DG_REQUIRE(n_groups >= 1 && n_groups <= 32 && starts && widths && outs, DGCNN_ERR_INVALID,
+             "tc_gemm_grouped: need 1..32 output groups");
+  DG_REQUIRE(tc_splits(M, N, K) == 1, DGCNN_ERR_UNSUPPORTED, "tc_gemm_grouped: shape would need split-K");
+  OutGroups og;
+  og.n = n_groups;
+  int covered = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    DG_REQUIRE(outs[g] && widths[g] > 0 && (widths[g] & 31) == 0 && (starts[g] & 31) == 0 && starts[g] >= 0 &&
+                   starts[g] + widths[g] <= N && ((uintptr_t)outs[g] & 15) == 0,
+               DGCNN_ERR_INVALID, "tc_gemm_grouped: group %d must be 32-column aligned inside [0,N) and 16-byte aligned", g);
+    og.start[g] = starts[g];
+    og.width[g] = widths[g];
+    og.ptr[g] = outs[g];
+    covered += widths[g];
+  }
+  DG_REQUIRE(covered <= N, DGCNN_ERR_INVALID, "tc_gemm_grouped: groups overlap");
+  return tc_gemm_impl(a_planes, b_planes, outs[0], M, N, K, transA, transB, nullptr, 0, og, stream);
+}
+
+static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
+                        int transB, void* ws, size_t ws_bytes, const OutGroups& og, dgcnn_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DG_REQUIRE(a_planes && b_planes && C, DGCNN_ERR_INVALID, "tc_gemm: null pointer");
   DG_REQUIRE(M > 0 && N > 0 && K > 0, DGCNN_ERR_INVALID, "tc_gemm: bad shape M=%d N=%d K=%d", M, N, K);
@@ -297,22 +354,33 @@ extern "C" int dgcnn_tc_gemm(const void* a_planes, const void* b_planes, float* 
   const int kb = cdiv(K, GB_K);
   const int kper = cdiv(kb, splits);
   dim3 grid(cdiv(M, GB_M), cdiv(N, GB_N), splits);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
-    cudaFuncSetAttribute(tc_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
-    cudaFuncSetAttribute(tc_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
-    cudaFuncSetAttribute(tc_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
-    attr_done = true;
+  static int forced = -1;  // DGCNN_TC_STAGES=1|3 overrides the heuristic (tuning aid)
+  if (forced < 0) {
+    const char* e = getenv("DGCNN_TC_STAGES");
+    forced = e ? atoi(e) : 0;
   }
-  if (a_k && b_k)
-    tc_gemm_kernel<true, true><<<grid, G_THREADS, G_SMEM, st>>>(tmA, tmB, out, M, N, K, kper);
-  else if (a_k && !b_k)
-    tc_gemm_kernel<true, false><<<grid, G_THREADS, G_SMEM, st>>>(tmA, tmB, out, M, N, K, kper);
-  else if (!a_k && !b_k)
-    tc_gemm_kernel<false, false><<<grid, G_THREADS, G_SMEM, st>>>(tmA, tmB, out, M, N, K, kper);
-  else
-    tc_gemm_kernel<false, true><<<grid, G_THREADS, G_SMEM, st>>>(tmA, tmB, out, M, N, K, kper);
+  const int stages = forced == 1 || forced == 3 ? forced : (kper >= 64 ? 3 : 1);
+#define DG_TC_LAUNCH(AK_, BK_, ST_)                                                                          \
+  do {                                                                                                       \
+    static bool done_ = false;                                                                               \
+    if (!done_) {                                                                                            \
+      cudaFuncSetAttribute(tc_gemm_kernel<AK_, BK_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                           (int)g_smem(ST_));                                                                \
+      done_ = true;                                                                                          \
+    }                                                                                                        \
+    tc_gemm_kernel<AK_, BK_, ST_><<<grid, G_THREADS, g_smem(ST_), st>>>(tmA, tmB, out, M, N, K, kper, og);    \
+  } while (0)
+#define DG_TC_LAUNCH_ST(AK_, BK_)          \
+  do {                                     \
+    if (stages == 3) DG_TC_LAUNCH(AK_, BK_, 3); \
+    else DG_TC_LAUNCH(AK_, BK_, 1);        \
+  } while (0)
+  if (a_k && b_k) DG_TC_LAUNCH_ST(true, true);
+  else if (a_k && !b_k) DG_TC_LAUNCH_ST(true, false);
+  else if (!a_k && !b_k) DG_TC_LAUNCH_ST(false, false);
+  else DG_TC_LAUNCH_ST(false, true);
+#undef DG_TC_LAUNCH_ST
+#undef DG_TC_LAUNCH
   count_launch();
   DG_CUDA_LAUNCH_CHECK("tc_gemm_kernel");
   if (splits > 1) {

@@ -36,6 +36,7 @@ SIGNATURES = {
     "dgcnn_split_bf16": (_i, [_vp, _i64, _i, _i64, _vp, _i64, _i64, _vp]),
     "dgcnn_tc_gemm_workspace_bytes": (_sz, [_i, _i, _i]),
     "dgcnn_tc_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "dgcnn_tc_gemm_grouped": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dgcnn_edgeconv_workspace_bytes": (_sz, [_i]),
     "dgcnn_edgeconv_fwd_stats": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dgcnn_edgeconv_fwd_apply": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -46,6 +47,8 @@ SIGNATURES = {
     "dgcnn_bn_act_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dgcnn_bn_act_fwd_gb": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dgcnn_bn_act_bwd_gb": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dgcnn_group_max_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "dgcnn_group_max_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "dgcnn_adam_tf_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _vp]),
 }
 

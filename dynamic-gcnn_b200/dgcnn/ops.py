@@ -238,11 +238,24 @@ class _ConcatConvTC(torch.autograd.Function):
         gw = _tc_gemm_raw(planes, pg, K, Cout, P, 1, 0) if ctx.needs_input_grad[0] else None   # X^T . g
         outs = [gw]
         if any(ctx.needs_input_grad[1:]):
-            gcat = _tc_gemm_raw(pg, pw, P, K, Cout, 0, 1)                                         # g . W^T
-            off = 0
-            for i, c in enumerate(ctx.widths):
-                outs.append(gcat[:, off:off + c] if ctx.needs_input_grad[1 + i] else None)
-                off += c
+            if len(ctx.widths) > 1 and len(ctx.widths) <= 32 and all(c % 32 == 0 for c in ctx.widths) and \
+                    nv.lib().dgcnn_tc_gemm_workspace_bytes(P, K, Cout) == 0:
+                # g . W^T with every source's gradient written to its own dense tensor (no strided slices)
+                import ctypes
+                n = len(ctx.widths)
+                bufs = [torch.empty((P, c), dtype=torch.float32, device=pg.device) for c in ctx.widths]
+                starts = (ctypes.c_int * n)(*[sum(ctx.widths[:i]) for i in range(n)])
+                widths = (ctypes.c_int * n)(*ctx.widths)
+                ptrs = (ctypes.c_void_p * n)(*[b.data_ptr() for b in bufs])
+                nv.check(nv.lib().dgcnn_tc_gemm_grouped(pg.data_ptr(), pw.data_ptr(), P, K, Cout, 0, 1, n, starts, widths,
+                                                        ptrs, nv.stream_ptr(pg.device)), "tc_gemm_grouped")
+                outs += [b if ctx.needs_input_grad[1 + i] else None for i, b in enumerate(bufs)]
+            else:
+                gcat = _tc_gemm_raw(pg, pw, P, K, Cout, 0, 1)                                     # g . W^T
+                off = 0
+                for i, c in enumerate(ctx.widths):
+                    outs.append(gcat[:, off:off + c] if ctx.needs_input_grad[1 + i] else None)
+                    off += c
         else:
             outs += [None] * len(ctx.widths)
         return tuple(outs)
@@ -351,6 +364,38 @@ class _BnAct(torch.autograd.Function):
                  "bn_act_bwd")
         ggb = gz.view(gb.shape[0], ctx.grows, C).sum(dim=1) if gb is not None else None
         return gz, gbeta, gpre, None, ggb
+
+
+class _GroupMax(torch.autograd.Function):
+    """max over the points of each cloud: x [G, rows, C] -> [G, C] (model.py:77)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = nv.require_cuda(x, "x")
+        G, rows, C = x.shape
+        out = torch.empty((G, C), dtype=torch.float32, device=x.device)
+        cnt = torch.empty((G, C), dtype=torch.float32, device=x.device)
+        nv.check(nv.lib().dgcnn_group_max_fwd(x.data_ptr(), G, rows, C, out.data_ptr(), cnt.data_ptr(),
+                                              nv.stream_ptr(x.device)), "group_max_fwd")
+        ctx.save_for_backward(x, out, cnt)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, out, cnt = ctx.saved_tensors
+        G, rows, C = x.shape
+        g = nv.require_cuda(g, "grad")
+        gx = torch.empty_like(x)
+        nv.check(nv.lib().dgcnn_group_max_bwd(x.data_ptr(), out.data_ptr(), cnt.data_ptr(), g.data_ptr(), G, rows, C,
+                                              gx.data_ptr(), nv.stream_ptr(x.device)), "group_max_bwd")
+        return gx
+
+
+def global_max_pool(x: torch.Tensor) -> torch.Tensor:
+    """x [B,N,C] -> [B,C]: hand-written kernels when C % 4 == 0, else torch.amax (same tie semantics)."""
+    if x.shape[-1] % 4 == 0:
+        return _GroupMax.apply(x)
+    return x.amax(dim=1)
 
 
 # =============================================================================== variables (slim.conv2d)

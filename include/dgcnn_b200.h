@@ -90,6 +90,13 @@ size_t dgcnn_tc_gemm_workspace_bytes(int M, int N, int K);
 int dgcnn_tc_gemm(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA, int transB,
                   void* ws, size_t ws_bytes, dgcnn_stream_t stream);
 
+/* Same product, but column ranges [starts[g], starts[g]+widths[g]) of the result go to separate contiguous
+ * [M, widths[g]] buffers outs[g] (host arrays of n_groups <= 32 entries; 32-column aligned ranges).  Used for the
+ * gradient of a multi-source (concatenated) operand: every source receives its own dense gradient tensor.   */
+int dgcnn_tc_gemm_grouped(const void* a_planes, const void* b_planes, int M, int N, int K, int transA, int transB,
+                          int n_groups, const int* starts, const int* widths, float* const* outs,
+                          dgcnn_stream_t stream);
+
 /* ---- fused EdgeConv core: ops.py:45-57 (edges -> conv0 -> BN(train) -> ReLU -> max_k, mean_k)
  * Uses [x_i, x_j - x_i].[Wa;Wb] = x_i.(Wa-Wb) + x_j.Wb: the caller first forms
  * uv[P, 2F] = x[P,C] . [Wa-Wb | Wb] with dgcnn_gemm (P = B*N), so that z_ij = u_i + v_{idx(i,j)}
@@ -139,6 +146,13 @@ int dgcnn_bn_act_fwd_gb(const float* z, int64_t rows, int C, const float* beta, 
 int dgcnn_bn_act_bwd_gb(const float* z, const float* out, const float* g_out, int64_t rows, int C, const float* mean,
                         const float* rstd, const float* group_bias, int group_rows, int relu, float* g_z,
                         float* g_beta, float* g_pre, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+
+/* ---- global max over the points of each cloud: gen_nn_ops.max_pool_v2 ksize [1,N,1,1], model.py:77 ----------
+ * x [groups, rows, C] -> out [groups, C] and cnt [groups, C] (# points attaining the max); the gradient goes to the
+ * arg-max, shared equally among exact ties.                                                                  */
+int dgcnn_group_max_fwd(const float* x, int groups, int rows, int C, float* out, float* cnt, dgcnn_stream_t stream);
+int dgcnn_group_max_bwd(const float* x, const float* out, const float* cnt, const float* g_out, int groups, int rows,
+                        int C, float* g_x, dgcnn_stream_t stream);
 
 /* ---- tf.train.AdamOptimizer update on a flat buffer: trainval.py:17,80 --------------------
  * g' = g*grad_scale; m = b1*m+(1-b1)g'; v = b2*v+(1-b2)g'^2; p -= lr_t*m/(sqrt(v)+eps),

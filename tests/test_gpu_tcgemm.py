@@ -93,3 +93,42 @@ def test_simt_gemm_exact_fp32(dg, cuda, M, N, K, tA, tB):
     out = ops._gemm_raw(A, B, M, N, K, tA, tB)
     ref = (A.double().t() if tA else A.double()) @ (B.double().t() if tB else B.double())
     assert (out.double() - ref).abs().max().item() <= 2e-6 * np.sqrt(K) * max(1.0, ref.abs().max().item())
+
+
+def test_concat_conv_grouped_gradients(dg, cuda):
+    """_ConcatConvTC: forward == conv of the concatenation; every source gets its own dense gradient."""
+    from dgcnn import ops
+    g = torch.Generator(device="cpu").manual_seed(5)
+    P = 2048
+    srcs = [torch.randn((P, c), generator=g).to(cuda).requires_grad_(True) for c in (64, 64, 128, 1024, 32)]
+    w = (torch.randn((sum(t.shape[1] for t in srcs), 256), generator=g) * 0.05).to(cuda).requires_grad_(True)
+    out = ops.conv1x1(srcs, w)
+    cat = torch.cat([t.detach() for t in srcs], 1).double().requires_grad_(True)
+    wd = w.detach().double().requires_grad_(True)
+    ref = cat @ wd
+    assert (out.double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    go = torch.randn((P, 256), generator=g).to(cuda)
+    out.backward(go)
+    ref.backward(go.double())
+    off = 0
+    for t in srcs:
+        c = t.shape[1]
+        assert t.grad.is_contiguous()
+        assert (t.grad.double() - cat.grad[:, off:off + c]).abs().max().item() <= 1e-4 * cat.grad.abs().max().item()
+        off += c
+    assert (w.grad.double() - wd.grad).abs().max().item() <= 1e-4 * wd.grad.abs().max().item()
+
+
+def test_global_max_pool_matches_amax(dg, cuda):
+    from dgcnn import ops
+    x = torch.randn(3, 257, 64, device=cuda)
+    x[:, 5] = x[:, 9]                      # exact ties across points
+    x[0, :, 3] = 0.0                       # a whole channel tied
+    a = x.clone().requires_grad_(True)
+    b = x.clone().requires_grad_(True)
+    ya, yb = ops.global_max_pool(a), b.amax(dim=1)
+    assert torch.equal(ya, yb)
+    w = torch.randn_like(ya)
+    (ya * w).sum().backward()
+    (yb * w).sum().backward()
+    assert torch.allclose(a.grad, b.grad, atol=1e-6)
