@@ -8,7 +8,7 @@
 namespace dgcnn {
 
 constexpr int BN_THREADS = 256;
-constexpr int BN_BLOCKS_PER_SM = 2;
+constexpr int BN_BLOCKS_PER_SM = 8;
 
 static inline int bn_max_blocks() { return num_sms() * BN_BLOCKS_PER_SM; }
 static inline int bn_blocks(int64_t rows) {
@@ -22,7 +22,7 @@ template <int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
     bn_colsum_kernel(const float* __restrict__ z, const float* __restrict__ out, const float* __restrict__ gout,
                      const float* __restrict__ mean, const float* __restrict__ rstd, int relu, int64_t rows, int C,
-                     float* __restrict__ partial, const float* __restrict__ gbias, int grows) {
+                     double* __restrict__ acc, const float* __restrict__ gbias, int grows) {
   __shared__ float red[2][4][64];
   const int cl = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int c = blockIdx.y * 64 + cl;
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(BN_THREADS)
   if (threadIdx.x < 128) {
     const int which = threadIdx.x >> 6;
     const float t = red[which][0][cl] + red[which][1][cl] + red[which][2][cl] + red[which][3][cl];
-    if (ok) partial[((int64_t)blockIdx.x * 2 + which) * C + c] = t;
+    if (ok) atomicAdd(&acc[which * C + c], (double)t);
   }
 }
 
@@ -222,7 +222,7 @@ using namespace dgcnn;
 
 extern "C" size_t dgcnn_bn_workspace_bytes(int C) {
   if (C <= 0) return 0;
-  return ((size_t)bn_max_blocks() * 2 * C + (size_t)C) * sizeof(float);
+  return (size_t)2 * C * sizeof(double) + (size_t)C * sizeof(float);
 }
 
 extern "C" int dgcnn_bn_act_fwd(const float* z, int64_t rows, int C, const float* beta, const float* residual,
@@ -242,11 +242,14 @@ extern "C" int dgcnn_bn_act_fwd_gb(const float* z, int64_t rows, int C, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const int nb = bn_blocks(rows);
   dim3 grid(nb, cdiv(C, 64));
-  bn_colsum_kernel<0><<<grid, BN_THREADS, 0, st>>>(z, nullptr, nullptr, nullptr, nullptr, 0, rows, C, (float*)ws,
+  DG_REQUIRE(((uintptr_t)ws & 7) == 0, DGCNN_ERR_INVALID, "bn_act_fwd: workspace must be 8-byte aligned");
+  int rc = stats_acc_reset(ws, C, st);
+  if (rc) return rc;
+  bn_colsum_kernel<0><<<grid, BN_THREADS, 0, st>>>(z, nullptr, nullptr, nullptr, nullptr, 0, rows, C, (double*)ws,
                                                    group_bias, group_rows);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_colsum_kernel<0>");
-  int rc = launch_finalize_stats((const float*)ws, nb, C, (double)rows, 1e-3f, mean, rstd, st);
+  rc = launch_finalize_stats((const double*)ws, C, (double)rows, 1e-3f, mean, rstd, st);
   if (rc) return rc;
   const int64_t total = rows * C;
   DG_REQUIRE(total < (1ll << 32), DGCNN_ERR_UNSUPPORTED, "bn_act_fwd: more than 2^32 elements");
@@ -281,14 +284,17 @@ extern "C" int dgcnn_bn_act_bwd_gb(const float* z, const float* out, const float
   DG_REQUIRE(ws_bytes >= dgcnn_bn_workspace_bytes(C), DGCNN_ERR_WORKSPACE, "bn_act_bwd: workspace");
   cudaStream_t st = (cudaStream_t)stream;
   const int nb = bn_blocks(rows);
-  float* partial = (float*)ws;
-  float* s2 = partial + (size_t)bn_max_blocks() * 2 * C;
+  DG_REQUIRE(((uintptr_t)ws & 7) == 0, DGCNN_ERR_INVALID, "bn_act_bwd: workspace must be 8-byte aligned");
+  double* acc = (double*)ws;
+  float* s2 = reinterpret_cast<float*>(acc + (size_t)2 * C);
   dim3 grid(nb, cdiv(C, 64));
-  bn_colsum_kernel<1><<<grid, BN_THREADS, 0, st>>>(z, out, g_out, mean, rstd, relu, rows, C, partial, group_bias,
+  int rc = stats_acc_reset(ws, C, st);
+  if (rc) return rc;
+  bn_colsum_kernel<1><<<grid, BN_THREADS, 0, st>>>(z, out, g_out, mean, rstd, relu, rows, C, acc, group_bias,
                                                    group_rows);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_colsum_kernel<1>");
-  int rc = launch_finalize_sums(partial, nb, C, g_beta, s2, st);
+  rc = launch_finalize_sums(acc, C, g_beta, s2, st);
   if (rc) return rc;
   const int64_t total = rows * C;
   DG_REQUIRE(total < (1ll << 32), DGCNN_ERR_UNSUPPORTED, "bn_act_bwd: more than 2^32 elements");

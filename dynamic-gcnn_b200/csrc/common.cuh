@@ -27,10 +27,10 @@ int set_err(int code, const char* fmt, ...);
 
 int num_sms();
 void count_launch(int n = 1);
-// partial [nblk][2][C] (sum, sum of squares) -> mean / rstd, or -> plain sums; fixed order, fp64 (edge.cu)
-int launch_finalize_stats(const float* partial, int nblk, int C, double count, float eps, float* mean, float* rstd,
-                          cudaStream_t st);
-int launch_finalize_sums(const float* partial, int nblk, int C, float* s1, float* s2, cudaStream_t st);
+// per-channel fp64 accumulators acc[2][C] filled by the statistics kernels with atomics (edge.cu)
+int stats_acc_reset(void* ws, int C, cudaStream_t st);
+int launch_finalize_stats(const double* acc, int C, double count, float eps, float* mean, float* rstd, cudaStream_t st);
+int launch_finalize_sums(const double* acc, int C, float* s1, float* s2, cudaStream_t st);
 
 constexpr unsigned FULL = 0xffffffffu;
 

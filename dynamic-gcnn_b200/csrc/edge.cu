@@ -12,7 +12,7 @@ namespace dgcnn {
 
 constexpr int EC_THREADS = 256;          // 8 warps
 constexpr int EC_WARPS = EC_THREADS / 32;
-constexpr int STAT_BLOCKS_PER_SM = 4;
+constexpr int STAT_BLOCKS_PER_SM = 8;
 
 // ------------------------------------------------------------------------------------------ edges()
 __global__ void edge_feature_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx,
@@ -71,7 +71,7 @@ __device__ __forceinline__ int64_t nbr_off(const EcArgs& a, const int (&rows)[2]
 
 // pass 1 forward: zmax, tie count, per-block partial sum / sum of squares
 __global__ void __launch_bounds__(EC_THREADS)
-    ec_fwd_stats_kernel(EcArgs a, float* __restrict__ zmax, float* __restrict__ cnt, float* __restrict__ partial) {
+    ec_fwd_stats_kernel(EcArgs a, float* __restrict__ zmax, float* __restrict__ cnt, double* __restrict__ acc) {
   __shared__ float red[2][EC_WARPS][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int f0 = blockIdx.y * 64 + lane, f1 = f0 + 32;
@@ -105,63 +105,30 @@ __global__ void __launch_bounds__(EC_THREADS)
 #pragma unroll
     for (int w = 0; w < EC_WARPS; ++w) t += red[which][w][c];
     const int f = blockIdx.y * 64 + c;
-    if (f < a.F) partial[((int64_t)blockIdx.x * 2 + which) * a.F + f] = t;
+    if (f < a.F) atomicAdd(&acc[which * a.F + f], (double)t);
   }
 }
 
-// partial [nblk][2][C] -> per-channel totals, fp64, fixed summation order (deterministic for a given grid).
-// Block = 64 channels x 16 block-groups: thread (g, c) adds blocks g, g+16, ... with coalesced 256 B reads, then the
-// 16 group sums are combined in a fixed tree through shared memory.
-constexpr int FIN_G = 16;
-__device__ __forceinline__ bool block_channel_totals(const float* __restrict__ partial, int nblk, int C, double& s,
-                                                     double& q, int& c_out) {
-  __shared__ double red[2][FIN_G][64];
-  const int cl = threadIdx.x & 63, g = threadIdx.x >> 6;
-  const int c = blockIdx.x * 64 + cl;
-  double a = 0.0, b2 = 0.0;
-  if (c < C) {
-#pragma unroll 4
-    for (int b = g; b < nblk; b += FIN_G) {
-      a += (double)partial[((int64_t)b * 2 + 0) * C + c];
-      b2 += (double)partial[((int64_t)b * 2 + 1) * C + c];
-    }
-  }
-  red[0][g][cl] = a;
-  red[1][g][cl] = b2;
-  __syncthreads();
-  if (g != 0 || c >= C) return false;
-  s = 0.0;
-  q = 0.0;
-#pragma unroll
-  for (int i = 0; i < FIN_G; ++i) {
-    s += red[0][i][cl];
-    q += red[1][i][cl];
-  }
-  c_out = c;
-  return true;
-}
-
-__global__ void __launch_bounds__(64 * FIN_G)
-    finalize_stats_kernel(const float* __restrict__ partial, int nblk, int C, double count, float eps,
-                          float* __restrict__ mean, float* __restrict__ rstd) {
-  double s, q;
-  int c;
-  if (!block_channel_totals(partial, nblk, C, s, q, c)) return;
-  const double m = s / count;
-  double var = q / count - m * m;
+// Per-channel totals are accumulated by the statistics kernels with fp64 atomics into acc[2][C] (sum, sum of
+// squares / cross term); fp64 makes the summation order irrelevant at fp32 resolution.  These kernels turn the
+// totals into what the apply passes need.
+__global__ void finalize_stats_kernel(const double* __restrict__ acc, int C, double count, float eps,
+                                      float* __restrict__ mean, float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = acc[c] / count;
+  double var = acc[C + c] / count - m * m;
   if (var < 0.0) var = 0.0;
   mean[c] = (float)m;
   rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-__global__ void __launch_bounds__(64 * FIN_G)
-    finalize_sums_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ s1,
-                         float* __restrict__ s2) {
-  double a, b2;
-  int c;
-  if (!block_channel_totals(partial, nblk, C, a, b2, c)) return;
-  s1[c] = (float)a;
-  s2[c] = (float)b2;
+__global__ void finalize_sums_kernel(const double* __restrict__ acc, int C, float* __restrict__ s1,
+                                     float* __restrict__ s2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  s1[c] = (float)acc[c];
+  s2[c] = (float)acc[C + c];
 }
 
 // pass 2 forward: out_max, out_mean
@@ -210,7 +177,7 @@ __global__ void __launch_bounds__(EC_THREADS)
     ec_bwd_kernel(EcArgs a, const float* __restrict__ zmax, const float* __restrict__ cnt,
                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ beta,
                   const float* __restrict__ gmax, const float* __restrict__ gmean, const float* __restrict__ s1,
-                  const float* __restrict__ s2, float* __restrict__ partial, float* __restrict__ guv) {
+                  const float* __restrict__ s2, double* __restrict__ acc, float* __restrict__ guv) {
   __shared__ float red[2][EC_WARPS][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int f0 = blockIdx.y * 64 + lane, f1 = f0 + 32;
@@ -273,7 +240,7 @@ __global__ void __launch_bounds__(EC_THREADS)
 #pragma unroll
       for (int w = 0; w < EC_WARPS; ++w) t += red[which][w][c];
       const int f = blockIdx.y * 64 + c;
-      if (f < a.F) partial[((int64_t)blockIdx.x * 2 + which) * a.F + f] = t;
+      if (f < a.F) atomicAdd(&acc[which * a.F + f], (double)t);
     }
   }
 }
@@ -285,15 +252,19 @@ __global__ void zero_vhalf_kernel(float* __restrict__ guv, int64_t P, int F) {
   guv[(e / F) * 2 * F + F + (e % F)] = 0.f;
 }
 
-int launch_finalize_stats(const float* partial, int nblk, int C, double count, float eps, float* mean, float* rstd,
-                          cudaStream_t st) {
-  finalize_stats_kernel<<<cdiv(C, 64), 64 * FIN_G, 0, st>>>(partial, nblk, C, count, eps, mean, rstd);
+int stats_acc_reset(void* ws, int C, cudaStream_t st) {
+  if (cudaMemsetAsync(ws, 0, (size_t)2 * C * sizeof(double), st) != cudaSuccess)
+    return set_err(DGCNN_ERR_CUDA, "stats: memset failed");
+  return DGCNN_OK;
+}
+int launch_finalize_stats(const double* acc, int C, double count, float eps, float* mean, float* rstd, cudaStream_t st) {
+  finalize_stats_kernel<<<cdiv(C, 128), 128, 0, st>>>(acc, C, count, eps, mean, rstd);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("finalize_stats_kernel");
   return DGCNN_OK;
 }
-int launch_finalize_sums(const float* partial, int nblk, int C, float* s1, float* s2, cudaStream_t st) {
-  finalize_sums_kernel<<<cdiv(C, 64), 64 * FIN_G, 0, st>>>(partial, nblk, C, s1, s2);
+int launch_finalize_sums(const double* acc, int C, float* s1, float* s2, cudaStream_t st) {
+  finalize_sums_kernel<<<cdiv(C, 128), 128, 0, st>>>(acc, C, s1, s2);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("finalize_sums_kernel");
   return DGCNN_OK;
@@ -304,7 +275,6 @@ static inline int stat_blocks(int P) {
   const int need = cdiv(P, EC_WARPS);
   return nb < need ? nb : need;
 }
-static inline int max_stat_blocks() { return num_sms() * STAT_BLOCKS_PER_SM; }
 
 static int ec_check(const float* uv, const int32_t* idx, int B, int N, int F, int k) {
   DG_REQUIRE(uv && idx, DGCNN_ERR_INVALID, "edgeconv: null pointer");
@@ -350,7 +320,7 @@ extern "C" int dgcnn_edge_feature_bwd(const float* g_out, const int32_t* idx, fl
 
 extern "C" size_t dgcnn_edgeconv_workspace_bytes(int F) {
   if (F <= 0) return 0;
-  return (size_t)max_stat_blocks() * 2 * F * sizeof(float);
+  return (size_t)2 * F * sizeof(double);
 }
 
 extern "C" int dgcnn_edgeconv_fwd_stats(const float* uv, const int32_t* idx, int B, int N, int F, int k, float* zmax,
@@ -364,10 +334,13 @@ extern "C" int dgcnn_edgeconv_fwd_stats(const float* uv, const int32_t* idx, int
   EcArgs a{uv, idx, B * N, N, F, k};
   const int nb = stat_blocks(a.P);
   dim3 grid(nb, cdiv(F, 64));
-  ec_fwd_stats_kernel<<<grid, EC_THREADS, 0, st>>>(a, zmax, cnt, (float*)ws);
+  DG_REQUIRE(((uintptr_t)ws & 7) == 0, DGCNN_ERR_INVALID, "edgeconv_fwd_stats: workspace must be 8-byte aligned");
+  rc = stats_acc_reset(ws, F, st);
+  if (rc) return rc;
+  ec_fwd_stats_kernel<<<grid, EC_THREADS, 0, st>>>(a, zmax, cnt, (double*)ws);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("ec_fwd_stats_kernel");
-  return launch_finalize_stats((const float*)ws, nb, F, (double)a.P * (double)k, 1e-3f, mean, rstd, st);
+  return launch_finalize_stats((const double*)ws, F, (double)a.P * (double)k, 1e-3f, mean, rstd, st);
 }
 
 extern "C" int dgcnn_edgeconv_fwd_apply(const float* uv, const int32_t* idx, int B, int N, int F, int k,
@@ -398,11 +371,14 @@ extern "C" int dgcnn_edgeconv_bwd_stats(const float* uv, const int32_t* idx, int
   EcArgs a{uv, idx, B * N, N, F, k};
   const int nb = stat_blocks(a.P);
   dim3 grid(nb, cdiv(F, 64));
+  DG_REQUIRE(((uintptr_t)ws & 7) == 0, DGCNN_ERR_INVALID, "edgeconv_bwd_stats: workspace must be 8-byte aligned");
+  rc = stats_acc_reset(ws, F, st);
+  if (rc) return rc;
   ec_bwd_kernel<false><<<grid, EC_THREADS, 0, st>>>(a, zmax, cnt, mean, rstd, beta, g_max, g_mean, nullptr, nullptr,
-                                                     (float*)ws, nullptr);
+                                                     (double*)ws, nullptr);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("ec_bwd_kernel<stats>");
-  return launch_finalize_sums((const float*)ws, nb, F, s1, s2, st);
+  return launch_finalize_sums((const double*)ws, F, s1, s2, st);
 }
 
 extern "C" int dgcnn_edgeconv_bwd_apply(const float* uv, const int32_t* idx, int B, int N, int F, int k,

@@ -35,6 +35,9 @@ constexpr int KT_CHK = 8;         // columns between drain checks
 constexpr int KT_LW = 32;         // list width per (row, column half)
 constexpr int KT_RH = 2 * KT_ROWS;  // (row, half) records
 constexpr float KT_EPS = 1.0f / 2048.0f;
+// Fast test: lower bound <= U  <=>  a(1-EPS) - 2g <= U  <=>  g - 0.5(1-EPS)s_j >= 0.5((1-EPS)s_i - U).  Evaluated with a
+// slightly smaller (1-EPS) factor and a relative slack so that fp32 reassociation can only ADMIT more, never fewer.
+constexpr float KT_HALF1ME = 0.5f * (1.0f - 1.0f / 2048.0f) * (1.0f - 1.0f / 1048576.0f);
 constexpr uint32_t KT_TILE = KT_ROWS * 64 * 2;  // one bf16 plane tile, 16 KB
 
 // byte offsets into the (1024-aligned) dynamic shared memory
@@ -48,7 +51,8 @@ constexpr size_t KT_LJ_OFF = KT_LD_OFF + (size_t)KT_RH * KT_LW * 4;
 constexpr size_t KT_TAUD_OFF = KT_LJ_OFF + (size_t)KT_RH * KT_LW * 4;
 constexpr size_t KT_TAUJ_OFF = KT_TAUD_OFF + KT_RH * 4;
 constexpr size_t KT_SB_OFF = KT_TAUJ_OFF + KT_RH * 4;                // 2 x 128 column norms
-constexpr size_t KT_BAR_OFF = KT_SB_OFF + 2 * KT_COLS * 4;
+constexpr size_t KT_HB_OFF = KT_SB_OFF + 2 * KT_COLS * 4;                // 2 x 128 pre-scaled column norms
+constexpr size_t KT_BAR_OFF = KT_HB_OFF + 2 * KT_COLS * 4;
 constexpr size_t KT_SMEM = KT_BAR_OFF + 128;
 
 extern __shared__ __align__(1024) unsigned char kt_smem[];
@@ -92,6 +96,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1)
   float* taud = reinterpret_cast<float*>(kt_smem + KT_TAUD_OFF);
   int* tauj = reinterpret_cast<int*>(kt_smem + KT_TAUJ_OFF);
   float* sB = reinterpret_cast<float*>(kt_smem + KT_SB_OFF);
+  float* hB = reinterpret_cast<float*>(kt_smem + KT_HB_OFF);
   uint64_t* bars = reinterpret_cast<uint64_t*>(kt_smem + KT_BAR_OFF);
   uint64_t* a_full = bars;            // 1
   uint64_t* b_full = bars + 1;        // 2
@@ -193,11 +198,16 @@ __global__ void __launch_bounds__(KT_THREADS, 1)
     for (int t = 0; t < T; ++t) {
       const int st = t & 1;
       // column norms of this tile -> smem (+inf for ragged columns: they then fail every test), then the accumulator
-      if (e < KT_COLS) sB[st * KT_COLS + e] = (t * KT_COLS + e < N) ? sb[t * KT_COLS + e] : __int_as_float(0x7f800000);
+      if (e < KT_COLS) {
+        const float sj = (t * KT_COLS + e < N) ? sb[t * KT_COLS + e] : __int_as_float(0x7f800000);
+        sB[st * KT_COLS + e] = sj;
+        hB[st * KT_COLS + e] = KT_HALF1ME * sj;
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&acc_full[st], (t >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const float* sBt = sB + st * KT_COLS + half * 64;
+      const float* hBt = hB + st * KT_COLS + half * 64;
 #pragma unroll 1
       for (int ch = 0; ch < 2; ++ch) {
         uint32_t v[32];
@@ -205,21 +215,27 @@ __global__ void __launch_bounds__(KT_THREADS, 1)
 #pragma unroll
         for (int hf = 0; hf < 32 / KT_CHK; ++hf) {
           const float uthr = fminf(taud[rh], taud[other]);
-          // branch-free pass mask over KT_CHK columns: lower bound of the distance interval <= threshold
+          // per-row constant of the fast test (conservative: decreased by a relative + absolute slack)
+          const float ci0 = KT_HALF1ME * si - 0.5f * uthr;
+          const float ci = ci0 - (fabsf(ci0) + fabsf(si)) * (1.0f / 524288.0f);
+          const float4 h0 = *reinterpret_cast<const float4*>(hBt + ch * 32 + hf * KT_CHK);
+          const float4 h1 = *reinterpret_cast<const float4*>(hBt + ch * 32 + hf * KT_CHK + 4);
+          const float hh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
           unsigned mask = 0;
 #pragma unroll
-          for (int i = 0; i < KT_CHK; ++i) {
-            const float a = si + sBt[ch * 32 + hf * KT_CHK + i];
-            const float dt = fmaf(-2.0f, __uint_as_float(v[hf * KT_CHK + i]), a);
-            const float lo = fmaf(-KT_EPS, a, dt);
-            mask |= (lo <= uthr) ? (1u << i) : 0u;
-          }
-          if (mask) {   // rare once the threshold is tight
+          for (int i = 0; i < KT_CHK; ++i)
+            mask |= (__uint_as_float(v[hf * KT_CHK + i]) - hh[i] >= ci) ? (1u << i) : 0u;
+          // exact interval test + append, one candidate per lane per iteration (iterations = max popcount in the warp)
+          while (__any_sync(FULL, mask != 0)) {
+            if (mask) {
+              const int i = __ffs(mask) - 1;
+              mask &= mask - 1;
+              float g = __uint_as_float(v[hf * KT_CHK]);
 #pragma unroll
-            for (int i = 0; i < KT_CHK; ++i) {
-              if (mask & (1u << i)) {
-                const float a = si + sBt[ch * 32 + hf * KT_CHK + i];
-                const float dt = fmaf(-2.0f, __uint_as_float(v[hf * KT_CHK + i]), a);
+              for (int q = 1; q < KT_CHK; ++q) g = (i == q) ? __uint_as_float(v[hf * KT_CHK + q]) : g;
+              const float a = si + sBt[ch * 32 + hf * KT_CHK + i];
+              const float dt = fmaf(-2.0f, g, a);
+              if (fmaf(-KT_EPS, a, dt) <= uthr) {
                 qd[rh * KT_QC + cnt] = fmaf(KT_EPS, a, dt);   // upper bound of the interval
                 qj[rh * KT_QC + cnt] = t * KT_COLS + half * 64 + ch * 32 + hf * KT_CHK + i;
                 ++cnt;

@@ -166,6 +166,15 @@ class _Conv1x1(torch.autograd.Function):
         P, Cin = a.shape
         Cout = w.shape[1]
         ga = gw = None
+        if _tc_ok(P, Cin, Cout):
+            # the forward stays exact fp32 (the next layer's kNN is built on it); gradients feed no kNN, so they
+            # take the tensor-core path like every other gradient GEMM of the model
+            pg = _split(g)
+            if ctx.needs_input_grad[0]:
+                ga = _tc_gemm_raw(pg, _split(w), P, Cin, Cout, 0, 1)
+            if ctx.needs_input_grad[1]:
+                gw = _tc_gemm_raw(_split(a), pg, Cin, Cout, P, 1, 0)
+            return ga, gw
         if ctx.needs_input_grad[0]:
             ga = _gemm_raw(g, w, P, Cin, Cout, 0, 1)  # g . W^T
         if ctx.needs_input_grad[1]:
