@@ -382,23 +382,20 @@ static int knn_common(const float* x, int B, int N, int C, void* ws, size_t ws_b
 using namespace dgcnn;
 
 namespace dgcnn {
-int knn_tc_run(const float* x, const float* s, const int32_t* hint, int32_t* idx, int B, int N, int Npad, int C, int k,
-               void* extra, int32_t** flags_out, cudaStream_t st);
-size_t knn_tc_extra_bytes(int B, int N, int C);
+// knn_tc.cu: tensor-core filter + exact refinement
+bool knn_tc_eligible(int B, int N, int C, int k);
+size_t knn_tc_bytes(int B, int N, int C, int k_max);
+int knn_tc_run(const float* x, int32_t* idx, int B, int N, int C, int k, void* ws, cudaStream_t st);
 static inline size_t knn_base_bytes(int B, int N, int C) {
   const size_t Npad = npad_of(N);
   return ((((size_t)B * C * Npad + (size_t)B * Npad) * sizeof(float)) + 255) & ~(size_t)255;
-}
-// the tensor-core filter needs a warm start, 16-byte rows of at most one 64-wide k-block, and list slack over k
-static inline bool knn_tc_eligible(const int32_t* hint, int N, int C, int k) {
-  return hint != nullptr && (C & 7) == 0 && C >= 8 && C <= 64 && k <= 24 && N >= 128;
 }
 }  // namespace dgcnn
 
 extern "C" size_t dgcnn_knn_workspace_bytes(int B, int N, int C) {
   if (B <= 0 || N <= 0 || C <= 0) return 0;
   size_t n = knn_base_bytes(B, N, C);
-  if ((C & 7) == 0 && C >= 8 && C <= 64 && N >= 128) n += knn_tc_extra_bytes(B, N, C);
+  if (knn_tc_eligible(B, N, C, 1)) n += knn_tc_bytes(B, N, C, 48);
   return n;
 }
 
@@ -429,20 +426,21 @@ extern "C" int dgcnn_knn_hinted(const float* x, const int32_t* hint, int32_t* id
   DG_REQUIRE(idx, DGCNN_ERR_INVALID, "knn: null output");
   DG_REQUIRE(k >= 1 && k <= N, DGCNN_ERR_INVALID, "knn: need 1 <= k <= N (k=%d, N=%d)", k, N);
   DG_REQUIRE(k <= DGCNN_KNN_MAX_K, DGCNN_ERR_UNSUPPORTED, "knn: k=%d > %d", k, DGCNN_KNN_MAX_K);
+  if (knn_tc_eligible(B, N, C, k)) {
+    // tensor-core filter + exact refinement (knn_tc.cu); the warm start is not needed on this path
+    DG_REQUIRE(x && ws, DGCNN_ERR_INVALID, "knn: null pointer");
+    DG_REQUIRE(B > 0 && B <= 65535, DGCNN_ERR_UNSUPPORTED, "knn: B=%d outside [1, 65535]", B);
+    DG_REQUIRE(((uintptr_t)ws & 255) == 0 && ((uintptr_t)x & 15) == 0, DGCNN_ERR_INVALID,
+               "knn: workspace must be 256-byte and x 16-byte aligned");
+    DG_REQUIRE(ws_bytes >= dgcnn_knn_workspace_bytes(B, N, C), DGCNN_ERR_WORKSPACE, "knn: workspace %zu < %zu bytes",
+               ws_bytes, dgcnn_knn_workspace_bytes(B, N, C));
+    return knn_tc_run(x, idx, B, N, C, k, reinterpret_cast<unsigned char*>(ws) + knn_base_bytes(B, N, C), st);
+  }
   float *xT = nullptr, *s = nullptr;
   int Npad = 0;
   int rc = knn_common(x, B, N, C, ws, ws_bytes, st, &xT, &s, &Npad);
   if (rc) return rc;
   const int32_t* rowflags = nullptr;
-  if (knn_tc_eligible(hint, N, C, k)) {
-    // tensor-core filter + exact refinement; the SIMT kernel below then only redoes uncertified rows
-    int32_t* fl = nullptr;
-    rc = knn_tc_run(x, s, hint, idx, B, N, Npad, C, k, reinterpret_cast<unsigned char*>(ws) + knn_base_bytes(B, N, C),
-                    &fl, st);
-    if (rc) return rc;
-    (void)fl;       // uncertified rows were already recomputed exactly by knn_row_fallback_kernel
-    return DGCNN_OK;
-  }
   dim3 g(cdiv(N, TM), B);
   static bool attr_done = false;  // raise the dynamic-smem cap once (idempotent, benign if raced)
   if (!attr_done) {

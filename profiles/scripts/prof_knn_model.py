@@ -28,13 +28,23 @@ for li, (f, h) in enumerate(feats):
     for _ in range(10): idx = ops.k_nn(f, 20, hint=h)
     e1.record(); torch.cuda.synchronize()
     msg = "layer %d C=%d hinted=%s: %.3f ms" % (li, C, h is not None, e0.elapsed_time(e1) / 10)
-    if h is not None and C % 8 == 0:
-        ws = nv._ws_cache[(0, "knn")]
-        Npad = (N + 127) // 128 * 128
-        base = (((B * C * Npad + B * Npad) * 4) + 255) // 256 * 256
-        P = B * N
-        off = base + ((2 * P * C * 2 + 255) // 256 * 256) + ((P * 64 * 4 + 255) // 256 * 256)
-        flags = ws[off:off + P * 4].view(torch.int32)
-        msg += "  uncertified rows: %d of %d" % (int(flags.sum()), P)
-        assert torch.equal(idx, ops.k_nn(f, 20))
     print(msg)
+
+# candidate statistics of the tensor-core filter, read back from the workspace (layout: knn_tc.cu knn_tc_run)
+def al(v): return (v + 255) // 256 * 256
+for li, (f, h) in enumerate(feats):
+    B, N, C = f.shape
+    k = 20
+    idx = ops.k_nn(f, k)
+    torch.cuda.synchronize()
+    ws = nv._ws_cache[(0, "knn")]
+    Npad = (N + 127) // 128 * 128
+    base = al((B * C * Npad + B * Npad) * 4)
+    P, Pp, Cp, cap = B * N, B * Npad, (C + 7) // 8 * 8, 32
+    off = base + 2 * al(Pp * 4) + al(B * C * 4) + al(B * 8) + al(2 * Pp * Cp * 2) + al(Pp * 32) + al(P * 2 * cap * 2)
+    cc = ws[off:off + P * 2].view(P, 2).int()
+    fl = ws[off + al(P * 2):off + al(P * 2) + P * 4].view(torch.int32)
+    tot = cc.sum(1).float()
+    qs = torch.tensor([0.1, 0.5, 0.9, 0.99, 0.999, 1.0], device="cuda")
+    print("layer %d: flagged rows %d; candidates/row mean %.2f q %s; per-half max %d" % (
+        li, int(fl.sum()), tot[fl == 0].mean().item(), torch.quantile(tot[fl == 0], qs).tolist(), int(cc[cc < 255].max())))
