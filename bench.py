@@ -246,7 +246,7 @@ def run_ours(args):
                 "knn_share_of_step": (sum(knn64) + sum(knn3)) / ms_dev}
 
     if rank == 0:
-        cb = cpu_baseline_run(3, 1) if world == 1 else None
+        cb = cpu_baseline_run(3, 1) if (world == 1 and not args.no_cpu_baseline) else None
         line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
@@ -268,6 +268,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

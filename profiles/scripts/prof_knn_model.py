@@ -40,11 +40,12 @@ for li, (f, h) in enumerate(feats):
     ws = nv._ws_cache[(0, "knn")]
     Npad = (N + 127) // 128 * 128
     base = al((B * C * Npad + B * Npad) * 4)
-    P, Pp, Cp, cap = B * N, B * Npad, (C + 7) // 8 * 8, 32
-    off = base + 2 * al(Pp * 4) + al(B * C * 4) + al(B * 8) + al(2 * Pp * Cp * 2) + al(Pp * 32) + al(P * 2 * cap * 2)
-    cc = ws[off:off + P * 2].view(P, 2).int()
-    fl = ws[off + al(P * 2):off + al(P * 2) + P * 4].view(torch.int32)
-    tot = cc.sum(1).float()
+    P, Pp, Cp, cap = B * N, B * Npad, (C + 7) // 8 * 8, 24
+    off = base + 2 * al(Pp * 4) + al(B * 16 * 2 * C * 4) + al(Pp * Cp * 2) + al(2 * Pp * 32) + al(P * 4 * cap * 2)
+    cc = ws[off:off + P * 4].view(P, 4).int()
+    nq = int(ws[off + al(P * 4):off + al(P * 4) + 4].view(torch.int32)[0])
+    ok = (cc < 255).all(1)
+    tot = cc.sum(1).float()[ok]
     qs = torch.tensor([0.1, 0.5, 0.9, 0.99, 0.999, 1.0], device="cuda")
-    print("layer %d: flagged rows %d; candidates/row mean %.2f q %s; per-half max %d" % (
-        li, int(fl.sum()), tot[fl == 0].mean().item(), torch.quantile(tot[fl == 0], qs).tolist(), int(cc[cc < 255].max())))
+    print("layer %d: fallback queue %d (rows %d); candidates/row mean %.2f q %s; per-quarter max %d" % (
+        li, nq, int((~ok).sum()), tot.mean().item(), torch.quantile(tot, qs).tolist(), int(cc[cc < 255].max())))
