@@ -77,8 +77,18 @@ def last_error() -> str:
     return lib().dgcnn_last_error().decode("utf-8", "replace")
 
 
+_replayed_launches = 0
+
+
+def add_replayed_launches(n: int) -> None:
+    """Kernels of this library launched by replaying a captured CUDA graph (the library's own counter only sees
+    the capture)."""
+    global _replayed_launches
+    _replayed_launches += int(n)
+
+
 def launch_count() -> int:
-    return int(lib().dgcnn_launch_count())
+    return int(lib().dgcnn_launch_count()) + _replayed_launches
 
 
 def check(rc: int, what: str) -> None:

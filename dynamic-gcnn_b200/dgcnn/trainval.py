@@ -129,20 +129,69 @@ class trainval(object):
             ops += [float(torch.stack(accs).mean()), float(torch.stack(losses).mean())]
         return ops
 
+    # ------------------------------------------------------------------ CUDA-graph replay of a micro-step
+    # One tower micro-step (forward + backward into the flat gradient buffer) is ~300 kernel launches of a few
+    # microseconds each; issued eagerly the host cannot keep up with the device.  After GRAPH_WARMUP eager runs
+    # with the same input shapes (lazy workspaces and function attributes are then in place) the micro-step is
+    # captured once into a CUDA graph on static input buffers and replayed.  DGCNN_CUDA_GRAPH=0 disables it.
+    GRAPH_WARMUP = 2
+
+    def _as_tensor(self, a):
+        return a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))
+
+    def _tower_step_eager(self, pts, lab, wgt, G):
+        _, acc, loss = self._forward(pts, lab, wgt)
+        (loss / G).backward()                                   # grads mean over towers: trainval.py:64-69
+        return acc.detach(), loss.detach()
+
+    def _tower_step(self, data_i, label_i, weight_i, G):
+        """forward + backward of one tower's micro-batch -> (accuracy, loss) 0-d device tensors."""
+        use_graph = os.environ.get("DGCNN_CUDA_GRAPH", "1") != "0" and label_i is not None
+        src_p = self._as_tensor(data_i)
+        key = (tuple(src_p.shape), weight_i is not None)
+        if not hasattr(self, "_graphs"):
+            self._graphs, self._graph_seen = {}, {}
+        ent = self._graphs.get(key) if use_graph else None
+        if ent is None:
+            pts = self._to_dev(data_i, torch.float32)
+            lab = self._to_dev(label_i, torch.int64)
+            wgt = self._to_dev(weight_i, torch.float32)
+            seen = self._graph_seen.get(key, 0)
+            if not use_graph or seen < self.GRAPH_WARMUP:
+                self._graph_seen[key] = seen + 1
+                return self._tower_step_eager(pts, lab, wgt, G)
+            # capture: static inputs, private memory pool, side stream (torch.cuda.graph does the stream dance)
+            ent = {"pts": pts.clone(), "lab": lab.clone(), "wgt": wgt.clone() if wgt is not None else None}
+            torch.cuda.synchronize(self._device)
+            n0 = nv.launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                acc, loss = self._tower_step_eager(ent["pts"], ent["lab"], ent["wgt"], G)
+            ent.update(graph=graph, acc=acc, loss=loss, launches=nv.launch_count() - n0)
+            self._graphs[key] = ent
+            # a capture records but does not execute: fall through to the replay below
+        else:
+            pass
+        ent["pts"].copy_(src_p, non_blocking=True)
+        ent["lab"].copy_(self._as_tensor(label_i), non_blocking=True)
+        if ent["wgt"] is not None:
+            ent["wgt"].copy_(self._as_tensor(weight_i), non_blocking=True)
+        ent["graph"].replay()
+        nv.add_replayed_launches(ent["launches"])
+        return ent["acc"], ent["loss"]
+
     def accum_gradient(self, sess, data, label, weight=None, summary=False, sync=True):
         """trainval.py:110-119 -> [None, accuracy, loss(, summary)].  Adds this micro-batch's tower-averaged
         gradient into the flat accumulator.  sync=False returns 0-d device tensors instead of floats."""
         if not self._flags.TRAIN:
             raise NotImplementedError
-        feeds = self.feed_dict(data, label, weight)
         G = float(len(self._flags.GPUS))
         accs, losses = [], []
         for i in self._towers:
-            pts, lab, wgt = feeds[i]
-            _, acc, loss = self._forward(pts, lab, wgt)
-            (loss / G).backward()                               # grads mean over towers: trainval.py:64-69
-            accs.append(acc.detach())
-            losses.append(loss.detach())
+            acc, loss = self._tower_step(data[i], label[i] if label is not None else None,
+                                         weight[i] if weight is not None else None, G)
+            accs.append(acc)
+            losses.append(loss)
         if losses:
             acc = torch.stack(accs).mean()
             loss = torch.stack(losses).mean()
