@@ -86,4 +86,18 @@ EncodeTiledFn tensor_map_encoder();
 // bf16 planes [2][rows][cols] row-major -> 3-D map with a {64, box_rows, 1} box, 128B swizzle, zero OOB fill
 int make_plane_map(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, uint32_t box_rows);
 
+// ---- wide (128x256, persistent) GEMM variant: tc_gemm_wide.cu ----
+struct WideOut {
+  float* C;            // [splits][M][N] (splits > 1: partial sums in the workspace)
+  float* colstats;     // [m_tiles][2][N] per-column sum / sum of squares of each 128-row tile, or null
+  int n_groups;        // > 0: column ranges go to separate dense buffers (gradient of a concat operand)
+  int start[32];
+  int width[32];
+  float* ptr[32];
+};
+bool tc_wide_ok(int M, int N, int K);
+int tc_wide_splits(int M, int N, int K);
+int tc_gemm_wide_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, bool a_k, bool b_k, int M, int N, int K,
+                        int splits, const WideOut& out, cudaStream_t st);
+
 }  // namespace dgcnn

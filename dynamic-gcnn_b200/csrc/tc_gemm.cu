@@ -290,19 +290,34 @@ extern "C" int dgcnn_split_bf16(const float* x, int64_t rows, int cols, int64_t 
 
 extern "C" size_t dgcnn_tc_gemm_workspace_bytes(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  const int s = tc_splits(M, N, K);
+  const int s = tc_wide_ok(M, N, K) ? tc_wide_splits(M, N, K) : tc_splits(M, N, K);
   return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
 }
 
 static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
-                        int transB, void* ws, size_t ws_bytes, const OutGroups& og, dgcnn_stream_t stream);
+                        int transB, void* ws, size_t ws_bytes, const OutGroups& og, float* colstats,
+                        dgcnn_stream_t stream);
 
 extern "C" int dgcnn_tc_gemm(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
                              int transB, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
   DG_REQUIRE(C, DGCNN_ERR_INVALID, "tc_gemm: null output");
   OutGroups og;
   og.n = 0;
-  return tc_gemm_impl(a_planes, b_planes, C, M, N, K, transA, transB, ws, ws_bytes, og, stream);
+  return tc_gemm_impl(a_planes, b_planes, C, M, N, K, transA, transB, ws, ws_bytes, og, nullptr, stream);
+}
+
+extern "C" int dgcnn_tc_gemm_stats_supported(int M, int N, int K) {
+  return (tc_wide_ok(M, N, K) && tc_wide_splits(M, N, K) == 1) ? 1 : 0;
+}
+
+extern "C" int dgcnn_tc_gemm_stats(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
+                                   int transB, float* colstats, dgcnn_stream_t stream) {
+  DG_REQUIRE(C && colstats, DGCNN_ERR_INVALID, "tc_gemm_stats: null output");
+  DG_REQUIRE(dgcnn_tc_gemm_stats_supported(M, N, K), DGCNN_ERR_UNSUPPORTED,
+             "tc_gemm_stats: needs N %% 256 == 0, M >= 128 and no k-split (M=%d N=%d K=%d)", M, N, K);
+  OutGroups og;
+  og.n = 0;
+  return tc_gemm_impl(a_planes, b_planes, C, M, N, K, transA, transB, nullptr, 0, og, colstats, stream);
 }
 
 extern "C" int dgcnn_tc_gemm_grouped(const void* a_planes, const void* b_planes, int M, int N, int K, int transA,
@@ -310,7 +325,8 @@ extern "C" int dgcnn_tc_gemm_grouped(const void* a_planes, const void* b_planes,
                                      float* const* outs, dgcnn_stream_t stream) {
   DG_REQUIRE(n_groups >= 1 && n_groups <= 32 && starts && widths && outs, DGCNN_ERR_INVALID,
              "tc_gemm_grouped: need 1..32 output groups");
-  DG_REQUIRE(tc_splits(M, N, K) == 1, DGCNN_ERR_UNSUPPORTED, "tc_gemm_grouped: shape would need split-K");
+  DG_REQUIRE((tc_wide_ok(M, N, K) ? tc_wide_splits(M, N, K) : tc_splits(M, N, K)) == 1, DGCNN_ERR_UNSUPPORTED,
+             "tc_gemm_grouped: shape would need split-K");
   OutGroups og;
   og.n = n_groups;
   int covered = 0;
@@ -324,11 +340,12 @@ extern "C" int dgcnn_tc_gemm_grouped(const void* a_planes, const void* b_planes,
     covered += widths[g];
   }
   DG_REQUIRE(covered <= N, DGCNN_ERR_INVALID, "tc_gemm_grouped: groups overlap");
-  return tc_gemm_impl(a_planes, b_planes, outs[0], M, N, K, transA, transB, nullptr, 0, og, stream);
+  return tc_gemm_impl(a_planes, b_planes, outs[0], M, N, K, transA, transB, nullptr, 0, og, nullptr, stream);
 }
 
 static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
-                        int transB, void* ws, size_t ws_bytes, const OutGroups& og, dgcnn_stream_t stream) {
+                        int transB, void* ws, size_t ws_bytes, const OutGroups& og, float* colstats,
+                        dgcnn_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DG_REQUIRE(a_planes && b_planes && C, DGCNN_ERR_INVALID, "tc_gemm: null pointer");
   DG_REQUIRE(M > 0 && N > 0 && K > 0, DGCNN_ERR_INVALID, "tc_gemm: bad shape M=%d N=%d K=%d", M, N, K);
@@ -344,6 +361,34 @@ static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, in
   if (rc) return rc;
   rc = make_map(&tmB, b_planes, b_k ? N : K, b_k ? K : N, b_k);
   if (rc) return rc;
+  if (tc_wide_ok(M, N, K)) {
+    // 128x256 persistent kernel (tc_gemm_wide.cu)
+    const int wsplits = tc_wide_splits(M, N, K);
+    WideOut wo;
+    wo.C = C;
+    wo.colstats = colstats;
+    wo.n_groups = og.n;
+    for (int g = 0; g < og.n; ++g) {
+      wo.start[g] = og.start[g];
+      wo.width[g] = og.width[g];
+      wo.ptr[g] = og.ptr[g];
+    }
+    if (wsplits > 1) {
+      const size_t need = (size_t)wsplits * M * N * sizeof(float);
+      DG_REQUIRE(ws && ws_bytes >= need, DGCNN_ERR_WORKSPACE, "tc_gemm: workspace %zu < %zu bytes", ws_bytes, need);
+      wo.C = reinterpret_cast<float*>(ws);
+    }
+    rc = tc_gemm_wide_launch(tmA, tmB, a_k, b_k, M, N, K, wsplits, wo, st);
+    if (rc) return rc;
+    if (wsplits > 1) {
+      const int64_t MN = (int64_t)M * N;
+      tc_splitk_reduce_kernel<<<cdiv(MN, 256), 256, 0, st>>>(wo.C, C, MN, wsplits);
+      count_launch();
+      DG_CUDA_LAUNCH_CHECK("tc_splitk_reduce_kernel");
+    }
+    return DGCNN_OK;
+  }
+  DG_REQUIRE(colstats == nullptr, DGCNN_ERR_UNSUPPORTED, "tc_gemm: column statistics need the wide kernel");
   const int splits = tc_splits(M, N, K);
   float* out = C;
   if (splits > 1) {

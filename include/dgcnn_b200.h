@@ -90,6 +90,14 @@ size_t dgcnn_tc_gemm_workspace_bytes(int M, int N, int K);
 int dgcnn_tc_gemm(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA, int transB,
                   void* ws, size_t ws_bytes, dgcnn_stream_t stream);
 
+/* Same product plus, from the accumulator, the per-column sum and sum of squares of every 128-row tile:
+ * colstats [ceil(M/128)][2][N] fp32 (train-mode BatchNorm statistics of the layer output, slim.batch_norm at
+ * ops.py:53,158 / model.py:71, without a second pass over C).  Only for shapes the 128x256 persistent kernel takes
+ * without a k-split (dgcnn_tc_gemm_stats_supported(M,N,K) == 1: N % 256 == 0, M >= 128).                       */
+int dgcnn_tc_gemm_stats_supported(int M, int N, int K);
+int dgcnn_tc_gemm_stats(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
+                        int transB, float* colstats, dgcnn_stream_t stream);
+
 /* Same product, but column ranges [starts[g], starts[g]+widths[g]) of the result go to separate contiguous
  * [M, widths[g]] buffers outs[g] (host arrays of n_groups <= 32 entries; 32-column aligned ranges).  Used for the
  * gradient of a multi-source (concatenated) operand: every source receives its own dense gradient tensor.   */

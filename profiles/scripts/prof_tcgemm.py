@@ -21,8 +21,9 @@ def timeit(fn, n=10):
     return e0.elapsed_time(e1) / n
 
 P = 24 * 2048
-for name, (M, N, K, tA, tB) in {"FC0 fwd": (P, 512, 2816, 0, 0), "FC0 dX": (P, 2816, 512, 0, 1), "FC0 dW": (2816, 512, P, 1, 0),
-                                "Merged fwd": (P, 1024, 256, 0, 0), "FC1 fwd": (P, 256, 512, 0, 0),
+for name, (M, N, K, tA, tB) in {"FC0 fwd": (P, 512, 1792, 0, 0), "FC0 dX": (P, 1792, 512, 0, 1), "FC0 dW": (1792, 512, P, 1, 0),
+                                "Merged fwd": (P, 1024, 256, 0, 0), "Merged dX": (P, 256, 1024, 0, 1), "Merged dW": (256, 1024, P, 1, 0),
+                                "FC1 fwd": (P, 256, 512, 0, 0), "FC1 dX": (P, 512, 256, 0, 1), "FC1 dW": (512, 256, P, 1, 0),
                                 "uv fwd": (P, 128, 64, 0, 0), "uv dW": (64, 128, P, 1, 0)}.items():
     A = torch.randn((K, M) if tA else (M, K), device=dev)
     B = torch.randn((N, K) if tB else (K, N), device=dev)
