@@ -3,6 +3,8 @@
 // /root/reference/dgcnn/ops.py:53,68,131,134 and tf.train.AdamOptimizer (trainval.py:17,80).
 // slim.batch_norm defaults: is_training=True (always -- SURVEY.md section 0), center=True, scale=False,
 // epsilon=1e-3, biased batch variance over every non-channel axis.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace dgcnn {
@@ -106,7 +108,8 @@ __global__ void __launch_bounds__(256)
     bn_act_bwd_kernel(const float* __restrict__ z, const float* __restrict__ out, const float* __restrict__ gout,
                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ s1,
                       const float* __restrict__ s2, int relu, uint32_t nvec, int C, float inv_rows,
-                      float* __restrict__ gz, float* __restrict__ gpre, const float* __restrict__ gbias, int grows) {
+                      float* __restrict__ gz, float* __restrict__ gpre, const float* __restrict__ gbias, int grows,
+                      __nv_bfloat16* __restrict__ gz_planes, size_t plane_elems) {
   const uint32_t cv = (uint32_t)C / VEC;
   for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
     const uint32_t r = v / cv;
@@ -136,10 +139,20 @@ __global__ void __launch_bounds__(256)
       gpv[i] = gp;
     }
     if (VEC == 4) {
-      *reinterpret_cast<float4*>(gz + e) = *reinterpret_cast<float4*>(gzv);
+      if (gz) *reinterpret_cast<float4*>(gz + e) = *reinterpret_cast<float4*>(gzv);
       if (gpre) *reinterpret_cast<float4*>(gpre + e) = *reinterpret_cast<float4*>(gpv);
+      if (gz_planes) {   // the gradient as a tcgen05 operand: bf16 hi / lo planes (tc_gemm.cu), no fp32 round trip
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          h[i] = __float2bfloat16_rn(gzv[i]);
+          l[i] = __float2bfloat16_rn(gzv[i] - __bfloat162float(h[i]));
+        }
+        *reinterpret_cast<uint2*>(gz_planes + e) = *reinterpret_cast<uint2*>(h);
+        *reinterpret_cast<uint2*>(gz_planes + plane_elems + e) = *reinterpret_cast<uint2*>(l);
+      }
     } else {
-      gz[e] = gzv[0];
+      if (gz) gz[e] = gzv[0];
       if (gpre) gpre[e] = gpv[0];
     }
   }
@@ -210,6 +223,75 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// BatchNorm statistics from the per-tile column partials the wide GEMM epilogue leaves behind (tc_gemm_wide.cu):
+// colstats [tiles][2][C] (sum, sum of squares over the 128 rows of each tile) -> mean, rstd.  With a per-group bias
+// (rows of group g get gbias[g] added before the statistics, group_rows % 128 == 0):
+//   sum (z+b) = sum z + group_rows * sum_g b_g ;  sum (z+b)^2 = sum z^2 + 2 sum_g b_g (sum_{tiles of g} sum z) + group_rows sum_g b_g^2
+__global__ void __launch_bounds__(256)
+    bn_tile_stats_kernel(const float* __restrict__ colstats, int tiles, int C, double rows, const float* __restrict__ gbias,
+                         int tiles_per_group, double group_rows, float eps, float* __restrict__ mean,
+                         float* __restrict__ rstd) {
+  __shared__ double r1[8][32], r2[8][32];
+  const int cl = threadIdx.x & 31, tl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double a = 0.0, q = 0.0;
+  if (c < C) {
+    for (int t = tl; t < tiles; t += 8) {
+      const double s1 = (double)colstats[((size_t)t * 2) * C + c];
+      const double s2 = (double)colstats[((size_t)t * 2 + 1) * C + c];
+      a += s1;
+      q += s2;
+      if (gbias) {
+        const double b = (double)gbias[(size_t)(t / tiles_per_group) * C + c];
+        q += 2.0 * b * s1;
+        if (t % tiles_per_group == 0) {
+          a += group_rows * b;
+          q += group_rows * b * b;
+        }
+      }
+    }
+  }
+  r1[tl][cl] = a;
+  r2[tl][cl] = q;
+  __syncthreads();
+  if (tl == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) {
+      a += r1[i][cl];
+      q += r2[i][cl];
+    }
+    const double m = a / rows;
+    double var = q / rows - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)m;
+    rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+// gx += gradient of the group max, in place: only the arg-max positions are touched (everything else of the incoming
+// gradient buffer is left as it is), so the dense [G,rows,C] pooling gradient and its accumulation pass never exist.
+__global__ void __launch_bounds__(256)
+    group_max_bwd_add_kernel(const float* __restrict__ x, const float* __restrict__ out, const float* __restrict__ cnt,
+                             const float* __restrict__ gout, int rows, int C, uint32_t nvec, float* __restrict__ gx) {
+  const uint32_t cv = (uint32_t)C / 4;
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
+    const uint32_t r = v / cv;
+    const uint32_t c = (v - r * cv) * 4;
+    const size_t go = (size_t)(r / rows) * C + c;
+    const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)r * C + c);
+    const float4 mv = *reinterpret_cast<const float4*>(out + go);
+    if (xv.x == mv.x || xv.y == mv.y || xv.z == mv.z || xv.w == mv.w) {
+      const float4 nv = *reinterpret_cast<const float4*>(cnt + go);
+      const float4 gv = *reinterpret_cast<const float4*>(gout + go);
+      float4 o = *reinterpret_cast<float4*>(gx + (size_t)r * C + c);
+      if (xv.x == mv.x) o.x += gv.x / nv.x;
+      if (xv.y == mv.y) o.y += gv.y / nv.y;
+      if (xv.z == mv.z) o.z += gv.z / nv.z;
+      if (xv.w == mv.w) o.w += gv.w / nv.w;
+      *reinterpret_cast<float4*>(gx + (size_t)r * C + c) = o;
+    }
+  }
+}
+
 static inline int ew_blocks(int64_t total) {
   int64_t b = (total + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 16;
@@ -265,6 +347,58 @@ extern "C" int dgcnn_bn_act_fwd_gb(const float* z, int64_t rows, int C, const fl
   return DGCNN_OK;
 }
 
+extern "C" int dgcnn_bn_stats_from_tiles(const float* colstats, int tiles, int C, int64_t rows, const float* group_bias,
+                                         int group_rows, float* mean, float* rstd, dgcnn_stream_t stream) {
+  DG_REQUIRE(colstats && mean && rstd, DGCNN_ERR_INVALID, "bn_stats_from_tiles: null pointer");
+  DG_REQUIRE(tiles > 0 && C > 0 && rows > 0 && (int64_t)tiles * 128 >= rows, DGCNN_ERR_INVALID,
+             "bn_stats_from_tiles: bad shape tiles=%d C=%d rows=%lld", tiles, C, (long long)rows);
+  DG_REQUIRE(!group_bias || (group_rows > 0 && group_rows % 128 == 0 && rows % group_rows == 0), DGCNN_ERR_INVALID,
+             "bn_stats_from_tiles: group_rows=%d must be a multiple of 128 dividing rows", group_rows);
+  bn_tile_stats_kernel<<<cdiv(C, 32), 256, 0, (cudaStream_t)stream>>>(colstats, tiles, C, (double)rows, group_bias,
+                                                                      group_bias ? group_rows / 128 : 1,
+                                                                      (double)group_rows, 1e-3f, mean, rstd);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("bn_tile_stats_kernel");
+  return DGCNN_OK;
+}
+
+extern "C" int dgcnn_bn_apply_fwd(const float* z, int64_t rows, int C, const float* beta, const float* residual,
+                                  const float* group_bias, int group_rows, int relu, const float* mean,
+                                  const float* rstd, float* out, dgcnn_stream_t stream) {
+  DG_REQUIRE(z && beta && out && mean && rstd, DGCNN_ERR_INVALID, "bn_apply_fwd: null pointer");
+  DG_REQUIRE(rows > 0 && C > 0, DGCNN_ERR_INVALID, "bn_apply_fwd: bad shape rows=%lld C=%d", (long long)rows, C);
+  DG_REQUIRE(!group_bias || (group_rows > 0 && rows % group_rows == 0), DGCNN_ERR_INVALID,
+             "bn_apply_fwd: rows=%lld is not a multiple of group_rows=%d", (long long)rows, group_rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = rows * C;
+  DG_REQUIRE(total < (1ll << 32), DGCNN_ERR_UNSUPPORTED, "bn_apply_fwd: more than 2^32 elements");
+  const bool vec = (C & 3) == 0 && (((uintptr_t)z | (uintptr_t)out | (uintptr_t)residual | (uintptr_t)group_bias) & 15) == 0;
+  if (vec)
+    bn_act_fwd_kernel<4><<<ew_blocks(total / 4), 256, 0, st>>>(z, mean, rstd, beta, residual, relu, (uint32_t)(total / 4), C,
+                                                               out, group_bias, group_rows);
+  else
+    bn_act_fwd_kernel<1><<<ew_blocks(total), 256, 0, st>>>(z, mean, rstd, beta, residual, relu, (uint32_t)total, C, out,
+                                                           group_bias, group_rows);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("bn_act_fwd_kernel");
+  return DGCNN_OK;
+}
+
+static int bn_act_bwd_impl(const float* z, const float* out, const float* g_out, int64_t rows, int C, const float* mean,
+                           const float* rstd, const float* group_bias, int group_rows, int relu, float* g_z,
+                           void* g_z_planes, float* g_beta, float* g_pre, void* ws, size_t ws_bytes,
+                           dgcnn_stream_t stream);
+
+extern "C" int dgcnn_bn_act_bwd_planes(const float* z, const float* out, const float* g_out, int64_t rows, int C,
+                                       const float* mean, const float* rstd, const float* group_bias, int group_rows,
+                                       int relu, float* g_z, void* g_z_planes, float* g_beta, void* ws, size_t ws_bytes,
+                                       dgcnn_stream_t stream) {
+  DG_REQUIRE(g_z_planes && (C & 3) == 0 && ((uintptr_t)g_z_planes & 7) == 0, DGCNN_ERR_INVALID,
+             "bn_act_bwd_planes: needs a plane buffer and C %% 4 == 0");
+  return bn_act_bwd_impl(z, out, g_out, rows, C, mean, rstd, group_bias, group_rows, relu, g_z, g_z_planes, g_beta,
+                         nullptr, ws, ws_bytes, stream);
+}
+
 extern "C" int dgcnn_bn_act_bwd(const float* z, const float* out, const float* g_out, int64_t rows, int C,
                                 const float* mean, const float* rstd, int relu, float* g_z, float* g_beta,
                                 float* g_pre, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
@@ -276,9 +410,19 @@ extern "C" int dgcnn_bn_act_bwd_gb(const float* z, const float* out, const float
                                    const float* mean, const float* rstd, const float* group_bias, int group_rows,
                                    int relu, float* g_z, float* g_beta, float* g_pre, void* ws, size_t ws_bytes,
                                    dgcnn_stream_t stream) {
+  DG_REQUIRE(g_z, DGCNN_ERR_INVALID, "bn_act_bwd: null pointer");
+  return bn_act_bwd_impl(z, out, g_out, rows, C, mean, rstd, group_bias, group_rows, relu, g_z, nullptr, g_beta, g_pre,
+                         ws, ws_bytes, stream);
+}
+
+static int bn_act_bwd_impl(const float* z, const float* out, const float* g_out, int64_t rows, int C, const float* mean,
+                           const float* rstd, const float* group_bias, int group_rows, int relu, float* g_z,
+                           void* g_z_planes, float* g_beta, float* g_pre, void* ws, size_t ws_bytes,
+                           dgcnn_stream_t stream) {
   DG_REQUIRE(!group_bias || (group_rows > 0 && rows % group_rows == 0), DGCNN_ERR_INVALID,
              "bn_act_bwd: rows=%lld is not a multiple of group_rows=%d", (long long)rows, group_rows);
-  DG_REQUIRE(z && g_out && mean && rstd && g_z && g_beta && ws, DGCNN_ERR_INVALID, "bn_act_bwd: null pointer");
+  DG_REQUIRE(z && g_out && mean && rstd && (g_z || g_z_planes) && g_beta && ws, DGCNN_ERR_INVALID,
+             "bn_act_bwd: null pointer");
   DG_REQUIRE(!relu || out, DGCNN_ERR_INVALID, "bn_act_bwd: relu backward needs the forward output");
   DG_REQUIRE(rows > 0 && C > 0, DGCNN_ERR_INVALID, "bn_act_bwd: bad shape rows=%lld C=%d", (long long)rows, C);
   DG_REQUIRE(ws_bytes >= dgcnn_bn_workspace_bytes(C), DGCNN_ERR_WORKSPACE, "bn_act_bwd: workspace");
@@ -300,13 +444,16 @@ extern "C" int dgcnn_bn_act_bwd_gb(const float* z, const float* out, const float
   DG_REQUIRE(total < (1ll << 32), DGCNN_ERR_UNSUPPORTED, "bn_act_bwd: more than 2^32 elements");
   const bool vec = (C & 3) == 0 && (((uintptr_t)z | (uintptr_t)out | (uintptr_t)g_out | (uintptr_t)g_z | (uintptr_t)g_pre |
                                      (uintptr_t)group_bias) & 15) == 0;
+  DG_REQUIRE(vec || !g_z_planes, DGCNN_ERR_INVALID, "bn_act_bwd: plane output needs 16-byte aligned buffers, C %% 4 == 0");
   if (vec)
     bn_act_bwd_kernel<4><<<ew_blocks(total / 4), 256, 0, st>>>(z, out, g_out, mean, rstd, g_beta, s2, relu,
                                                                (uint32_t)(total / 4), C, 1.0f / (float)rows, g_z, g_pre,
-                                                               group_bias, group_rows);
+                                                               group_bias, group_rows, (__nv_bfloat16*)g_z_planes,
+                                                               (size_t)total);
   else
     bn_act_bwd_kernel<1><<<ew_blocks(total), 256, 0, st>>>(z, out, g_out, mean, rstd, g_beta, s2, relu, (uint32_t)total, C,
-                                                           1.0f / (float)rows, g_z, g_pre, group_bias, group_rows);
+                                                           1.0f / (float)rows, g_z, g_pre, group_bias, group_rows, nullptr,
+                                                           0);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_act_bwd_kernel");
   return DGCNN_OK;
@@ -343,5 +490,18 @@ extern "C" int dgcnn_group_max_bwd(const float* x, const float* out, const float
                                                                                (uint32_t)(total / 4), g_x);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("group_max_bwd_kernel");
+  return DGCNN_OK;
+}
+
+extern "C" int dgcnn_group_max_bwd_add(const float* x, const float* out, const float* cnt, const float* g_out, int groups,
+                                       int rows, int C, float* g_x_inout, dgcnn_stream_t stream) {
+  DG_REQUIRE(x && out && cnt && g_out && g_x_inout, DGCNN_ERR_INVALID, "group_max_bwd_add: null pointer");
+  DG_REQUIRE(groups > 0 && rows > 0 && C > 0 && (C & 3) == 0, DGCNN_ERR_INVALID, "group_max_bwd_add: bad shape (C %% 4)");
+  const int64_t total = (int64_t)groups * rows * C;
+  DG_REQUIRE(total < (1ll << 32), DGCNN_ERR_UNSUPPORTED, "group_max_bwd_add: more than 2^32 elements");
+  group_max_bwd_add_kernel<<<ew_blocks(total / 4), 256, 0, (cudaStream_t)stream>>>(x, out, cnt, g_out, rows, C,
+                                                                                   (uint32_t)(total / 4), g_x_inout);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("group_max_bwd_add_kernel");
   return DGCNN_OK;
 }

@@ -49,8 +49,12 @@ SIGNATURES = {
     "dgcnn_bn_act_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dgcnn_bn_act_fwd_gb": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dgcnn_bn_act_bwd_gb": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dgcnn_bn_stats_from_tiles": (_i, [_vp, _i, _i, _i64, _vp, _i, _vp, _vp, _vp]),
+    "dgcnn_bn_apply_fwd": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "dgcnn_bn_act_bwd_planes": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dgcnn_group_max_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "dgcnn_group_max_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "dgcnn_group_max_bwd_add": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "dgcnn_adam_tf_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _vp]),
 }
 

@@ -216,6 +216,41 @@ def _tc_gemm_raw(pa, pb, M, N, K, tA, tB):
     return out
 
 
+def _tc_dx_sources(pg, pw, P, K, Cout, widths, needs):
+    """g . W^T for a multi-source (concatenated) operand -> one dense gradient tensor per source."""
+    if not any(needs):
+        return [None] * len(widths)
+    if len(widths) > 1 and len(widths) <= 32 and all(c % 32 == 0 for c in widths) and \
+            nv.lib().dgcnn_tc_gemm_workspace_bytes(P, K, Cout) == 0:
+        import ctypes
+        n = len(widths)
+        bufs = [torch.empty((P, c), dtype=torch.float32, device=pg.device) for c in widths]
+        starts = (ctypes.c_int * n)(*[sum(widths[:i]) for i in range(n)])
+        cw = (ctypes.c_int * n)(*widths)
+        ptrs = (ctypes.c_void_p * n)(*[b.data_ptr() for b in bufs])
+        nv.check(nv.lib().dgcnn_tc_gemm_grouped(pg.data_ptr(), pw.data_ptr(), P, K, Cout, 0, 1, n, starts, cw, ptrs,
+                                                nv.stream_ptr(pg.device)), "tc_gemm_grouped")
+        return [b if needs[i] else None for i, b in enumerate(bufs)]
+    gcat = _tc_gemm_raw(pg, pw, P, K, Cout, 0, 1)                                     # g . W^T
+    outs, off = [], 0
+    for i, c in enumerate(widths):
+        outs.append(gcat[:, off:off + c] if needs[i] else None)
+        off += c
+    return outs
+
+
+def _split_sources(srcs, w):
+    P = srcs[0].shape[0]
+    widths = [int(t.shape[1]) for t in srcs]
+    K = sum(widths)
+    planes = torch.empty((2, P, K), dtype=torch.bfloat16, device=w.device)
+    off = 0
+    for t, c in zip(srcs, widths):
+        _split_into(t, planes, off)
+        off += c
+    return planes, widths, P, K
+
+
 class _ConcatConvTC(torch.autograd.Function):
     """1x1 conv of the channel-concatenation of several [P, c_i] tensors with W [sum c_i, Cout], without building
     the concatenation (model.py:60-63,83-85 + slim.conv2d): each source is split straight into its column slice of
@@ -225,14 +260,8 @@ class _ConcatConvTC(torch.autograd.Function):
     def forward(ctx, w, *srcs):
         w = nv.require_cuda(w, "conv weights")
         srcs = [nv.require_cuda(t, "conv input") for t in srcs]
-        P = srcs[0].shape[0]
-        widths = [int(t.shape[1]) for t in srcs]
-        K, Cout = sum(widths), w.shape[1]
-        planes = torch.empty((2, P, K), dtype=torch.bfloat16, device=w.device)
-        off = 0
-        for t, c in zip(srcs, widths):
-            _split_into(t, planes, off)
-            off += c
+        planes, widths, P, K = _split_sources(srcs, w)
+        Cout = w.shape[1]
         pw = _split(w)
         ctx.save_for_backward(planes, pw)
         ctx.widths = widths
@@ -245,29 +274,72 @@ class _ConcatConvTC(torch.autograd.Function):
         Cout = pw.shape[2]
         pg = _split(nv.require_cuda(g, "grad"))
         gw = _tc_gemm_raw(planes, pg, K, Cout, P, 1, 0) if ctx.needs_input_grad[0] else None   # X^T . g
-        outs = [gw]
-        if any(ctx.needs_input_grad[1:]):
-            if len(ctx.widths) > 1 and len(ctx.widths) <= 32 and all(c % 32 == 0 for c in ctx.widths) and \
-                    nv.lib().dgcnn_tc_gemm_workspace_bytes(P, K, Cout) == 0:
-                # g . W^T with every source's gradient written to its own dense tensor (no strided slices)
-                import ctypes
-                n = len(ctx.widths)
-                bufs = [torch.empty((P, c), dtype=torch.float32, device=pg.device) for c in ctx.widths]
-                starts = (ctypes.c_int * n)(*[sum(ctx.widths[:i]) for i in range(n)])
-                widths = (ctypes.c_int * n)(*ctx.widths)
-                ptrs = (ctypes.c_void_p * n)(*[b.data_ptr() for b in bufs])
-                nv.check(nv.lib().dgcnn_tc_gemm_grouped(pg.data_ptr(), pw.data_ptr(), P, K, Cout, 0, 1, n, starts, widths,
-                                                        ptrs, nv.stream_ptr(pg.device)), "tc_gemm_grouped")
-                outs += [b if ctx.needs_input_grad[1 + i] else None for i, b in enumerate(bufs)]
-            else:
-                gcat = _tc_gemm_raw(pg, pw, P, K, Cout, 0, 1)                                     # g . W^T
-                off = 0
-                for i, c in enumerate(ctx.widths):
-                    outs.append(gcat[:, off:off + c] if ctx.needs_input_grad[1 + i] else None)
-                    off += c
+        return tuple([gw] + _tc_dx_sources(pg, pw, P, K, Cout, ctx.widths, ctx.needs_input_grad[1:]))
+
+
+class _ConvBnActTC(torch.autograd.Function):
+    """One whole head layer (model.py:65-72, ops.py:151-160): 1x1 conv of a channel-concatenation + train-mode
+    BatchNorm [+ per-cloud bias] [+ ReLU], fused around the tcgen05 GEMM:
+      forward : sources -> bf16 planes -> GEMM whose epilogue also leaves the BN column statistics of every 128-row
+                tile -> tiny finalisation -> one apply pass.  (No separate statistics pass over z.)
+      backward: BN backward writes g_z directly as bf16 planes (the operand format of the dW / dX GEMMs)."""
+
+    @staticmethod
+    def forward(ctx, w, beta, gb, relu_flag, grows, *srcs):
+        w = nv.require_cuda(w, "conv weights")
+        beta = nv.require_cuda(beta, "beta")
+        gb = nv.require_cuda(gb, "group_bias") if gb is not None else None
+        srcs = [nv.require_cuda(t, "conv input") for t in srcs]
+        planes, widths, P, K = _split_sources(srcs, w)
+        Cout = w.shape[1]
+        pw = _split(w)
+        dev = w.device
+        L = nv.lib()
+        st = nv.stream_ptr(dev)
+        grows = int(grows) if gb is not None else 0
+        mean = torch.empty(Cout, dtype=torch.float32, device=dev)
+        rstd = torch.empty(Cout, dtype=torch.float32, device=dev)
+        out = torch.empty((P, Cout), dtype=torch.float32, device=dev)
+        if L.dgcnn_tc_gemm_stats_supported(P, Cout, K) and (gb is None or grows % 128 == 0):
+            z = torch.empty((P, Cout), dtype=torch.float32, device=dev)
+            tiles = (P + 127) // 128
+            cs = torch.empty((tiles, 2, Cout), dtype=torch.float32, device=dev)
+            nv.check(L.dgcnn_tc_gemm_stats(planes.data_ptr(), pw.data_ptr(), z.data_ptr(), P, Cout, K, 0, 0, cs.data_ptr(),
+                                           st), "tc_gemm_stats")
+            nv.check(L.dgcnn_bn_stats_from_tiles(cs.data_ptr(), tiles, Cout, P, nv.ptr(gb), grows, mean.data_ptr(),
+                                                 rstd.data_ptr(), st), "bn_stats_from_tiles")
+            nv.check(L.dgcnn_bn_apply_fwd(z.data_ptr(), P, Cout, beta.data_ptr(), 0, nv.ptr(gb), grows,
+                                          int(bool(relu_flag)), mean.data_ptr(), rstd.data_ptr(), out.data_ptr(), st),
+                     "bn_apply_fwd")
         else:
-            outs += [None] * len(ctx.widths)
-        return tuple(outs)
+            z = _tc_gemm_raw(planes, pw, P, Cout, K, 0, 0)
+            ws = nv.workspace(dev, L.dgcnn_bn_workspace_bytes(Cout), "stats")
+            nv.check(L.dgcnn_bn_act_fwd_gb(z.data_ptr(), P, Cout, beta.data_ptr(), 0, nv.ptr(gb), grows,
+                                           int(bool(relu_flag)), out.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), st), "bn_act_fwd")
+        ctx.save_for_backward(planes, pw, z, out, mean, rstd, gb)
+        ctx.widths, ctx.relu, ctx.grows = widths, bool(relu_flag), grows
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        planes, pw, z, out, mean, rstd, gb = ctx.saved_tensors
+        _, P, K = planes.shape
+        Cout = pw.shape[2]
+        g = nv.require_cuda(g, "grad")
+        dev = g.device
+        L = nv.lib()
+        ws = nv.workspace(dev, L.dgcnn_bn_workspace_bytes(Cout), "stats")
+        pg = torch.empty((2, P, Cout), dtype=torch.bfloat16, device=dev)
+        gz = torch.empty_like(z) if gb is not None else None      # fp32 copy only for the per-cloud bias gradient
+        gbeta = torch.empty(Cout, dtype=torch.float32, device=dev)
+        nv.check(L.dgcnn_bn_act_bwd_planes(z.data_ptr(), out.data_ptr(), g.data_ptr(), P, Cout, mean.data_ptr(),
+                                           rstd.data_ptr(), nv.ptr(gb), ctx.grows, int(ctx.relu), nv.ptr(gz),
+                                           pg.data_ptr(), gbeta.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           nv.stream_ptr(dev)), "bn_act_bwd_planes")
+        gw = _tc_gemm_raw(planes, pg, K, Cout, P, 1, 0) if ctx.needs_input_grad[0] else None   # X^T . g_z
+        ggb = gz.view(gb.shape[0], ctx.grows, Cout).sum(dim=1) if gb is not None else None
+        return tuple([gw, gbeta, ggb, None, None] + _tc_dx_sources(pg, pw, P, K, Cout, ctx.widths, ctx.needs_input_grad[5:]))
 
 
 def conv1x1(srcs, w) -> torch.Tensor:
@@ -398,6 +470,44 @@ class _GroupMax(torch.autograd.Function):
         nv.check(nv.lib().dgcnn_group_max_bwd(x.data_ptr(), out.data_ptr(), cnt.data_ptr(), g.data_ptr(), G, rows, C,
                                               gx.data_ptr(), nv.stream_ptr(x.device)), "group_max_bwd")
         return gx
+
+
+class _PoolAndPass(torch.autograd.Function):
+    """x [G, rows, C] -> (x itself, max over rows [G, C]) for a tensor that is BOTH max-pooled and consumed directly
+    (model.py:76-85: the MergedEdgeConv output).  Backward adds the pooling gradient into the other consumer's
+    gradient buffer at the arg-max positions only, instead of materialising a dense pooling gradient and summing."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = nv.require_cuda(x, "x")
+        G, rows, C = x.shape
+        out = torch.empty((G, C), dtype=torch.float32, device=x.device)
+        cnt = torch.empty((G, C), dtype=torch.float32, device=x.device)
+        nv.check(nv.lib().dgcnn_group_max_fwd(x.data_ptr(), G, rows, C, out.data_ptr(), cnt.data_ptr(),
+                                              nv.stream_ptr(x.device)), "group_max_fwd")
+        ctx.save_for_backward(x, out, cnt)
+        return x.view_as(x), out
+
+    @staticmethod
+    def backward(ctx, gx, gp):
+        x, out, cnt = ctx.saved_tensors
+        G, rows, C = x.shape
+        if gx is None:
+            gx = torch.zeros_like(x)
+        else:
+            gx = nv.require_cuda(gx, "grad")
+        if gp is not None:
+            gp = nv.require_cuda(gp, "grad pooled")
+            nv.check(nv.lib().dgcnn_group_max_bwd_add(x.data_ptr(), out.data_ptr(), cnt.data_ptr(), gp.data_ptr(), G, rows,
+                                                      C, gx.data_ptr(), nv.stream_ptr(x.device)), "group_max_bwd_add")
+        return gx
+
+
+def pool_and_pass(x: torch.Tensor):
+    """-> (x, global max over dim 1) with the fused backward above (C % 4 == 0), else the separate ops."""
+    if x.shape[-1] % 4 == 0:
+        return _PoolAndPass.apply(x)
+    return x, x.amax(dim=1)
 
 
 def global_max_pool(x: torch.Tensor) -> torch.Tensor:

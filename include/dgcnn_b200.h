@@ -155,12 +155,32 @@ int dgcnn_bn_act_bwd_gb(const float* z, const float* out, const float* g_out, in
                         const float* rstd, const float* group_bias, int group_rows, int relu, float* g_z,
                         float* g_beta, float* g_pre, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
 
+/* The same layer in pieces, for a 1x1 conv that ran on dgcnn_tc_gemm_stats:
+ *   stats_from_tiles : colstats [tiles][2][C] (per 128-row tile: column sum, column sum of squares of z) -> mean, rstd,
+ *                      including the per-group bias analytically (group_rows % 128 == 0)
+ *   apply_fwd        : out = act((z [+ bias_g] - mean) * rstd + beta [+ residual]) with given statistics
+ *   bwd_planes       : dgcnn_bn_act_bwd_gb whose g_z leaves as bf16 hi/lo planes [2][rows][C] -- the operand format of
+ *                      the weight / input gradient GEMMs -- and, only if g_z != NULL, also as fp32               */
+int dgcnn_bn_stats_from_tiles(const float* colstats, int tiles, int C, int64_t rows, const float* group_bias,
+                              int group_rows, float* mean, float* rstd, dgcnn_stream_t stream);
+int dgcnn_bn_apply_fwd(const float* z, int64_t rows, int C, const float* beta, const float* residual,
+                       const float* group_bias, int group_rows, int relu, const float* mean, const float* rstd,
+                       float* out, dgcnn_stream_t stream);
+int dgcnn_bn_act_bwd_planes(const float* z, const float* out, const float* g_out, int64_t rows, int C, const float* mean,
+                            const float* rstd, const float* group_bias, int group_rows, int relu, float* g_z,
+                            void* g_z_planes, float* g_beta, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+
 /* ---- global max over the points of each cloud: gen_nn_ops.max_pool_v2 ksize [1,N,1,1], model.py:77 ----------
  * x [groups, rows, C] -> out [groups, C] and cnt [groups, C] (# points attaining the max); the gradient goes to the
  * arg-max, shared equally among exact ties.                                                                  */
 int dgcnn_group_max_fwd(const float* x, int groups, int rows, int C, float* out, float* cnt, dgcnn_stream_t stream);
 int dgcnn_group_max_bwd(const float* x, const float* out, const float* cnt, const float* g_out, int groups, int rows,
                         int C, float* g_x, dgcnn_stream_t stream);
+
+/* g_x_inout [groups, rows, C] += that gradient, touching only the arg-max positions (fuses the accumulation with the
+ * gradient the tensor receives from its other consumer: model.py:83-85 feeds the pooled tensor to the concat too). */
+int dgcnn_group_max_bwd_add(const float* x, const float* out, const float* cnt, const float* g_out, int groups, int rows,
+                            int C, float* g_x_inout, dgcnn_stream_t stream);
 
 /* ---- tf.train.AdamOptimizer update on a flat buffer: trainval.py:17,80 --------------------
  * g' = g*grad_scale; m = b1*m+(1-b1)g'; v = b2*v+(1-b2)g'^2; p -= lr_t*m/(sqrt(v)+eps),
