@@ -24,7 +24,8 @@ template <int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
     bn_colsum_kernel(const float* __restrict__ z, const float* __restrict__ out, const float* __restrict__ gout,
                      const float* __restrict__ mean, const float* __restrict__ rstd, int relu, int64_t rows, int C,
-                     double* __restrict__ acc, const float* __restrict__ gbias, int grows) {
+                     double* __restrict__ acc, const float* __restrict__ gbias, int grows,
+                     const float* __restrict__ beta) {
   __shared__ float red[2][4][64];
   const int cl = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int c = blockIdx.y * 64 + cl;
@@ -33,10 +34,11 @@ __global__ void __launch_bounds__(BN_THREADS)
   const int64_t rbeg = (int64_t)blockIdx.x * rpb;
   const int64_t rend = rbeg + rpb < rows ? rbeg + rpb : rows;
   float a = 0.f, q = 0.f;
-  float mu = 0.f, rs = 0.f;
+  float mu = 0.f, rs = 0.f, be = 0.f;
   if (MODE == 1 && ok) {
     mu = mean[c];
     rs = rstd[c];
+    if (beta) be = beta[c];
   }
   if (ok) {
     for (int64_t r = rbeg + rg; r < rend; r += 4) {
@@ -48,10 +50,11 @@ __global__ void __launch_bounds__(BN_THREADS)
         q = fmaf(v, v, q);
       } else {
         float gp = gout[o];
-        if (relu && !(out[o] > 0.f)) gp = 0.f;
-        a += gp;
         float zv = z[o];
         if (gbias) zv += gbias[(r / grows) * C + c];
+        // ReLU mask: from the saved output, or (out == null, no residual) by re-evaluating the forward expression
+        if (relu && !((out ? out[o] : fmaf(zv - mu, rs, be)) > 0.f)) gp = 0.f;
+        a += gp;
         q = fmaf(gp, (zv - mu) * rs, q);
       }
     }
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(256)
                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ s1,
                       const float* __restrict__ s2, int relu, uint32_t nvec, int C, float inv_rows,
                       float* __restrict__ gz, float* __restrict__ gpre, const float* __restrict__ gbias, int grows,
-                      __nv_bfloat16* __restrict__ gz_planes, size_t plane_elems) {
+                      __nv_bfloat16* __restrict__ gz_planes, size_t plane_elems, const float* __restrict__ beta) {
   const uint32_t cv = (uint32_t)C / VEC;
   for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
     const uint32_t r = v / cv;
@@ -119,21 +122,21 @@ __global__ void __launch_bounds__(256)
     if (VEC == 4) {
       *reinterpret_cast<float4*>(zz) = *reinterpret_cast<const float4*>(z + e);
       *reinterpret_cast<float4*>(gg) = *reinterpret_cast<const float4*>(gout + e);
-      if (relu) *reinterpret_cast<float4*>(oo) = *reinterpret_cast<const float4*>(out + e);
+      if (relu && out) *reinterpret_cast<float4*>(oo) = *reinterpret_cast<const float4*>(out + e);
       if (gbias) *reinterpret_cast<float4*>(gb) = *reinterpret_cast<const float4*>(gbias + (size_t)(r / grows) * C + c);
     } else {
       zz[0] = z[e];
       gg[0] = gout[e];
-      if (relu) oo[0] = out[e];
+      if (relu && out) oo[0] = out[e];
       if (gbias) gb[0] = gbias[(size_t)(r / grows) * C + c];
     }
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       float gp = gg[i];
-      if (relu && !(oo[i] > 0.f)) gp = 0.f;
       const float rs = rstd[c + i];
       float zv = zz[i];
       if (gbias) zv += gb[i];
+      if (relu && !((out ? oo[i] : fmaf(zv - mean[c + i], rs, beta[c + i])) > 0.f)) gp = 0.f;
       const float zh = (zv - mean[c + i]) * rs;
       gzv[i] = rs * (gp - s1[c + i] * inv_rows - zh * (s2[c + i] * inv_rows));
       gpv[i] = gp;
@@ -176,29 +179,60 @@ __global__ void adam_tf_kernel(float* __restrict__ p, const float* __restrict__ 
 // x [G, rows, C] -> out [G, C], cnt [G, C] = number of points attaining the maximum.
 __global__ void __launch_bounds__(256)
     group_max_fwd_kernel(const float* __restrict__ x, int rows, int C, float* __restrict__ out, float* __restrict__ cnt) {
-  __shared__ float rm[4][64];
-  __shared__ float rc[4][64];
-  const int cl = threadIdx.x & 63, rg = threadIdx.x >> 6;
-  const int c = blockIdx.x * 64 + cl;
+  // block = 64 channels (16 float4 lanes) x 16 row groups; 4 independent 16-byte loads in flight per thread
+  __shared__ float rm[16][64];
+  __shared__ float rc[16][64];
+  const int cv = threadIdx.x & 15, rg = threadIdx.x >> 4;
+  const int c0 = blockIdx.x * 64 + cv * 4;
   const int g = blockIdx.y;
-  float m = -INFINITY, n = 0.f;
-  if (c < C) {
-    const float* xg = x + (size_t)g * rows * C + c;
-    for (int r = rg; r < rows; r += 4) {
-      const float v = xg[(size_t)r * C];
-      if (v > m) { m = v; n = 1.f; } else if (v == m) n += 1.f;
+  float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, n[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* xg = x + (size_t)g * rows * C;
+  auto upd = [&](const float (&v)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (v[i] > m[i]) { m[i] = v[i]; n[i] = 1.f; } else if (v[i] == m[i]) n[i] += 1.f;
+    }
+  };
+  if ((C & 3) == 0 && c0 + 3 < C && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    int r = rg;
+    for (; r + 48 < rows; r += 64) {
+      float v[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        *reinterpret_cast<float4*>(v[u]) = *reinterpret_cast<const float4*>(xg + (size_t)(r + 16 * u) * C + c0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) upd(v[u]);
+    }
+    for (; r < rows; r += 16) {
+      float v[4];
+      *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(xg + (size_t)r * C + c0);
+      upd(v);
+    }
+  } else {
+    for (int r = rg; r < rows; r += 16) {
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = c0 + i < C ? xg[(size_t)r * C + c0 + i] : -INFINITY;
+      upd(v);
     }
   }
-  rm[rg][cl] = m;
-  rc[rg][cl] = n;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    rm[rg][cv * 4 + i] = m[i];
+    rc[rg][cv * 4 + i] = n[i];
+  }
   __syncthreads();
-  if (rg == 0 && c < C) {
-    for (int i = 1; i < 4; ++i) {
-      const float mi = rm[i][cl], ni = rc[i][cl];
-      if (mi > m) { m = mi; n = ni; } else if (mi == m) n += ni;
+  if (threadIdx.x < 64) {
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    float mm = rm[0][threadIdx.x], nn = rc[0][threadIdx.x];
+    for (int i = 1; i < 16; ++i) {
+      const float mi = rm[i][threadIdx.x], ni = rc[i][threadIdx.x];
+      if (mi > mm) { mm = mi; nn = ni; } else if (mi == mm) nn += ni;
     }
-    out[(size_t)g * C + c] = m;
-    cnt[(size_t)g * C + c] = n;
+    if (c < C) {
+      out[(size_t)g * C + c] = mm;
+      cnt[(size_t)g * C + c] = nn;
+    }
   }
 }
 
@@ -231,12 +265,13 @@ __global__ void __launch_bounds__(256)
     bn_tile_stats_kernel(const float* __restrict__ colstats, int tiles, int C, double rows, const float* __restrict__ gbias,
                          int tiles_per_group, double group_rows, float eps, float* __restrict__ mean,
                          float* __restrict__ rstd) {
-  __shared__ double r1[8][32], r2[8][32];
-  const int cl = threadIdx.x & 31, tl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  // block = 8 columns x 32 tile lanes; 8 consecutive columns of one tile are one 32-byte sector
+  __shared__ double r1[32][8], r2[32][8];
+  const int cl = threadIdx.x & 7, tl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + cl;
   double a = 0.0, q = 0.0;
   if (c < C) {
-    for (int t = tl; t < tiles; t += 8) {
+    for (int t = tl; t < tiles; t += 32) {
       const double s1 = (double)colstats[((size_t)t * 2) * C + c];
       const double s2 = (double)colstats[((size_t)t * 2 + 1) * C + c];
       a += s1;
@@ -255,7 +290,7 @@ __global__ void __launch_bounds__(256)
   r2[tl][cl] = q;
   __syncthreads();
   if (tl == 0 && c < C) {
-    for (int i = 1; i < 8; ++i) {
+    for (int i = 1; i < 32; ++i) {
       a += r1[i][cl];
       q += r2[i][cl];
     }
@@ -328,7 +363,7 @@ extern "C" int dgcnn_bn_act_fwd_gb(const float* z, int64_t rows, int C, const fl
   int rc = stats_acc_reset(ws, C, st);
   if (rc) return rc;
   bn_colsum_kernel<0><<<grid, BN_THREADS, 0, st>>>(z, nullptr, nullptr, nullptr, nullptr, 0, rows, C, (double*)ws,
-                                                   group_bias, group_rows);
+                                                   group_bias, group_rows, nullptr);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_colsum_kernel<0>");
   rc = launch_finalize_stats((const double*)ws, C, (double)rows, 1e-3f, mean, rstd, st);
@@ -354,7 +389,7 @@ extern "C" int dgcnn_bn_stats_from_tiles(const float* colstats, int tiles, int C
              "bn_stats_from_tiles: bad shape tiles=%d C=%d rows=%lld", tiles, C, (long long)rows);
   DG_REQUIRE(!group_bias || (group_rows > 0 && group_rows % 128 == 0 && rows % group_rows == 0), DGCNN_ERR_INVALID,
              "bn_stats_from_tiles: group_rows=%d must be a multiple of 128 dividing rows", group_rows);
-  bn_tile_stats_kernel<<<cdiv(C, 32), 256, 0, (cudaStream_t)stream>>>(colstats, tiles, C, (double)rows, group_bias,
+  bn_tile_stats_kernel<<<cdiv(C, 8), 256, 0, (cudaStream_t)stream>>>(colstats, tiles, C, (double)rows, group_bias,
                                                                       group_bias ? group_rows / 128 : 1,
                                                                       (double)group_rows, 1e-3f, mean, rstd);
   count_launch();
@@ -386,17 +421,18 @@ extern "C" int dgcnn_bn_apply_fwd(const float* z, int64_t rows, int C, const flo
 
 static int bn_act_bwd_impl(const float* z, const float* out, const float* g_out, int64_t rows, int C, const float* mean,
                            const float* rstd, const float* group_bias, int group_rows, int relu, float* g_z,
-                           void* g_z_planes, float* g_beta, float* g_pre, void* ws, size_t ws_bytes,
+                           void* g_z_planes, float* g_beta, float* g_pre, const float* beta, void* ws, size_t ws_bytes,
                            dgcnn_stream_t stream);
 
-extern "C" int dgcnn_bn_act_bwd_planes(const float* z, const float* out, const float* g_out, int64_t rows, int C,
-                                       const float* mean, const float* rstd, const float* group_bias, int group_rows,
-                                       int relu, float* g_z, void* g_z_planes, float* g_beta, void* ws, size_t ws_bytes,
-                                       dgcnn_stream_t stream) {
+extern "C" int dgcnn_bn_act_bwd_planes(const float* z, const float* out, const float* beta, const float* g_out,
+                                       int64_t rows, int C, const float* mean, const float* rstd,
+                                       const float* group_bias, int group_rows, int relu, float* g_z, void* g_z_planes,
+                                       float* g_beta, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
+  DG_REQUIRE(!relu || out || beta, DGCNN_ERR_INVALID, "bn_act_bwd_planes: relu backward needs out or beta");
   DG_REQUIRE(g_z_planes && (C & 3) == 0 && ((uintptr_t)g_z_planes & 7) == 0, DGCNN_ERR_INVALID,
              "bn_act_bwd_planes: needs a plane buffer and C %% 4 == 0");
   return bn_act_bwd_impl(z, out, g_out, rows, C, mean, rstd, group_bias, group_rows, relu, g_z, g_z_planes, g_beta,
-                         nullptr, ws, ws_bytes, stream);
+                         nullptr, out ? nullptr : beta, ws, ws_bytes, stream);
 }
 
 extern "C" int dgcnn_bn_act_bwd(const float* z, const float* out, const float* g_out, int64_t rows, int C,
@@ -412,18 +448,18 @@ extern "C" int dgcnn_bn_act_bwd_gb(const float* z, const float* out, const float
                                    dgcnn_stream_t stream) {
   DG_REQUIRE(g_z, DGCNN_ERR_INVALID, "bn_act_bwd: null pointer");
   return bn_act_bwd_impl(z, out, g_out, rows, C, mean, rstd, group_bias, group_rows, relu, g_z, nullptr, g_beta, g_pre,
-                         ws, ws_bytes, stream);
+                         nullptr, ws, ws_bytes, stream);
 }
 
 static int bn_act_bwd_impl(const float* z, const float* out, const float* g_out, int64_t rows, int C, const float* mean,
                            const float* rstd, const float* group_bias, int group_rows, int relu, float* g_z,
-                           void* g_z_planes, float* g_beta, float* g_pre, void* ws, size_t ws_bytes,
+                           void* g_z_planes, float* g_beta, float* g_pre, const float* beta, void* ws, size_t ws_bytes,
                            dgcnn_stream_t stream) {
   DG_REQUIRE(!group_bias || (group_rows > 0 && rows % group_rows == 0), DGCNN_ERR_INVALID,
              "bn_act_bwd: rows=%lld is not a multiple of group_rows=%d", (long long)rows, group_rows);
   DG_REQUIRE(z && g_out && mean && rstd && (g_z || g_z_planes) && g_beta && ws, DGCNN_ERR_INVALID,
              "bn_act_bwd: null pointer");
-  DG_REQUIRE(!relu || out, DGCNN_ERR_INVALID, "bn_act_bwd: relu backward needs the forward output");
+  DG_REQUIRE(!relu || out || beta, DGCNN_ERR_INVALID, "bn_act_bwd: relu backward needs the forward output");
   DG_REQUIRE(rows > 0 && C > 0, DGCNN_ERR_INVALID, "bn_act_bwd: bad shape rows=%lld C=%d", (long long)rows, C);
   DG_REQUIRE(ws_bytes >= dgcnn_bn_workspace_bytes(C), DGCNN_ERR_WORKSPACE, "bn_act_bwd: workspace");
   cudaStream_t st = (cudaStream_t)stream;
@@ -435,7 +471,7 @@ static int bn_act_bwd_impl(const float* z, const float* out, const float* g_out,
   int rc = stats_acc_reset(ws, C, st);
   if (rc) return rc;
   bn_colsum_kernel<1><<<grid, BN_THREADS, 0, st>>>(z, out, g_out, mean, rstd, relu, rows, C, acc, group_bias,
-                                                   group_rows);
+                                                   group_rows, beta);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_colsum_kernel<1>");
   rc = launch_finalize_sums(acc, C, g_beta, s2, st);
@@ -449,11 +485,11 @@ static int bn_act_bwd_impl(const float* z, const float* out, const float* g_out,
     bn_act_bwd_kernel<4><<<ew_blocks(total / 4), 256, 0, st>>>(z, out, g_out, mean, rstd, g_beta, s2, relu,
                                                                (uint32_t)(total / 4), C, 1.0f / (float)rows, g_z, g_pre,
                                                                group_bias, group_rows, (__nv_bfloat16*)g_z_planes,
-                                                               (size_t)total);
+                                                               (size_t)total, beta);
   else
     bn_act_bwd_kernel<1><<<ew_blocks(total), 256, 0, st>>>(z, out, g_out, mean, rstd, g_beta, s2, relu, (uint32_t)total, C,
                                                            1.0f / (float)rows, g_z, g_pre, group_bias, group_rows, nullptr,
-                                                           0);
+                                                           0, beta);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_act_bwd_kernel");
   return DGCNN_OK;

@@ -135,7 +135,7 @@ __global__ void finalize_sums_kernel(const double* __restrict__ acc, int C, floa
 __global__ void __launch_bounds__(EC_THREADS)
     ec_fwd_apply_kernel(EcArgs a, const float* __restrict__ zmax, const float* __restrict__ mean,
                         const float* __restrict__ rstd, const float* __restrict__ beta, float* __restrict__ omax,
-                        float* __restrict__ omean) {
+                        float* __restrict__ omean, int opitch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int f0 = blockIdx.y * 64 + lane, f1 = f0 + 32;
   const bool ok0 = f0 < a.F, ok1 = f1 < a.F;
@@ -157,14 +157,14 @@ __global__ void __launch_bounds__(EC_THREADS)
       y0 += fmaxf(fmaf(z0 - mu0, r0, b0), 0.f);
       y1 += fmaxf(fmaf(z1 - mu1, r1, b1), 0.f);
     }
-    const int64_t o = (int64_t)p * a.F;
+    const int64_t o = (int64_t)p * a.F, oo = (int64_t)p * opitch;
     if (ok0) {
-      omean[o + f0] = y0 * invk;
-      omax[o + f0] = fmaxf(fmaf(zmax[o + f0] - mu0, r0, b0), 0.f);  // BN(+)ReLU are monotone: max commutes
+      omean[oo + f0] = y0 * invk;
+      omax[oo + f0] = fmaxf(fmaf(zmax[o + f0] - mu0, r0, b0), 0.f);  // BN(+)ReLU are monotone: max commutes
     }
     if (ok1) {
-      omean[o + f1] = y1 * invk;
-      omax[o + f1] = fmaxf(fmaf(zmax[o + f1] - mu1, r1, b1), 0.f);
+      omean[oo + f1] = y1 * invk;
+      omax[oo + f1] = fmaxf(fmaf(zmax[o + f1] - mu1, r1, b1), 0.f);
     }
   }
 }
@@ -176,8 +176,9 @@ template <bool APPLY>
 __global__ void __launch_bounds__(EC_THREADS)
     ec_bwd_kernel(EcArgs a, const float* __restrict__ zmax, const float* __restrict__ cnt,
                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ beta,
-                  const float* __restrict__ gmax, const float* __restrict__ gmean, const float* __restrict__ s1,
-                  const float* __restrict__ s2, double* __restrict__ acc, float* __restrict__ guv) {
+                  const float* __restrict__ gmax, const float* __restrict__ gmean, const float* __restrict__ gboth,
+                  const float* __restrict__ s1, const float* __restrict__ s2, double* __restrict__ acc,
+                  float* __restrict__ guv) {
   __shared__ float red[2][EC_WARPS][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int f0 = blockIdx.y * 64 + lane, f1 = f0 + 32;
@@ -200,8 +201,18 @@ __global__ void __launch_bounds__(EC_THREADS)
     const int64_t o = (int64_t)p * a.F;
     const float u0 = ok0 ? up[f0] : 0.f, u1 = ok1 ? up[f1] : 0.f;
     const float zm0 = ok0 ? zmax[o + f0] : 0.f, zm1 = ok1 ? zmax[o + f1] : 0.f;
-    const float gm0 = ok0 ? gmean[o + f0] * invk : 0.f, gm1 = ok1 ? gmean[o + f1] * invk : 0.f;
-    const float gx0 = ok0 ? gmax[o + f0] / cnt[o + f0] : 0.f, gx1 = ok1 ? gmax[o + f1] / cnt[o + f1] : 0.f;
+    // the gradients of max / mean arrive from up to two consumers: separate [P,F] tensors and/or one packed
+    // [P,2F] = (max | mean) tensor (the conv1 operand); summed here instead of in a separate pass
+    float gM0 = 0.f, gM1 = 0.f, gA0 = 0.f, gA1 = 0.f;
+    if (gmax) { if (ok0) gM0 = gmax[o + f0]; if (ok1) gM1 = gmax[o + f1]; }
+    if (gmean) { if (ok0) gA0 = gmean[o + f0]; if (ok1) gA1 = gmean[o + f1]; }
+    if (gboth) {
+      const float* gb = gboth + (int64_t)p * 2 * a.F;
+      if (ok0) { gM0 += gb[f0]; gA0 += gb[a.F + f0]; }
+      if (ok1) { gM1 += gb[f1]; gA1 += gb[a.F + f1]; }
+    }
+    const float gm0 = gA0 * invk, gm1 = gA1 * invk;
+    const float gx0 = ok0 ? gM0 / cnt[o + f0] : 0.f, gx1 = ok1 ? gM1 / cnt[o + f1] : 0.f;
     float gu0 = 0.f, gu1 = 0.f;
 #pragma unroll 4
     for (int j = 0; j < a.k; ++j) {
@@ -343,28 +354,52 @@ extern "C" int dgcnn_edgeconv_fwd_stats(const float* uv, const int32_t* idx, int
   return launch_finalize_stats((const double*)ws, F, (double)a.P * (double)k, 1e-3f, mean, rstd, st);
 }
 
-extern "C" int dgcnn_edgeconv_fwd_apply(const float* uv, const int32_t* idx, int B, int N, int F, int k,
-                                        const float* zmax, const float* mean, const float* rstd, const float* beta,
-                                        float* out_max, float* out_mean, dgcnn_stream_t stream) {
+static int ec_fwd_apply_impl(const float* uv, const int32_t* idx, int B, int N, int F, int k, const float* zmax,
+                             const float* mean, const float* rstd, const float* beta, float* out_max, float* out_mean,
+                             int pitch, dgcnn_stream_t stream) {
   int rc = ec_check(uv, idx, B, N, F, k);
   if (rc) return rc;
   DG_REQUIRE(zmax && mean && rstd && beta && out_max && out_mean, DGCNN_ERR_INVALID,
              "edgeconv_fwd_apply: null pointer");
   EcArgs a{uv, idx, B * N, N, F, k};
   dim3 grid(stat_blocks(a.P), cdiv(F, 64));
-  ec_fwd_apply_kernel<<<grid, EC_THREADS, 0, (cudaStream_t)stream>>>(a, zmax, mean, rstd, beta, out_max, out_mean);
+  ec_fwd_apply_kernel<<<grid, EC_THREADS, 0, (cudaStream_t)stream>>>(a, zmax, mean, rstd, beta, out_max, out_mean,
+                                                                     pitch);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("ec_fwd_apply_kernel");
   return DGCNN_OK;
+}
+
+extern "C" int dgcnn_edgeconv_fwd_apply(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                        const float* zmax, const float* mean, const float* rstd, const float* beta,
+                                        float* out_max, float* out_mean, dgcnn_stream_t stream) {
+  return ec_fwd_apply_impl(uv, idx, B, N, F, k, zmax, mean, rstd, beta, out_max, out_mean, F, stream);
+}
+
+extern "C" int dgcnn_edgeconv_fwd_apply_packed(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                               const float* zmax, const float* mean, const float* rstd,
+                                               const float* beta, float* out_both, dgcnn_stream_t stream) {
+  DG_REQUIRE(out_both, DGCNN_ERR_INVALID, "edgeconv_fwd_apply_packed: null pointer");
+  return ec_fwd_apply_impl(uv, idx, B, N, F, k, zmax, mean, rstd, beta, out_both, out_both + F, 2 * F, stream);
 }
 
 extern "C" int dgcnn_edgeconv_bwd_stats(const float* uv, const int32_t* idx, int B, int N, int F, int k,
                                         const float* zmax, const float* cnt, const float* mean, const float* rstd,
                                         const float* beta, const float* g_max, const float* g_mean, float* s1,
                                         float* s2, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
+  DG_REQUIRE(g_max && g_mean, DGCNN_ERR_INVALID, "edgeconv_bwd_stats: null pointer");
+  return dgcnn_edgeconv_bwd_stats_packed(uv, idx, B, N, F, k, zmax, cnt, mean, rstd, beta, g_max, g_mean, nullptr, s1,
+                                         s2, ws, ws_bytes, stream);
+}
+
+extern "C" int dgcnn_edgeconv_bwd_stats_packed(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                               const float* zmax, const float* cnt, const float* mean,
+                                               const float* rstd, const float* beta, const float* g_max,
+                                               const float* g_mean, const float* g_both, float* s1, float* s2,
+                                               void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
   int rc = ec_check(uv, idx, B, N, F, k);
   if (rc) return rc;
-  DG_REQUIRE(zmax && cnt && mean && rstd && beta && g_max && g_mean && s1 && s2 && ws, DGCNN_ERR_INVALID,
+  DG_REQUIRE(zmax && cnt && mean && rstd && beta && s1 && s2 && ws, DGCNN_ERR_INVALID,
              "edgeconv_bwd_stats: null pointer");
   DG_REQUIRE(ws_bytes >= dgcnn_edgeconv_workspace_bytes(F), DGCNN_ERR_WORKSPACE, "edgeconv_bwd_stats: workspace");
   cudaStream_t st = (cudaStream_t)stream;
@@ -374,8 +409,8 @@ extern "C" int dgcnn_edgeconv_bwd_stats(const float* uv, const int32_t* idx, int
   DG_REQUIRE(((uintptr_t)ws & 7) == 0, DGCNN_ERR_INVALID, "edgeconv_bwd_stats: workspace must be 8-byte aligned");
   rc = stats_acc_reset(ws, F, st);
   if (rc) return rc;
-  ec_bwd_kernel<false><<<grid, EC_THREADS, 0, st>>>(a, zmax, cnt, mean, rstd, beta, g_max, g_mean, nullptr, nullptr,
-                                                     (double*)ws, nullptr);
+  ec_bwd_kernel<false><<<grid, EC_THREADS, 0, st>>>(a, zmax, cnt, mean, rstd, beta, g_max, g_mean, g_both, nullptr,
+                                                     nullptr, (double*)ws, nullptr);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("ec_bwd_kernel<stats>");
   return launch_finalize_sums((const double*)ws, F, s1, s2, st);
@@ -385,9 +420,19 @@ extern "C" int dgcnn_edgeconv_bwd_apply(const float* uv, const int32_t* idx, int
                                         const float* zmax, const float* cnt, const float* mean, const float* rstd,
                                         const float* beta, const float* g_max, const float* g_mean, const float* s1,
                                         const float* s2, float* g_uv, dgcnn_stream_t stream) {
+  DG_REQUIRE(g_max && g_mean, DGCNN_ERR_INVALID, "edgeconv_bwd_apply: null pointer");
+  return dgcnn_edgeconv_bwd_apply_packed(uv, idx, B, N, F, k, zmax, cnt, mean, rstd, beta, g_max, g_mean, nullptr, s1,
+                                         s2, g_uv, stream);
+}
+
+extern "C" int dgcnn_edgeconv_bwd_apply_packed(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                               const float* zmax, const float* cnt, const float* mean,
+                                               const float* rstd, const float* beta, const float* g_max,
+                                               const float* g_mean, const float* g_both, const float* s1,
+                                               const float* s2, float* g_uv, dgcnn_stream_t stream) {
   int rc = ec_check(uv, idx, B, N, F, k);
   if (rc) return rc;
-  DG_REQUIRE(zmax && cnt && mean && rstd && beta && g_max && g_mean && s1 && s2 && g_uv, DGCNN_ERR_INVALID,
+  DG_REQUIRE(zmax && cnt && mean && rstd && beta && s1 && s2 && g_uv, DGCNN_ERR_INVALID,
              "edgeconv_bwd_apply: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   EcArgs a{uv, idx, B * N, N, F, k};
@@ -396,8 +441,8 @@ extern "C" int dgcnn_edgeconv_bwd_apply(const float* uv, const int32_t* idx, int
   count_launch();
   DG_CUDA_LAUNCH_CHECK("zero_vhalf_kernel");
   dim3 grid(stat_blocks(a.P), cdiv(F, 64));
-  ec_bwd_kernel<true><<<grid, EC_THREADS, 0, st>>>(a, zmax, cnt, mean, rstd, beta, g_max, g_mean, s1, s2, nullptr,
-                                                    g_uv);
+  ec_bwd_kernel<true><<<grid, EC_THREADS, 0, st>>>(a, zmax, cnt, mean, rstd, beta, g_max, g_mean, g_both, s1, s2,
+                                                    nullptr, g_uv);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("ec_bwd_kernel<apply>");
   return DGCNN_OK;

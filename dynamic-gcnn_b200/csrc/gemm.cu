@@ -161,6 +161,116 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
   C[i] = s;
 }
 
+// ---- skinny shapes: the 2-class `Final` conv (model.py:94-101: [P,256] x [256,2]) and the weight gradients whose
+// output is a few hundred numbers but whose contraction runs over all B*N points (Final, and EdgeConv0's 3-channel
+// input).  The 128x64 tile kernel wastes >90 % of its lanes on them; these two are plain streaming kernels that keep
+// the sequential-in-k fmaf order per output (per k-chunk for the gradient, chunks then summed in a fixed order).
+// C[M,N] = A[M,K] . B[K,N], N <= 4, K % 128 == 0... (general K handled with a guarded tail): one warp per row, lanes
+// own interleaved k (coalesced 16-byte loads), a fixed shuffle tree adds the 32 partial dot products.  Deterministic;
+// NOT the sequential-in-k order of sgemm_kernel -- used only for the class-score layer, which no kNN graph depends on.
+__global__ void __launch_bounds__(256)
+    sgemm_skinny_n_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C, int M, int N,
+                          int K) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = warp; row < M; row += nwarps) {
+    const float* ar = A + (size_t)row * K;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane * 4; k < K; k += 128) {
+      float a[4];
+      if (k + 3 < K && (K & 3) == 0) {
+        *reinterpret_cast<float4*>(a) = __ldg(reinterpret_cast<const float4*>(ar + k));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = k + i < K ? __ldg(ar + k + i) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (k + i < K) {
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+            if (n < N) acc[n] = __fmaf_rn(a[i], __ldg(Bm + (size_t)(k + i) * N + n), acc[n]);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(FULL, acc[n], o);
+    }
+    if (lane == 0) {
+      for (int n = 0; n < N; ++n) C[(size_t)row * N + n] = acc[n];
+    }
+  }
+}
+
+// Weight gradient with one narrow operand (width <= 4) and one wide operand (width <= 256), contraction over K rows:
+//   out[w][s] = sum_k Wd[k][w] * Sd[k][s].  Threads own wide columns (coalesced loads of Wd rows), the narrow row is a
+// broadcast load; block-local row groups and the blocks' partials are summed in a fixed order.
+// part[block][wide][narrow]
+__global__ void __launch_bounds__(256)
+    sgemm_skinny_dw_kernel(const float* __restrict__ Wd, const float* __restrict__ Sd, float* __restrict__ part, int wide,
+                           int narrow, int K, int kper) {
+  __shared__ float red[256][4];
+  const int groups = 256 / wide;              // row groups per block (wide is 64, 128 or 256 -> 4, 2, 1)
+  const int w = threadIdx.x % wide, rg = threadIdx.x / wide;
+  const int kbeg = blockIdx.x * kper, kend = min(K, kbeg + kper);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rg < groups) {
+#pragma unroll 4
+    for (int k = kbeg + rg; k < kend; k += groups) {
+      const float x = __ldg(Wd + (size_t)k * wide + w);
+#pragma unroll
+      for (int s2 = 0; s2 < 4; ++s2)
+        if (s2 < narrow) acc[s2] = __fmaf_rn(x, __ldg(Sd + (size_t)k * narrow + s2), acc[s2]);
+    }
+  }
+#pragma unroll
+  for (int s2 = 0; s2 < 4; ++s2) red[threadIdx.x][s2] = acc[s2];
+  __syncthreads();
+  if (threadIdx.x < wide) {
+    float* o = part + ((size_t)blockIdx.x * wide + threadIdx.x) * narrow;
+    for (int s2 = 0; s2 < narrow; ++s2) {
+      float t = 0.f;
+      for (int g = 0; g < groups; ++g) t += red[g * wide + threadIdx.x][s2];
+      o[s2] = t;
+    }
+  }
+}
+
+// C[m][n] = sum over blocks of part; `wide_is_a` : part is [wide = M][narrow = N], else [wide = N][narrow = M]
+__global__ void skinny_dw_reduce_kernel(const float* __restrict__ part, float* __restrict__ C, int M, int N, int nb,
+                                        int wide_is_a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  const int m = i / N, n = i - m * N;
+  const int src = wide_is_a ? m * N + n : n * M + m;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  int b = 0;
+  for (; b + 3 < nb; b += 4) {
+    t0 += part[(size_t)b * M * N + src];
+    t1 += part[(size_t)(b + 1) * M * N + src];
+    t2 += part[(size_t)(b + 2) * M * N + src];
+    t3 += part[(size_t)(b + 3) * M * N + src];
+  }
+  for (; b < nb; ++b) t0 += part[(size_t)b * M * N + src];
+  C[i] = (t0 + t1) + (t2 + t3);
+}
+
+static inline bool skinny_n(int M, int N, int K, int transA, int transB) {
+  return !transA && !transB && N <= 4 && M >= 4096;
+}
+static inline bool skinny_wide_ok(int w) { return w == 64 || w == 128 || w == 256; }
+static inline bool skinny_dw(int M, int N, int K, int transA, int transB) {
+  return transA && !transB && K >= 8192 && ((M <= 4 && skinny_wide_ok(N)) || (N <= 4 && skinny_wide_ok(M)));
+}
+static inline int skinny_dw_blocks(int K) {
+  int b = 2 * num_sms();
+  const int maxb = cdiv(K, 64);
+  return b < maxb ? b : maxb;
+}
+
 static int pick_splits(int M, int N, int K) {
   const int64_t tiles = (int64_t)cdiv(M, BM) * cdiv(N, BN);
   const int sms = num_sms();
@@ -177,9 +287,9 @@ static int pick_splits(int M, int N, int K) {
 using namespace dgcnn;
 
 extern "C" size_t dgcnn_gemm_workspace_bytes(int M, int N, int K, int transA, int transB) {
-  (void)transA;
-  (void)transB;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (skinny_n(M, N, K, transA, transB)) return 0;
+  if (skinny_dw(M, N, K, transA, transB)) return (size_t)skinny_dw_blocks(K) * M * N * sizeof(float);
   const int s = pick_splits(M, N, K);
   return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
 }
@@ -190,6 +300,31 @@ extern "C" int dgcnn_gemm(const float* A, const float* B, float* C, int M, int N
   DG_REQUIRE(A && B && C, DGCNN_ERR_INVALID, "gemm: null pointer");
   DG_REQUIRE(M > 0 && N > 0 && K > 0, DGCNN_ERR_INVALID, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   DG_REQUIRE(((uintptr_t)C & 15) == 0, DGCNN_ERR_INVALID, "gemm: C must be 16-byte aligned");
+  if (skinny_n(M, N, K, transA, transB)) {
+    const int blocks = cdiv(M, 8) < 8 * num_sms() ? cdiv(M, 8) : 8 * num_sms();
+    sgemm_skinny_n_kernel<<<blocks, 256, 0, st>>>(A, B, C, M, N, K);
+    count_launch();
+    DG_CUDA_LAUNCH_CHECK("sgemm_skinny_n_kernel");
+    return DGCNN_OK;
+  }
+  if (skinny_dw(M, N, K, transA, transB)) {
+    const int nb = skinny_dw_blocks(K);
+    const size_t need = (size_t)nb * M * N * sizeof(float);
+    DG_REQUIRE(ws && ws_bytes >= need, DGCNN_ERR_WORKSPACE, "gemm: workspace %zu < %zu bytes", ws_bytes, need);
+    const int kper = cdiv(K, nb);
+    const bool wide_is_a = N <= 4 && skinny_wide_ok(M);
+    if (wide_is_a)
+      sgemm_skinny_dw_kernel<<<nb, 256, 0, st>>>(A, B, reinterpret_cast<float*>(ws), M, N, K, kper);
+    else
+      sgemm_skinny_dw_kernel<<<nb, 256, 0, st>>>(B, A, reinterpret_cast<float*>(ws), N, M, K, kper);
+    count_launch();
+    DG_CUDA_LAUNCH_CHECK("sgemm_skinny_dw_kernel");
+    skinny_dw_reduce_kernel<<<cdiv((int64_t)M * N, 128), 128, 0, st>>>(reinterpret_cast<float*>(ws), C, M, N, nb,
+                                                                        wide_is_a ? 1 : 0);
+    count_launch();
+    DG_CUDA_LAUNCH_CHECK("skinny_dw_reduce_kernel");
+    return DGCNN_OK;
+  }
   const int splits = pick_splits(M, N, K);
   float* out = C;
   if (splits > 1) {

@@ -44,6 +44,9 @@ SIGNATURES = {
     "dgcnn_edgeconv_fwd_apply": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dgcnn_edgeconv_bwd_stats": (_i, [_vp, _vp, _i, _i, _i, _i] + [_vp] * 9 + [_vp, _sz, _vp]),
     "dgcnn_edgeconv_bwd_apply": (_i, [_vp, _vp, _i, _i, _i, _i] + [_vp] * 10 + [_vp]),
+    "dgcnn_edgeconv_fwd_apply_packed": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dgcnn_edgeconv_bwd_stats_packed": (_i, [_vp, _vp, _i, _i, _i, _i] + [_vp] * 10 + [_vp, _sz, _vp]),
+    "dgcnn_edgeconv_bwd_apply_packed": (_i, [_vp, _vp, _i, _i, _i, _i] + [_vp] * 11 + [_vp]),
     "dgcnn_bn_workspace_bytes": (_sz, [_i]),
     "dgcnn_bn_act_fwd": (_i, [_vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dgcnn_bn_act_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -51,7 +54,7 @@ SIGNATURES = {
     "dgcnn_bn_act_bwd_gb": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dgcnn_bn_stats_from_tiles": (_i, [_vp, _i, _i, _i64, _vp, _i, _vp, _vp, _vp]),
     "dgcnn_bn_apply_fwd": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
-    "dgcnn_bn_act_bwd_planes": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dgcnn_bn_act_bwd_planes": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dgcnn_group_max_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "dgcnn_group_max_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "dgcnn_group_max_bwd_add": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
@@ -116,6 +119,21 @@ def require_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tenso
         raise RuntimeError("dgcnn: %s must live on a CUDA device (no CPU fallback exists)" % name)
     if t.dtype != dtype:
         raise TypeError("dgcnn: %s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+def require_cuda_rows(t: torch.Tensor, name: str) -> torch.Tensor:
+    """fp32 CUDA [rows, cols] whose rows may be strided (a column slice of a wider buffer): no copy if the elements of
+    a row are contiguous and rows / base are 16-byte aligned."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("dgcnn: %s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("dgcnn: %s must live on a CUDA device (no CPU fallback exists)" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("dgcnn: %s must be float32, got %s" % (name, t.dtype))
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1] and t.stride(0) % 4 == 0 and \
+            t.data_ptr() % 16 == 0:
+        return t
     return t.contiguous()
 
 

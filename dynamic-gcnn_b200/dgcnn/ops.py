@@ -259,7 +259,7 @@ class _ConcatConvTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, w, *srcs):
         w = nv.require_cuda(w, "conv weights")
-        srcs = [nv.require_cuda(t, "conv input") for t in srcs]
+        srcs = [nv.require_cuda_rows(t, "conv input") for t in srcs]
         planes, widths, P, K = _split_sources(srcs, w)
         Cout = w.shape[1]
         pw = _split(w)
@@ -289,7 +289,7 @@ class _ConvBnActTC(torch.autograd.Function):
         w = nv.require_cuda(w, "conv weights")
         beta = nv.require_cuda(beta, "beta")
         gb = nv.require_cuda(gb, "group_bias") if gb is not None else None
-        srcs = [nv.require_cuda(t, "conv input") for t in srcs]
+        srcs = [nv.require_cuda_rows(t, "conv input") for t in srcs]
         planes, widths, P, K = _split_sources(srcs, w)
         Cout = w.shape[1]
         pw = _split(w)
@@ -317,13 +317,13 @@ class _ConvBnActTC(torch.autograd.Function):
             nv.check(L.dgcnn_bn_act_fwd_gb(z.data_ptr(), P, Cout, beta.data_ptr(), 0, nv.ptr(gb), grows,
                                            int(bool(relu_flag)), out.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                            ws.data_ptr(), ws.numel(), st), "bn_act_fwd")
-        ctx.save_for_backward(planes, pw, z, out, mean, rstd, gb)
+        ctx.save_for_backward(planes, pw, z, beta, mean, rstd, gb)   # the ReLU mask is re-evaluated from z in backward
         ctx.widths, ctx.relu, ctx.grows = widths, bool(relu_flag), grows
         return out
 
     @staticmethod
     def backward(ctx, g):
-        planes, pw, z, out, mean, rstd, gb = ctx.saved_tensors
+        planes, pw, z, beta, mean, rstd, gb = ctx.saved_tensors
         _, P, K = planes.shape
         Cout = pw.shape[2]
         g = nv.require_cuda(g, "grad")
@@ -333,7 +333,7 @@ class _ConvBnActTC(torch.autograd.Function):
         pg = torch.empty((2, P, Cout), dtype=torch.bfloat16, device=dev)
         gz = torch.empty_like(z) if gb is not None else None      # fp32 copy only for the per-cloud bias gradient
         gbeta = torch.empty(Cout, dtype=torch.float32, device=dev)
-        nv.check(L.dgcnn_bn_act_bwd_planes(z.data_ptr(), out.data_ptr(), g.data_ptr(), P, Cout, mean.data_ptr(),
+        nv.check(L.dgcnn_bn_act_bwd_planes(z.data_ptr(), 0, beta.data_ptr(), g.data_ptr(), P, Cout, mean.data_ptr(),
                                            rstd.data_ptr(), nv.ptr(gb), ctx.grows, int(ctx.relu), nv.ptr(gz),
                                            pg.data_ptr(), gbeta.data_ptr(), ws.data_ptr(), ws.numel(),
                                            nv.stream_ptr(dev)), "bn_act_bwd_planes")
@@ -352,7 +352,9 @@ def conv1x1(srcs, w) -> torch.Tensor:
 
 
 class _EdgeConvGather(torch.autograd.Function):
-    """ops.py:45-57 after the algebraic split z_ij = u_i + v_idx(i,j): BN(train)+ReLU+max_k/mean_k."""
+    """ops.py:45-58 after the algebraic split z_ij = u_i + v_idx(i,j): BN(train)+ReLU+max_k/mean_k.
+    -> (max [P,F], mean [P,F], both [P,2F]); max and mean are the two column halves of `both`, which therefore IS
+    ops.py:58's concat(max, mean).  Backward sums the gradients of all three inside the gather kernels."""
 
     @staticmethod
     def forward(ctx, uv, idx, beta, B, N, k):
@@ -372,32 +374,33 @@ class _EdgeConvGather(torch.autograd.Function):
         nv.check(L.dgcnn_edgeconv_fwd_stats(uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(),
                                             cnt.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(),
                                             ws.numel(), st), "edgeconv_fwd_stats")
-        omax = torch.empty((P, F), dtype=torch.float32, device=dev)
-        omean = torch.empty((P, F), dtype=torch.float32, device=dev)
-        nv.check(L.dgcnn_edgeconv_fwd_apply(uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(),
-                                            mean.data_ptr(), rstd.data_ptr(), beta.data_ptr(), omax.data_ptr(),
-                                            omean.data_ptr(), st), "edgeconv_fwd_apply")
+        both = torch.empty((P, 2 * F), dtype=torch.float32, device=dev)
+        nv.check(L.dgcnn_edgeconv_fwd_apply_packed(uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(),
+                                                   mean.data_ptr(), rstd.data_ptr(), beta.data_ptr(), both.data_ptr(),
+                                                   st), "edgeconv_fwd_apply")
         ctx.save_for_backward(uv, idx, beta, zmax, cnt, mean, rstd)
         ctx.dims = (B, N, F, k)
-        return omax, omean
+        return both[:, :F], both[:, F:], both
 
     @staticmethod
-    def backward(ctx, gmax, gmean):
+    def backward(ctx, gmax, gmean, gboth):
         uv, idx, beta, zmax, cnt, mean, rstd = ctx.saved_tensors
         B, N, F, k = ctx.dims
         dev = uv.device
         L = nv.lib()
         st = nv.stream_ptr(dev)
-        gmax = nv.require_cuda(gmax, "grad max")
-        gmean = nv.require_cuda(gmean, "grad mean")
+        gmax = nv.require_cuda(gmax, "grad max") if gmax is not None else None
+        gmean = nv.require_cuda(gmean, "grad mean") if gmean is not None else None
+        gboth = nv.require_cuda(gboth, "grad concat") if gboth is not None else None
         ws = nv.workspace(dev, L.dgcnn_edgeconv_workspace_bytes(F), "stats")
         s1 = torch.empty(F, dtype=torch.float32, device=dev)
         s2 = torch.empty(F, dtype=torch.float32, device=dev)
         common = (uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(), cnt.data_ptr(), mean.data_ptr(),
-                  rstd.data_ptr(), beta.data_ptr(), gmax.data_ptr(), gmean.data_ptr(), s1.data_ptr(), s2.data_ptr())
-        nv.check(L.dgcnn_edgeconv_bwd_stats(*common, ws.data_ptr(), ws.numel(), st), "edgeconv_bwd_stats")
+                  rstd.data_ptr(), beta.data_ptr(), nv.ptr(gmax), nv.ptr(gmean), nv.ptr(gboth), s1.data_ptr(),
+                  s2.data_ptr())
+        nv.check(L.dgcnn_edgeconv_bwd_stats_packed(*common, ws.data_ptr(), ws.numel(), st), "edgeconv_bwd_stats")
         guv = torch.empty_like(uv)
-        nv.check(L.dgcnn_edgeconv_bwd_apply(*common, guv.data_ptr(), st), "edgeconv_bwd_apply")
+        nv.check(L.dgcnn_edgeconv_bwd_apply_packed(*common, guv.data_ptr(), st), "edgeconv_bwd_apply")
         return guv, None, s1, None, None, None
 
 
@@ -567,9 +570,8 @@ def edge_conv(point_cloud, k, num_filters, trainable, activation=relu, debug=Fal
     w0, b0 = _conv_bn_vars("conv0", 2 * C, F, trainable, x.device)              # ops.py:47-54
     wp = torch.cat([w0[:C] - w0[C:], w0[C:]], dim=1)                            # [C, 2F] = [Wa-Wb | Wb]
     uv = _Conv1x1.apply(x.reshape(B * N, C), wp)   # exact fp32 SIMT: the next layer's kNN is built on these features
-    net_max, net_mean = _EdgeConvGather.apply(uv, idx, b0, B, N, k)             # ops.py:53-57
+    net_max, net_mean, net = _EdgeConvGather.apply(uv, idx, b0, B, N, k)        # ops.py:53-58 (net = concat, in place)
     if debug: _dbg(debug, torch.empty(B, N, k, F, device="meta"), _cur_scope() + "/conv0 (never materialised)")
-    net = torch.cat([net_max, net_mean], dim=-1)                                # ops.py:58
     _dbg(debug, net_max.view(B, N, 1, F), _cur_scope() + "/Max")
     _dbg(debug, net_mean.view(B, N, 1, F), _cur_scope() + "/Mean")
     _dbg(debug, net.view(B, N, 1, 2 * F), _cur_scope() + "/concat")

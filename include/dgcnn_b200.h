@@ -131,6 +131,22 @@ int dgcnn_edgeconv_bwd_apply(const float* uv, const int32_t* idx, int B, int N, 
                              const float* beta, const float* g_max, const float* g_mean, const float* s1,
                              const float* s2, float* g_uv, dgcnn_stream_t stream);
 
+/* Packed variants for the layer as the model uses it (ops.py:58: conv1 consumes concat(max, mean)):
+ *   fwd_apply_packed : out_both [P,2F] = (out_max | out_mean), i.e. the concat is produced in place
+ *   bwd_*_packed     : the gradients of max and mean may arrive as separate [P,F] tensors (g_max, g_mean; either may
+ *                      be NULL) and/or as one packed [P,2F] tensor g_both (may be NULL); they are summed on the fly */
+int dgcnn_edgeconv_fwd_apply_packed(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                    const float* zmax, const float* mean, const float* rstd, const float* beta,
+                                    float* out_both, dgcnn_stream_t stream);
+int dgcnn_edgeconv_bwd_stats_packed(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                    const float* zmax, const float* cnt, const float* mean, const float* rstd,
+                                    const float* beta, const float* g_max, const float* g_mean, const float* g_both,
+                                    float* s1, float* s2, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+int dgcnn_edgeconv_bwd_apply_packed(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                    const float* zmax, const float* cnt, const float* mean, const float* rstd,
+                                    const float* beta, const float* g_max, const float* g_mean, const float* g_both,
+                                    const float* s1, const float* s2, float* g_uv, dgcnn_stream_t stream);
+
 /* ---- train-mode BatchNorm (+residual) (+ReLU) on a [rows,C] per-point tensor ---------------
  * slim.batch_norm defaults (is_training=True, center=True, scale=False, eps=1e-3) after a 1x1 conv:
  * ops.py:53,68 ; residual add + relu: ops.py:134.
@@ -160,15 +176,17 @@ int dgcnn_bn_act_bwd_gb(const float* z, const float* out, const float* g_out, in
  *                      including the per-group bias analytically (group_rows % 128 == 0)
  *   apply_fwd        : out = act((z [+ bias_g] - mean) * rstd + beta [+ residual]) with given statistics
  *   bwd_planes       : dgcnn_bn_act_bwd_gb whose g_z leaves as bf16 hi/lo planes [2][rows][C] -- the operand format of
- *                      the weight / input gradient GEMMs -- and, only if g_z != NULL, also as fp32               */
+ *                      the weight / input gradient GEMMs -- and, only if g_z != NULL, also as fp32.  out may be NULL
+ *                      (layers without residual): the ReLU mask is then re-evaluated from z, mean, rstd, beta      */
 int dgcnn_bn_stats_from_tiles(const float* colstats, int tiles, int C, int64_t rows, const float* group_bias,
                               int group_rows, float* mean, float* rstd, dgcnn_stream_t stream);
 int dgcnn_bn_apply_fwd(const float* z, int64_t rows, int C, const float* beta, const float* residual,
                        const float* group_bias, int group_rows, int relu, const float* mean, const float* rstd,
                        float* out, dgcnn_stream_t stream);
-int dgcnn_bn_act_bwd_planes(const float* z, const float* out, const float* g_out, int64_t rows, int C, const float* mean,
-                            const float* rstd, const float* group_bias, int group_rows, int relu, float* g_z,
-                            void* g_z_planes, float* g_beta, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+int dgcnn_bn_act_bwd_planes(const float* z, const float* out, const float* beta, const float* g_out, int64_t rows, int C,
+                            const float* mean, const float* rstd, const float* group_bias, int group_rows, int relu,
+                            float* g_z, void* g_z_planes, float* g_beta, void* ws, size_t ws_bytes,
+                            dgcnn_stream_t stream);
 
 /* ---- global max over the points of each cloud: gen_nn_ops.max_pool_v2 ksize [1,N,1,1], model.py:77 ----------
  * x [groups, rows, C] -> out [groups, C] and cnt [groups, C] (# points attaining the max); the gradient goes to the
