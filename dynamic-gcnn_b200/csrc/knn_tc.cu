@@ -35,8 +35,14 @@
 //                             + 2^-24 sqrt(C) (sqrt n_i + sqrt n_j)   (the absolute term: fp16 subnormals)
 //   accumulation            : <= 80 fp32 adds (possibly truncating) of exact products, |sum| <= (n_i+n_j)  -> 2^-16
 //   norms                   : n itself 2^-18 n; the bf16 parts of c are exact to 2^-24 c
-//   => sig = 1.125 * 2^-10 n + 2^-16 S + 2^-21 sqrt(n): the dominant fp16 term is a theorem, the 12.5 % on top of it
-//      is ~6x the sum of the remaining terms.
+//   => coarse mode: sig = 1.125 * 2^-10 n + 2^-16 S + 2^-21 sqrt(n): the dominant fp16 term is a theorem, the 12.5 %
+//      on top of it is ~6x the sum of the remaining terms.
+//   fine mode (clouds of more than 4096 points): operands h = hi + lo (two fp16 roundings, |y - hi - lo| <= 2^-22 |y|) and three MMAs per
+//      k-slice (lo.hi + hi.lo + hi.hi): the product term drops to 2^-20 (n_i+n_j) and the accumulation dominates:
+//      <= 13*16 adds, each off by <= 2^-23 of a partial sum that never exceeds n_i/2 + n_j  ->  2^-14.3 in D units
+//      if EVERY add truncated in the same direction.  Budget 2^-13 n per point (2.5x that worst case).  Dense clouds
+//      (N = 16384: neighbour distances ~1 % of the norms) need this mode; it costs tensor time only, and the sweeps
+//      are bound by reading the accumulators out of TMEM (64 B/clk/SM), not by the MMAs.
 #include <stdlib.h>
 
 #include <cuda_fp16.h>
@@ -52,22 +58,23 @@ constexpr int K2_SCANW = 16;        // scan warps: 4 per TMEM sub-partition, one
 constexpr int K2_SCAN = 32 * K2_SCANW;
 constexpr int K2_THREADS = 64 + K2_SCAN;  // warp 0 TMA, warp 1 MMA
 constexpr int K2_GMAX = 128;        // group maxima per row (32 per scan thread)
-constexpr int K2_CAPMAX = 32;       // list entries per (row, column quarter)
+constexpr int K2_CAPMAX = 48;       // list entries per (row, column quarter)
 constexpr int K2_SLACK = 8;         // writes past the cap land here (one clamp per 8 columns)
 constexpr int K2_BISECT = 10;
-constexpr int K2_NST = 6;           // B-tile ring depth (TMA latency >> MMA time of a tile)
+constexpr int K2_NST = 3;           // B-tile ring depth (TMA latency >> MMA time of a tile)
 constexpr int K2_NACC = 4;          // TMEM accumulator ring: 4 x 128 columns
-constexpr float K2_EPS = 1.125f / 1024.0f;
+constexpr float K2_EPS = 1.125f / 1024.0f;          // one fp16 product per pair
+constexpr float K2_EPS_FINE = 1.0f / 8192.0f;        // fp16 hi/lo operands, three products per pair
 constexpr float K2_EPS_ORACLE = 1.0f / 65536.0f;
 constexpr float K2_EPS_ABS = 1.0f / 2097152.0f;
 constexpr float K2_PAD_NORM = 1.0e36f;   // squared norm given to padding columns: they never pass a test
 constexpr uint32_t K2_TILE = K2_ROWS * 64 * 2;   // one fp16 tile, 128B rows, 16 KB
 constexpr uint32_t K2_QTILE = K2_ROWS * 16 * 2;  // the -0.5 c_j k-slice, 32B rows, 4 KB
-constexpr uint32_t K2_STAGE = K2_TILE + K2_QTILE;
+constexpr uint32_t K2_STAGE = 2 * K2_TILE + K2_QTILE;   // B hi, B lo (fine mode only), norm slice
 
 // byte offsets into the (1024-aligned) dynamic shared memory
-constexpr size_t K2_A_OFF = 0;                                // A tile
-constexpr size_t K2_ONES_OFF = K2_A_OFF + K2_TILE;            // 128 x 16 ones
+constexpr size_t K2_A_OFF = 0;                                // A hi, A lo
+constexpr size_t K2_ONES_OFF = K2_A_OFF + 2 * K2_TILE;        // 128 x 16 ones
 constexpr size_t K2_B_OFF = K2_ONES_OFF + K2_QTILE;           // K2_NST stages of (B tile, q slice)
 constexpr size_t K2_GM_OFF = K2_B_OFF + (size_t)K2_NST * K2_STAGE;   // group maxima (sweep 1) / candidate lists (sweep 2)
 constexpr size_t K2_GM_BYTES = (size_t)K2_GMAX * K2_ROWS * 4;
@@ -133,6 +140,7 @@ struct K2Args {
   int N, Npad, C, k, cap;
   int wg;              // columns per group (8, 16 or 32)
   int tiles_per_group; // > 1 only with wg == 32
+  int fine;            // operands split hi + lo, three MMAs per k-slice (error budget 2^-15 instead of 2^-10)
   int dbg;             // K2_DEBUG experiments
 };
 
@@ -189,31 +197,19 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(a_full, K2_TILE);
-      tma_load_2d(sm + K2_A_OFF, &tmX, 0, grow0 + r0, a_full);
+      mbar_expect_tx(a_full, A.fine ? 2 * K2_TILE : K2_TILE);
+      tma_load_3d(sm + K2_A_OFF, &tmX, 0, grow0 + r0, 0, a_full);
+      if (A.fine) tma_load_3d(sm + K2_A_OFF + K2_TILE, &tmX, 0, grow0 + r0, 1, a_full);
       for (int step = 0; step < 2 * T; ++step) {
         const int st = step % K2_NST;
         const int sweep = step >= T;
         const int t = sweep ? step - T : step;
         mbar_wait(&b_empty[st], ((step / K2_NST) & 1) ^ 1);
         unsigned char* dst = sm + K2_B_OFF + (size_t)st * K2_STAGE;
-#ifdef K2_DEBUG
-        if (A.dbg == 1) {
-          mbar_expect_tx(&b_full[st], K2_TILE);
-          tma_load_2d(dst, &tmX, 0, grow0 + t * K2_COLS, &b_full[st]);
-          continue;
-        } else if (A.dbg == 2) {
-          mbar_expect_tx(&b_full[st], K2_QTILE);
-          tma_load_3d(dst + K2_TILE, &tmQ, 0, grow0 + t * K2_COLS, sweep, &b_full[st]);
-          continue;
-        } else if (A.dbg == 3) {
-          mbar_arrive(&b_full[st]);
-          continue;
-        }
-#endif
-        mbar_expect_tx(&b_full[st], K2_STAGE);
-        tma_load_2d(dst, &tmX, 0, grow0 + t * K2_COLS, &b_full[st]);
-        tma_load_3d(dst + K2_TILE, &tmQ, 0, grow0 + t * K2_COLS, sweep, &b_full[st]);
+        mbar_expect_tx(&b_full[st], (A.fine ? 2 * K2_TILE : K2_TILE) + K2_QTILE);
+        tma_load_3d(dst, &tmX, 0, grow0 + t * K2_COLS, 0, &b_full[st]);
+        if (A.fine) tma_load_3d(dst + K2_TILE, &tmX, 0, grow0 + t * K2_COLS, 1, &b_full[st]);
+        tma_load_3d(dst + 2 * K2_TILE, &tmQ, 0, grow0 + t * K2_COLS, sweep, &b_full[st]);
         if (step == T - 1) K2_STAMP(8);
       }
       K2_STAMP(9);
@@ -234,13 +230,19 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
       mbar_wait(&acc_empty[ab], ((step / K2_NACC) & 1) ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
-        const uint32_t a_h = smem_u32(sm + K2_A_OFF);
-        const uint32_t b_h = smem_u32(sm + K2_B_OFF + (size_t)st * K2_STAGE);
+        const uint32_t a_h = smem_u32(sm + K2_A_OFF), a_l = a_h + K2_TILE;
+        const uint32_t b_h = smem_u32(sm + K2_B_OFF + (size_t)st * K2_STAGE), b_l = b_h + K2_TILE;
         const uint32_t acc = tmem_base + (uint32_t)(ab * K2_COLS);
-        // -0.5 c_j first (it also clears the accumulator), then the products
-        umma_bf16(acc, umma_desc_sw32(smem_u32(sm + K2_ONES_OFF)), umma_desc_sw32(b_h + K2_TILE), idesc_bf16, 0);
-        for (int ks = 0; ks < nks; ++ks)
-          umma_bf16(acc, umma_desc(a_h + ks * 32, 16, 1024), umma_desc(b_h + ks * 32, 16, 1024), idesc_f16, 1);
+        // -0.5 c_j first (it also clears the accumulator), then the products (small terms before hi.hi)
+        umma_bf16(acc, umma_desc_sw32(smem_u32(sm + K2_ONES_OFF)), umma_desc_sw32(b_h + 2 * K2_TILE), idesc_bf16, 0);
+        for (int ks = 0; ks < nks; ++ks) {
+          const uint64_t dah = umma_desc(a_h + ks * 32, 16, 1024), dbh = umma_desc(b_h + ks * 32, 16, 1024);
+          if (A.fine) {
+            umma_bf16(acc, umma_desc(a_l + ks * 32, 16, 1024), dbh, idesc_f16, 1);
+            umma_bf16(acc, dah, umma_desc(b_l + ks * 32, 16, 1024), idesc_f16, 1);
+          }
+          umma_bf16(acc, dah, dbh, idesc_f16, 1);
+        }
         umma_commit(&b_empty[st]);
         umma_commit(&acc_full[ab]);
       }
@@ -527,11 +529,14 @@ template <int KS>
 __global__ void __launch_bounds__(256)
     knn_row_fallback_kernel(const float* __restrict__ x, const float* __restrict__ s, const int32_t* __restrict__ fbq,
                             int N, int Npad, int C, int k, int32_t* __restrict__ idx) {
+  // one BLOCK per queued row: the 8 warps scan interleaved 128-column chunks, then warp 0 merges the 8 lists
   __shared__ float qd_s[8][QCAP];
   __shared__ int qj_s[8][QCAP];
+  __shared__ float md_s[8][32 * KS];
+  __shared__ int mj_s[8][32 * KS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nq = fbq[0];
-  for (int it = blockIdx.x * 8 + warp; it < nq; it += gridDim.x * 8) {
+  for (int it = blockIdx.x; it < nq; it += gridDim.x) {
     const int64_t p = fbq[1 + it];
     const int b = (int)(p / N);
     const float* sb = s + (size_t)b * Npad;
@@ -540,7 +545,7 @@ __global__ void __launch_bounds__(256)
     const float si = sb[p - (int64_t)b * N];
     RowSel<KS> R;
     R.init();
-    for (int c0 = 0; c0 < N; c0 += 128) {
+    for (int c0 = warp * 128; c0 < N; c0 += 8 * 128) {
       float dv[4];
       int cj[4];
       const float* xj[4];
@@ -561,13 +566,25 @@ __global__ void __launch_bounds__(256)
       R.offer4(dv, cj, N, k, qd_s[warp], qj_s[warp], lane);
     }
     R.finish(k, qd_s[warp], qj_s[warp], lane);
-    int32_t* o = idx + p * k;
 #pragma unroll
     for (int q = 0; q < KS; ++q) {
-      const int pos = q * 32 + lane;
-      if (pos < k) o[pos] = R.j[q];
+      md_s[warp][q * 32 + lane] = R.d[q];
+      mj_s[warp][q * 32 + lane] = R.j[q];
     }
-    __syncwarp();
+    __syncthreads();
+    if (warp == 0) {
+      for (int w = 1; w < 8; ++w) {
+#pragma unroll
+        for (int q = 0; q < KS; ++q) R.merge_batch(md_s[w][q * 32 + lane], mj_s[w][q * 32 + lane], k, lane);
+      }
+      int32_t* o = idx + p * k;
+#pragma unroll
+      for (int q = 0; q < KS; ++q) {
+        const int pos = q * 32 + lane;
+        if (pos < k) o[pos] = R.j[q];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -611,7 +628,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(128)
     knn_tc_prep_kernel(const float* __restrict__ x, const float* __restrict__ part, int N, int Npad, int C, int Cp,
                        float* __restrict__ s, float* __restrict__ sig, __half* __restrict__ h,
-                       __nv_bfloat16* __restrict__ q, int64_t q_plane) {
+                       __nv_bfloat16* __restrict__ q, int64_t q_plane, int64_t h_plane, int fine) {
   extern __shared__ float pt[];   // [128][C + 1] | origin [C] | scale, scale^2
   const int b = blockIdx.y;
   const int n0 = blockIdx.x * 128;
@@ -665,7 +682,7 @@ __global__ void __launch_bounds__(128)
     }
     const size_t g = (size_t)b * Npad + n0 + tid;
     s[g] = valid ? so : 0.0f;
-    const float sg = K2_EPS * nn + K2_EPS_ORACLE * (so * sc2) + K2_EPS_ABS * sqrtf(nn);
+    const float sg = (fine ? K2_EPS_FINE : K2_EPS) * nn + K2_EPS_ORACLE * (so * sc2) + K2_EPS_ABS * sqrtf(nn);
     sig[g] = valid ? sg : 0.0f;
 #pragma unroll
     for (int sw = 0; sw < 2; ++sw) {
@@ -690,18 +707,23 @@ __global__ void __launch_bounds__(128)
     const int r = e / hp, c = (e - r * hp) * 2;
     const float v0 = c < C ? pt[r * pitch + c] : 0.0f;
     const float v1 = c + 1 < C ? pt[r * pitch + c + 1] : 0.0f;
-    *reinterpret_cast<__half2*>(ph + (size_t)r * Cp + c) = __floats2half2_rn(v0, v1);
+    const __half2 hh = __floats2half2_rn(v0, v1);
+    *reinterpret_cast<__half2*>(ph + (size_t)r * Cp + c) = hh;
+    if (fine) {   // second plane: what the first rounding left over
+      const float2 hf = __half22float2(hh);
+      *reinterpret_cast<__half2*>(ph + h_plane + (size_t)r * Cp + c) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    }
   }
 }
 
 static int make_h_map(CUtensorMap* tm, const void* h, int64_t rows, int64_t cols) {
   EncodeTiledFn fn = tensor_map_encoder();
   if (!fn) return set_err(DGCNN_ERR_CUDA, "tensor map: cuTensorMapEncodeTiled unavailable");
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)K2_COLS};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(h), dims, strides, box, estr,
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * (cuuint64_t)cols * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)K2_COLS, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(h), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_err(DGCNN_ERR_CUDA, "tensor map (h): cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -724,7 +746,7 @@ static int make_q_map(CUtensorMap* tm, const void* q, int64_t rows) {
 
 static inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 static inline int k2_cp(int C) { return ((C + 7) / 8) * 8; }
-static inline int k2_cap(int k) { return k <= 24 ? 24 : 32; }
+static inline int k2_cap(int k) { return k <= 24 ? 32 : 48; }
 
 bool knn_tc_eligible(int B, int N, int C, int k) {
   return C >= 1 && C <= 64 && k <= 48 && N >= 256 && N <= 65536 && (int64_t)B * (((N + 127) / 128) * 128) < (1ll << 31);
@@ -734,7 +756,7 @@ bool knn_tc_eligible(int B, int N, int C, int k) {
 size_t knn_tc_bytes(int B, int N, int C, int k_max) {
   const size_t Npad = ((size_t)N + 127) / 128 * 128;
   const size_t P = (size_t)B * N, Pp = (size_t)B * Npad;
-  return 2 * al256(Pp * 4) + al256((size_t)B * K2_CHUNKS * 2 * C * 4) + al256(Pp * k2_cp(C) * 2) + al256(2 * Pp * 32) +
+  return 2 * al256(Pp * 4) + al256((size_t)B * K2_CHUNKS * 2 * C * 4) + al256(2 * Pp * k2_cp(C) * 2) + al256(2 * Pp * 32) +
          al256(P * 4 * k2_cap(k_max) * 2) + al256(P * 4) + al256((4 * P + 1) * 4);
 }
 
@@ -748,7 +770,7 @@ int knn_tc_run(const float* x, int32_t* idx, int B, int N, int C, int k, void* w
   float* s = reinterpret_cast<float*>(base + off); off += al256((size_t)Pp * 4);
   float* sig = reinterpret_cast<float*>(base + off); off += al256((size_t)Pp * 4);
   float* part = reinterpret_cast<float*>(base + off); off += al256((size_t)B * K2_CHUNKS * 2 * C * 4);
-  __half* h = reinterpret_cast<__half*>(base + off); off += al256((size_t)Pp * Cp * 2);
+  __half* h = reinterpret_cast<__half*>(base + off); off += al256((size_t)2 * Pp * Cp * 2);
   __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(base + off); off += al256((size_t)2 * Pp * 32);
   uint16_t* cand = reinterpret_cast<uint16_t*>(base + off); off += al256((size_t)P * 4 * cap * 2);
   uint8_t* ccnt = reinterpret_cast<uint8_t*>(base + off); off += al256((size_t)P * 4);
@@ -759,7 +781,17 @@ int knn_tc_run(const float* x, int32_t* idx, int B, int N, int C, int k, void* w
   count_launch();
   DG_CUDA_LAUNCH_CHECK("knn_tc_range_kernel");
   dim3 gp(Npad / 128, B);
-  knn_tc_prep_kernel<<<gp, 128, (size_t)(128 * (C + 1) + C + 2) * 4, st>>>(x, part, N, Npad, C, Cp, s, sig, h, q, Pp * 16);
+  // Precision mode of the filter.  Coarse (one fp16 product) is enough while the k-th neighbour distance is more than
+  // a few percent of the squared norms; dense clouds (many points per cloud) need the hi/lo split or most rows would
+  // overflow their candidate lists into the slow exact fallback.  The result is identical either way.
+  static int fine_env = -2;    // DGCNN_KNN_FINE=0|1 overrides the rule (tuning aid)
+  if (fine_env == -2) {
+    const char* e = getenv("DGCNN_KNN_FINE");
+    fine_env = e ? (atoi(e) != 0) : -1;
+  }
+  const int fine = fine_env >= 0 ? fine_env : (N > 4096 ? 1 : 0);
+  knn_tc_prep_kernel<<<gp, 128, (size_t)(128 * (C + 1) + C + 2) * 4, st>>>(x, part, N, Npad, C, Cp, s, sig, h, q, Pp * 16,
+                                                                          Pp * Cp, fine);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("knn_tc_prep_kernel");
 
@@ -786,14 +818,15 @@ int knn_tc_run(const float* x, int32_t* idx, int B, int N, int C, int k, void* w
   while (wg < 32 && Npad / wg > K2_GMAX) wg *= 2;
   a.wg = wg;
   a.tiles_per_group = wg == 32 ? (T + 31) / 32 : 1;
-  a.dbg = getenv("DGCNN_K2_DBG") ? atoi(getenv("DGCNN_K2_DBG")) : 0;
+  a.fine = fine;
+  a.dbg = 0;
   dim3 grid(Npad / K2_ROWS, B);
   knn_tc_filter_kernel<<<grid, K2_THREADS, K2_SMEM, st>>>(tmX, tmQ, a);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("knn_tc_filter_kernel");
   const bool staged = (C & 3) == 0 && C >= 16;
   const size_t rsm = staged ? (size_t)8 * 33 * (C + 4) * 4 : 0;
-  const int fb_grid = 2 * num_sms();
+  const int fb_grid = 4 * num_sms();
   if (k <= 32) {
     if (C == 64)
       knn_tc_refine_kernel<1, 64><<<cdiv(P, 8), 256, rsm, st>>>(x, s, cand, ccnt, N, Npad, C, k, cap, P, idx);
