@@ -69,6 +69,97 @@ __global__ void __launch_bounds__(BN_THREADS)
   }
 }
 
+// The same reduction with 16-byte loads (C % 4 == 0, 16-byte aligned buffers): a thread owns 4 consecutive channels,
+// a block covers CB = min(C, 256) channels x (256 / (CB/4)) row lanes, two rows in flight per thread.
+template <int MODE>
+__global__ void __launch_bounds__(BN_THREADS)
+    bn_colsum_vec_kernel(const float* __restrict__ z, const float* __restrict__ out, const float* __restrict__ gout,
+                         const float* __restrict__ mean, const float* __restrict__ rstd, int relu, int64_t rows, int C,
+                         int cb, double* __restrict__ acc, const float* __restrict__ gbias, int grows,
+                         const float* __restrict__ beta) {
+  __shared__ float red[2][BN_THREADS][4];
+  const int tpr = cb >> 2;                        // threads per row
+  const int cv = threadIdx.x % tpr, rl = threadIdx.x / tpr, lanes = BN_THREADS / tpr;
+  const int c = blockIdx.y * cb + cv * 4;
+  const bool ok = c < C;
+  const int64_t rpb = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t rbeg = (int64_t)blockIdx.x * rpb;
+  const int64_t rend = rbeg + rpb < rows ? rbeg + rpb : rows;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  float mu[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {0.f, 0.f, 0.f, 0.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+  if (MODE == 1 && ok) {
+    *reinterpret_cast<float4*>(mu) = *reinterpret_cast<const float4*>(mean + c);
+    *reinterpret_cast<float4*>(rs) = *reinterpret_cast<const float4*>(rstd + c);
+    if (beta) *reinterpret_cast<float4*>(be) = *reinterpret_cast<const float4*>(beta + c);
+  }
+  auto step = [&](int64_t r) {
+    const int64_t o = r * C + c;
+    float zv[4], gp[4], ov[4], gb[4] = {0.f, 0.f, 0.f, 0.f};
+    *reinterpret_cast<float4*>(zv) = *reinterpret_cast<const float4*>(z + o);
+    if (MODE == 1) {
+      *reinterpret_cast<float4*>(gp) = *reinterpret_cast<const float4*>(gout + o);
+      if (relu && out) *reinterpret_cast<float4*>(ov) = *reinterpret_cast<const float4*>(out + o);
+    }
+    if (gbias) *reinterpret_cast<float4*>(gb) = *reinterpret_cast<const float4*>(gbias + (r / grows) * C + c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float v = zv[i] + gb[i];
+      if (MODE == 0) {
+        a[i] += v;
+        q[i] = fmaf(v, v, q[i]);
+      } else {
+        float g = gp[i];
+        if (relu && !((out ? ov[i] : fmaf(v - mu[i], rs[i], be[i])) > 0.f)) g = 0.f;
+        a[i] += g;
+        q[i] = fmaf(g, (v - mu[i]) * rs[i], q[i]);
+      }
+    }
+  };
+  if (ok) {
+    int64_t r = rbeg + rl;
+    for (; r + lanes < rend; r += 2 * lanes) {
+      step(r);
+      step(r + lanes);
+    }
+    if (r < rend) step(r);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    red[0][threadIdx.x][i] = a[i];
+    red[1][threadIdx.x][i] = q[i];
+  }
+  __syncthreads();
+  // thread t < 2*cb: which = t / cb, channel t % cb; sum over the row lanes in a fixed order
+  for (int t = threadIdx.x; t < 2 * cb; t += BN_THREADS) {
+    const int which = t / cb, ch = t - which * cb;
+    const int ccv = ch >> 2, ci = ch & 3;
+    float sum = 0.f;
+    for (int l = 0; l < lanes; ++l) sum += red[which][l * tpr + ccv][ci];
+    const int cc = blockIdx.y * cb + ch;
+    if (cc < C) atomicAdd(&acc[which * C + cc], (double)sum);
+  }
+}
+
+template <int MODE>
+static void launch_colsum(const float* z, const float* out, const float* gout, const float* mean, const float* rstd,
+                          int relu, int64_t rows, int C, double* acc, const float* gbias, int grows, const float* beta,
+                          cudaStream_t st) {
+  const bool vec = (C & 3) == 0 && C >= 16 &&
+                   (((uintptr_t)z | (uintptr_t)out | (uintptr_t)gout | (uintptr_t)gbias | (uintptr_t)mean |
+                     (uintptr_t)rstd | (uintptr_t)beta) & 15) == 0;
+  const int nb = bn_blocks(rows);
+  if (vec) {
+    int cb = 256;
+    while (cb > C) cb >>= 1;                        // 16 .. 256, a power of two <= C
+    dim3 grid(nb, cdiv(C, cb));
+    bn_colsum_vec_kernel<MODE><<<grid, BN_THREADS, 0, st>>>(z, out, gout, mean, rstd, relu, rows, C, cb, acc, gbias,
+                                                            grows, beta);
+  } else {
+    dim3 grid(nb, cdiv(C, 64));
+    bn_colsum_kernel<MODE><<<grid, BN_THREADS, 0, st>>>(z, out, gout, mean, rstd, relu, rows, C, acc, gbias, grows, beta);
+  }
+}
+
 // Element-wise passes.  VEC = 4: one thread handles 4 consecutive channels of one row (float4 traffic, one 32-bit
 // division per 4 elements); VEC = 1 is the fallback for C % 4 != 0.
 template <int VEC>
@@ -357,13 +448,10 @@ extern "C" int dgcnn_bn_act_fwd_gb(const float* z, int64_t rows, int C, const fl
   DG_REQUIRE(rows > 0 && C > 0, DGCNN_ERR_INVALID, "bn_act_fwd: bad shape rows=%lld C=%d", (long long)rows, C);
   DG_REQUIRE(ws_bytes >= dgcnn_bn_workspace_bytes(C), DGCNN_ERR_WORKSPACE, "bn_act_fwd: workspace");
   cudaStream_t st = (cudaStream_t)stream;
-  const int nb = bn_blocks(rows);
-  dim3 grid(nb, cdiv(C, 64));
   DG_REQUIRE(((uintptr_t)ws & 7) == 0, DGCNN_ERR_INVALID, "bn_act_fwd: workspace must be 8-byte aligned");
   int rc = stats_acc_reset(ws, C, st);
   if (rc) return rc;
-  bn_colsum_kernel<0><<<grid, BN_THREADS, 0, st>>>(z, nullptr, nullptr, nullptr, nullptr, 0, rows, C, (double*)ws,
-                                                   group_bias, group_rows, nullptr);
+  launch_colsum<0>(z, nullptr, nullptr, nullptr, nullptr, 0, rows, C, (double*)ws, group_bias, group_rows, nullptr, st);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_colsum_kernel<0>");
   rc = launch_finalize_stats((const double*)ws, C, (double)rows, 1e-3f, mean, rstd, st);
@@ -463,15 +551,12 @@ static int bn_act_bwd_impl(const float* z, const float* out, const float* g_out,
   DG_REQUIRE(rows > 0 && C > 0, DGCNN_ERR_INVALID, "bn_act_bwd: bad shape rows=%lld C=%d", (long long)rows, C);
   DG_REQUIRE(ws_bytes >= dgcnn_bn_workspace_bytes(C), DGCNN_ERR_WORKSPACE, "bn_act_bwd: workspace");
   cudaStream_t st = (cudaStream_t)stream;
-  const int nb = bn_blocks(rows);
   DG_REQUIRE(((uintptr_t)ws & 7) == 0, DGCNN_ERR_INVALID, "bn_act_bwd: workspace must be 8-byte aligned");
   double* acc = (double*)ws;
   float* s2 = reinterpret_cast<float*>(acc + (size_t)2 * C);
-  dim3 grid(nb, cdiv(C, 64));
   int rc = stats_acc_reset(ws, C, st);
   if (rc) return rc;
-  bn_colsum_kernel<1><<<grid, BN_THREADS, 0, st>>>(z, out, g_out, mean, rstd, relu, rows, C, acc, group_bias,
-                                                   group_rows, beta);
+  launch_colsum<1>(z, out, g_out, mean, rstd, relu, rows, C, acc, group_bias, group_rows, beta, st);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_colsum_kernel<1>");
   rc = launch_finalize_sums(acc, C, g_beta, s2, st);

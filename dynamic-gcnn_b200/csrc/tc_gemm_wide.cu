@@ -6,12 +6,12 @@
 // MMAs per slice (hi.hi + hi.lo + lo.hi) both the shared-memory read port (8 KB per 64-cycle MMA = 128 B/clk) and the
 // per-SM share of L2 bandwidth (64 KB per 768 MMA cycles = 83 B/clk against ~42 B/clk) sit at or past their limits.
 // A 128x256 tile moves (128+256) rows for twice the outputs: 96 B/clk of shared memory and 62 -> 47 B/clk of L2.
-// Structure (192 threads, one CTA per SM, CTAs loop over (m-tile, n-tile, k-split) work items, n fastest so that
+// Structure (320 threads, one CTA per SM, CTAs loop over (m-tile, n-tile, k-split) work items, n fastest so that
 // neighbouring CTAs share A rows in L2):
 //   warp 0    TMA producer: 2-stage ring of {A hi, A lo (16 KB each), B hi, B lo (32 KB each)} = 96 KB per stage
 //   warp 1    MMA issuer: tcgen05.mma M=128 N=256 K=16, accumulators double-buffered in TMEM (2 x 256 columns), so
 //             the epilogue of one tile overlaps the main loop of the next
-//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns -> fp32 stores; optionally the per-column sum and sum of
+//   warps 2-9 epilogue: tcgen05.ld 32 lanes x 32 columns -> fp32 stores (eight warps: it is store-issue bound); optionally (warps 2-5 only) the per-column sum and sum of
 //             squares of the tile's rows (train-mode BatchNorm statistics of slim.batch_norm, ops.py:53, taken from
 //             the accumulator instead of a second pass over the output) -> colstats[m_tile][2][N]
 #include <stdlib.h>
@@ -20,7 +20,7 @@
 
 namespace dgcnn {
 
-constexpr int W_M = 128, W_N = 256, W_K = 64, W_THREADS = 192, W_STAGES = 2;
+constexpr int W_M = 128, W_N = 256, W_K = 64, W_THREADS = 320, W_STAGES = 2;
 constexpr uint32_t W_ATILE = W_M * W_K * 2;   // 16 KB: one bf16 plane of the A tile
 constexpr uint32_t W_BTILE = W_N * W_K * 2;   // 32 KB: one bf16 plane of the B tile
 constexpr uint32_t W_STAGE = 2 * W_ATILE + 2 * W_BTILE;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(W_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);   // one arrival per epilogue warp
+      mbar_init(&acc_empty[i], out.colstats != nullptr ? 4 : 8);   // one arrival per active epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -143,12 +143,18 @@ __global__ void __launch_bounds__(W_THREADS, 1)
       if (kb_end <= kb_begin && lane == 0) mbar_arrive(&acc_full[ab]);   // empty split: publish (garbage is never read)
     }
   } else {
-    // epilogue warps 2..5 -> TMEM sub-partitions (warp % 4)
+    // epilogue warps 2..9 -> TMEM sub-partitions (warp % 4).  Plain epilogue: all eight warps, the two warps of a
+    // sub-partition take four 32-column chunks each (the epilogue is bound by how many stores are in flight).
+    // Statistics epilogue: warps 2..5 only (its transpose buffers exist four times).
     const int sub = warp & 3;
-    const int et = threadIdx.x - 64;   // 0..127
+    const int eh = (warp - 2) >> 2;    // 0: warps 2..5, 1: warps 6..9
+    const bool stats = out.colstats != nullptr;
+    const bool active = !(stats && eh == 1);
+    const int ch_begin = stats ? 0 : eh * 4, ch_end = stats ? W_N / 32 : eh * 4 + 4;
+    const int et = threadIdx.x - 64;   // 0..127 for warps 2..5
     float* trw = tr + sub * 32 * 33;
     uint32_t tile = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++tile) {
+    for (int w = blockIdx.x; active && w < total; w += gridDim.x, ++tile) {
       const int split = w / (mt_n * nt_n);
       const int rem = w - split * (mt_n * nt_n);
       const int mt = rem / nt_n;
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(W_THREADS, 1)
       mbar_wait(&acc_full[ab], (tile >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int ch = 0; ch < W_N / 32; ++ch) {
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(sub * 32) << 16) + ab * W_N + (uint32_t)(ch * 32), v);
         if (empty) {

@@ -32,8 +32,8 @@ def test_workspace_queries_are_pure(dg):
     # xT [B,C,Npad] + s [B,Npad], Npad = N rounded up to 128
     base = (24 * 64 * 2048 + 24 * 2048) * 4
     got = lib.dgcnn_knn_workspace_bytes(24, 2048, 64)   # + tensor-core filter scratch: norms, fp16 operand, norm
-    # k-slices, candidate lists (4 x 32 x u16 per row), counts, fallback queue  (knn_tc.cu knn_tc_bytes)
-    per_row = 8 + 64 * 2 + 64 + 4 * 32 * 2 + 4 + 16
+    # k-slices, candidate lists (4 x 48 x u16 per row), counts, fallback queue  (knn_tc.cu knn_tc_bytes)
+    per_row = 8 + 2 * 64 * 2 + 64 + 4 * 48 * 2 + 4 + 16
     assert base + 24 * 2048 * per_row <= got <= base + 24 * 2048 * (per_row + 8)   # + per-cloud range partials
     assert lib.dgcnn_knn_workspace_bytes(24, 2048, 64) == got                 # pure function of the shape
     assert lib.dgcnn_knn_workspace_bytes(2, 100, 3) == (2 * 3 * 128 + 2 * 128) * 4
