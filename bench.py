@@ -217,43 +217,61 @@ def run_ours(args):
     ms_e2e, _ = timed(True, args.steps)
 
     # per-kernel timing for the roofline entry: the same steps issued eagerly (a captured graph cannot carry timing
-    # events), k_nn bracketed by CUDA events on the launching stream
+    # events), the kernels of interest bracketed by CUDA events on the launching stream
     os.environ["DGCNN_CUDA_GRAPH"] = "0"
-    ops._knn_events = []
+    ops._knn_events, ops._gemm_events = [], []
     barrier()
     for i in range(3):
         step(i, False)
     barrier()
     ev, ops._knn_events = ops._knn_events, None
+    gev, ops._gemm_events = ops._gemm_events, None
     os.environ.pop("DGCNN_CUDA_GRAPH", None)
 
     pts_per_step = B_PER_GPU * NPTS * world
     value = pts_per_step * args.steps / (ms_dev * 1e-3)
     e2e = pts_per_step * args.steps / (ms_e2e * 1e-3)
 
-    # roofline of the dominant hand-written kernel: fused k_nn on 64-channel features
+    # Roofline of the dominant kernel: tc_gemm_wide_kernel on the FC0 layer (ops.py:151-160: the 1x1 conv over the
+    # 1792 non-broadcast channels of model.py:83-85's concat -> 512), the largest single launch of the step.
     pk, pk_kind = peaks()
+    P_ = B_PER_GPU * NPTS
+    fc0 = [a.elapsed_time(b) for (m, n, k, a, b) in gev if n == FCF[0] and m == P_]
+    kfc0 = max([k for (m, n, k, a, b) in gev if n == FCF[0] and m == P_], default=0)
     knn64 = [a.elapsed_time(b) for (_, _, c, _, a, b) in ev if c == 64]
     knn3 = [a.elapsed_time(b) for (_, _, c, _, a, b) in ev if c == CH]
     roof = None
-    if knn64:
-        t_ms = float(np.mean(knn64))
-        flops = 2.0 * B_PER_GPU * NPTS * NPTS * 64          # 12.88 GF of -2.X.X^T per 64-channel layer
-        unfused_bytes = 821.9e6                              # K1 415.3 MB + K2 406.6 MB if the matrix hit HBM
+    if fc0:
+        t_ms = float(np.mean(fc0))
+        flops = 2.0 * P_ * FCF[0] * kfc0                     # algorithmic: one fp32 multiply-add per (row, col, k)
         ach = flops / (t_ms * 1e-3) / 1e12
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-        roof = {"kernel": "fused k_nn on the 64-channel layers: dgcnn_knn_hinted = prep + bf16 split + hint bound + "
-                          "knn_tc_filter_kernel (tcgen05 bf16x3 -> TMEM -> threshold scan) + exact refine (+ row fallback)",
+        roof = {"kernel": "tc_gemm_wide_kernel<A K-major, B MN-major> on FC0 forward: [%d x %d] . [%d x %d], persistent "
+                          "128x256 tiles, TMA -> 2-stage smem ring -> tcgen05.mma (3 bf16 MMAs per k-slice: hi.hi + hi.lo + "
+                          "lo.hi, fp32 accumulate in TMEM, double-buffered) -> epilogue with BN column statistics"
+                          % (P_, kfc0, kfc0, FCF[0]),
                 "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": None, "peak_source": pk_kind + " bf16 sustained (kernel timed inside the step)",
-                "ms_per_launch": t_ms, "launches_timed": len(knn64),
+                "traffic": 438.2e6, "traffic_source": "profiles/r01e_top_kernels_ncu_full.csv: ncu --set full of this launch, "
+                                                       "dram read 362.8 MB + write 75.4 MB (algorithmic: bf16 hi/lo operand "
+                                                       "planes 352 MB + weights 3.7 MB + fp32 output 100.7 MB)",
+                "peak_source": pk_kind + " bf16 sustained (kernel timed inside the step)",
+                "ms_per_launch": t_ms, "launches_timed": len(fc0),
                 "algorithmic_flops": flops, "executed_tensor_flops": 3 * flops,
-                "effective_unfused_hbm_gbs": unfused_bytes / (t_ms * 1e-3) / 1e9,
-                "note": "algorithmic FLOPs = one fp32 X.X^T per layer (12.88 GF); the kernel executes 3 bf16 MMAs per "
-                        "k-slice for a certified fp32-accurate filter, and the [B,N,N] matrix never leaves TMEM "
-                        "(compulsory HBM traffic 16.5 MB), so the call is selection/latency bound, not HBM bound",
-                "knn_c3_ms_per_launch": float(np.mean(knn3)) if knn3 else None,
-                "knn_share_of_step": (sum(knn64) + sum(knn3)) / 3.0 / (ms_dev / args.steps)}
+                "executed_frac_of_peak": 3 * ach / peak,
+                "note": "achieved counts ONE multiply-add per product (the fp32 GEMM the reference runs); the kernel "
+                        "executes three bf16 MMAs per product to stay within the 1e-3 logits bound, so the tensor pipe "
+                        "itself runs at executed_frac_of_peak of the measured cuBLAS bf16 rate",
+                "other_kernels": {
+                    "k_nn_fused_64ch": {
+                        "what": "dgcnn_knn on [24,2048,64]: range + prep + knn_tc_filter_kernel (fp16 tcgen05 pass, two "
+                                "sweeps over TMEM accumulators) + exact refine; the [B,N,N] matrix never leaves the SM",
+                        "ms_per_call": float(np.mean(knn64)) if knn64 else None,
+                        "bound": "TMEM read port (64 B/clk/SM): 2 sweeps x 402.7 MB of fp32 accumulators",
+                        "effective_unfused_hbm_gbs": (821.9e6 / (float(np.mean(knn64)) * 1e-3) / 1e9) if knn64 else None,
+                        "algorithmic_tflops": (2.0 * B_PER_GPU * NPTS * NPTS * 64 / (float(np.mean(knn64)) * 1e-3) / 1e12)
+                        if knn64 else None},
+                    "k_nn_fused_xyz": {"ms_per_call": float(np.mean(knn3)) if knn3 else None},
+                    "knn_share_of_step": (sum(knn64) + sum(knn3)) / 3.0 / (ms_dev / args.steps)}}
 
     if rank == 0:
         cb = cpu_baseline_run(3, 1) if (world == 1 and not args.no_cpu_baseline) else None

@@ -30,8 +30,10 @@ CONV1_WIDTH = 64  # ops.py:63
 # test hooks (never set by the product): _knn_trace collects each layer's kNN indices; _knn_forced supplies them
 _knn_trace = None
 _knn_forced = None
-# bench.py hook: when a list, k_nn() brackets its C-ABI call with CUDA events on the launching stream
+# bench.py hooks: when a list, k_nn() / the head's forward GEMM bracket their C-ABI call with CUDA events on the
+# launching stream (eager mode only: a captured graph cannot carry timing events)
 _knn_events = None
+_gemm_events = None
 
 
 def _layer_knn(x, k, hint=None):
@@ -304,8 +306,15 @@ class _ConvBnActTC(torch.autograd.Function):
             z = torch.empty((P, Cout), dtype=torch.float32, device=dev)
             tiles = (P + 127) // 128
             cs = torch.empty((tiles, 2, Cout), dtype=torch.float32, device=dev)
+            ev = None
+            if _gemm_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             nv.check(L.dgcnn_tc_gemm_stats(planes.data_ptr(), pw.data_ptr(), z.data_ptr(), P, Cout, K, 0, 0, cs.data_ptr(),
                                            st), "tc_gemm_stats")
+            if ev is not None:
+                ev[1].record()
+                _gemm_events.append((P, Cout, K, ev[0], ev[1]))
             nv.check(L.dgcnn_bn_stats_from_tiles(cs.data_ptr(), tiles, Cout, P, nv.ptr(gb), grows, mean.data_ptr(),
                                                  rstd.data_ptr(), st), "bn_stats_from_tiles")
             nv.check(L.dgcnn_bn_apply_fwd(z.data_ptr(), P, Cout, beta.data_ptr(), 0, nv.ptr(gb), grows,
