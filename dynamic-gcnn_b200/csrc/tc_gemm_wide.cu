@@ -11,7 +11,7 @@
 //   warp 0    TMA producer: 2-stage ring of {A hi, A lo (16 KB each), B hi, B lo (32 KB each)} = 96 KB per stage
 //   warp 1    MMA issuer: tcgen05.mma M=128 N=256 K=16, accumulators double-buffered in TMEM (2 x 256 columns), so
 //             the epilogue of one tile overlaps the main loop of the next
-//   warps 2-9 epilogue: tcgen05.ld 32 lanes x 32 columns -> fp32 stores (eight warps: it is store-issue bound); optionally (warps 2-5 only) the per-column sum and sum of
+//   warps 2-9 epilogue: tcgen05.ld 32 lanes x 32 columns -> fp32 stores; optionally the per-column sum and sum of
 //             squares of the tile's rows (train-mode BatchNorm statistics of slim.batch_norm, ops.py:53, taken from
 //             the accumulator instead of a second pass over the output) -> colstats[m_tile][2][N]
 #include <stdlib.h>
@@ -24,8 +24,8 @@ constexpr int W_M = 128, W_N = 256, W_K = 64, W_THREADS = 320, W_STAGES = 2;
 constexpr uint32_t W_ATILE = W_M * W_K * 2;   // 16 KB: one bf16 plane of the A tile
 constexpr uint32_t W_BTILE = W_N * W_K * 2;   // 32 KB: one bf16 plane of the B tile
 constexpr uint32_t W_STAGE = 2 * W_ATILE + 2 * W_BTILE;
-constexpr size_t W_TR_OFF = (size_t)W_STAGES * W_STAGE;            // 4 warps x [32][33] floats (transpose for stats)
-constexpr size_t W_CS_OFF = W_TR_OFF + 4 * 32 * 33 * 4;            // [4 warps][256 cols][2] floats
+constexpr size_t W_TR_OFF = (size_t)W_STAGES * W_STAGE;            // 8 warps x [32][17] floats (half-chunk transposes)
+constexpr size_t W_CS_OFF = W_TR_OFF + 8 * 32 * 17 * 4;            // [4 sub-partitions][256 cols][2] floats
 constexpr size_t W_BAR_OFF = W_CS_OFF + 4 * 256 * 2 * 4;
 constexpr size_t W_SMEM = W_BAR_OFF + 128 + 1024 /*align*/;
 
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(W_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], out.colstats != nullptr ? 4 : 8);   // one arrival per active epilogue warp
+      mbar_init(&acc_empty[i], 8);   // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -143,16 +143,14 @@ __global__ void __launch_bounds__(W_THREADS, 1)
       if (kb_end <= kb_begin && lane == 0) mbar_arrive(&acc_full[ab]);   // empty split: publish (garbage is never read)
     }
   } else {
-    // epilogue warps 2..9 -> TMEM sub-partitions (warp % 4).  Plain epilogue: all eight warps, the two warps of a
-    // sub-partition take four 32-column chunks each (the epilogue is bound by how many stores are in flight).
-    // Statistics epilogue: warps 2..5 only (its transpose buffers exist four times).
+    // epilogue warps 2..9 -> TMEM sub-partitions (warp % 4); the two warps of a sub-partition take four 32-column
+    // chunks each (the epilogue is bound by latency and stores in flight, not by instruction issue)
     const int sub = warp & 3;
     const int eh = (warp - 2) >> 2;    // 0: warps 2..5, 1: warps 6..9
-    const bool stats = out.colstats != nullptr;
-    const bool active = !(stats && eh == 1);
-    const int ch_begin = stats ? 0 : eh * 4, ch_end = stats ? W_N / 32 : eh * 4 + 4;
-    const int et = threadIdx.x - 64;   // 0..127 for warps 2..5
-    float* trw = tr + sub * 32 * 33;
+    const bool active = true;
+    const int ch_begin = eh * 4, ch_end = eh * 4 + 4;
+    const int et = threadIdx.x - 64;   // 0..255
+    float* trw = tr + (warp - 2) * 32 * 17;
     uint32_t tile = 0;
     for (int w = blockIdx.x; active && w < total; w += gridDim.x, ++tile) {
       const int split = w / (mt_n * nt_n);
@@ -162,7 +160,6 @@ __global__ void __launch_bounds__(W_THREADS, 1)
       const int kb_begin = split * kblocks_per_split;
       const bool empty = min(kb_total, kb_begin + kblocks_per_split) <= kb_begin;
       const uint32_t ab = tile & 1;
-      const int row = m0 + sub * 32 + lane;
       float* Cout = out.C + (size_t)split * M * N;
       mbar_wait(&acc_full[ab], (tile >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -175,47 +172,57 @@ __global__ void __launch_bounds__(W_THREADS, 1)
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
         const int c0 = n0 + ch * 32;
-        if (out.colstats != nullptr) {
-          // transpose through shared memory: lane c then owns column c of the warp's 32 rows
+        // where this 32-column chunk goes
+        float* obase = Cout + c0;
+        int opitch = N;
+        if (out.n_groups > 0) {
+          obase = nullptr;
+          for (int g = 0; g < out.n_groups; ++g)
+            if (c0 >= out.start[g] && c0 < out.start[g] + out.width[g]) {
+              obase = out.ptr[g] + (c0 - out.start[g]);
+              opitch = out.width[g];
+            }
+        }
+        if (out.dbg_nostore) obase = nullptr;
+        // Transpose through shared memory in two 16-column halves: lane (c, rh) then owns column c of the rows
+        // rh, rh+2, ...  Every store instruction writes two 64-byte row segments (whole 32-byte sectors; a lane
+        // storing 16 bytes of its own row would fill half a sector per transaction), and the column statistics
+        // fall out of the same loop.
+        const int c = lane & 15, rh = lane >> 4;
+        const int rbase = m0 + sub * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) trw[lane * 33 + i] = __uint_as_float(v[i]);
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) trw[lane * 17 + i] = __uint_as_float(v[h * 16 + i]);
           __syncwarp();
           float s1 = 0.0f, s2 = 0.0f;
+          float* o = obase != nullptr ? obase + (size_t)(rbase + rh) * opitch + h * 16 + c : nullptr;
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const float z = trw[r * 33 + lane];
+          for (int r = 0; r < 16; ++r) {
+            const float z = trw[(2 * r + rh) * 17 + c];
             s1 += z;
             s2 = fmaf(z, z, s2);
+            if (o != nullptr && rbase + 2 * r + rh < M) o[(size_t)(2 * r) * opitch] = z;
           }
-          cs[(sub * 256 + ch * 32 + lane) * 2] = s1;
-          cs[(sub * 256 + ch * 32 + lane) * 2 + 1] = s2;
+          if (out.colstats != nullptr) {
+            s1 += __shfl_xor_sync(FULL, s1, 16);
+            s2 += __shfl_xor_sync(FULL, s2, 16);
+            if (rh == 0) {
+              cs[(sub * 256 + ch * 32 + h * 16 + c) * 2] = s1;
+              cs[(sub * 256 + ch * 32 + h * 16 + c) * 2 + 1] = s2;
+            }
+          }
           __syncwarp();
-        }
-        if (row < M) {
-          float* o = Cout + (size_t)row * N + c0;
-          if (out.n_groups > 0) {
-            o = nullptr;
-            for (int g = 0; g < out.n_groups; ++g)
-              if (c0 >= out.start[g] && c0 < out.start[g] + out.width[g])
-                o = out.ptr[g] + (size_t)row * out.width[g] + (c0 - out.start[g]);
-          }
-          if (o != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(o + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
-                                                              __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[ab]);   // accumulator drained: the MMA warp may start tile + 2
       if (out.colstats != nullptr) {
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync 2, 256;" ::: "memory");
         float* o = out.colstats + (size_t)mt * 2 * N + n0;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int c = et + q * 128;
+        {
+          const int c = et;   // one column per epilogue thread
           float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
           for (int wv = 0; wv < 4; ++wv) {
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(W_THREADS, 1)
           o[c] = s1;
           o[N + c] = s2;
         }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync 2, 256;" ::: "memory");
       }
     }
   }
