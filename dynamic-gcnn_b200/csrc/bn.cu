@@ -147,7 +147,10 @@ static void launch_colsum(const float* z, const float* out, const float* gout, c
   const bool vec = (C & 3) == 0 && C >= 16 &&
                    (((uintptr_t)z | (uintptr_t)out | (uintptr_t)gout | (uintptr_t)gbias | (uintptr_t)mean |
                      (uintptr_t)rstd | (uintptr_t)beta) & 15) == 0;
-  const int nb = bn_blocks(rows);
+  int nb = bn_blocks(rows);
+  // every block ends with 2*cb fp64 atomics onto the same 2*C addresses: with narrow tensors (C <= 128) that tail, not
+  // the streaming, sets the time -- fewer, longer blocks there
+  if (C <= 128 && nb > 2 * num_sms()) nb = 2 * num_sms();
   if (vec) {
     int cb = 256;
     while (cb > C) cb >>= 1;                        // 16 .. 256, a power of two <= C
@@ -182,11 +185,21 @@ __global__ void __launch_bounds__(256)
       if (res) rr[0] = res[e];
       if (gbias) gb[0] = gbias[(size_t)(r / grows) * C + c];
     }
+    float mu[VEC], rs[VEC], be[VEC];
+    if (VEC == 4) {   // per-channel constants as 16-byte loads too (they are L1-resident)
+      *reinterpret_cast<float4*>(mu) = __ldg(reinterpret_cast<const float4*>(mean + c));
+      *reinterpret_cast<float4*>(rs) = __ldg(reinterpret_cast<const float4*>(rstd + c));
+      *reinterpret_cast<float4*>(be) = __ldg(reinterpret_cast<const float4*>(beta + c));
+    } else {
+      mu[0] = mean[c];
+      rs[0] = rstd[c];
+      be[0] = beta[c];
+    }
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       float zv = zz[i];
       if (gbias) zv += gb[i];
-      float t = fmaf(zv - mean[c + i], rstd[c + i], beta[c + i]);
+      float t = fmaf(zv - mu[i], rs[i], be[i]);
       if (res) t += rr[i];
       y[i] = relu ? fmaxf(t, 0.f) : t;
     }
@@ -221,15 +234,29 @@ __global__ void __launch_bounds__(256)
       if (relu && out) oo[0] = out[e];
       if (gbias) gb[0] = gbias[(size_t)(r / grows) * C + c];
     }
+    float mu[VEC], rsv[VEC], be[VEC], a1[VEC], a2[VEC];
+    if (VEC == 4) {   // per-channel constants as 16-byte loads too (they are L1-resident)
+      *reinterpret_cast<float4*>(mu) = __ldg(reinterpret_cast<const float4*>(mean + c));
+      *reinterpret_cast<float4*>(rsv) = __ldg(reinterpret_cast<const float4*>(rstd + c));
+      *reinterpret_cast<float4*>(a1) = __ldg(reinterpret_cast<const float4*>(s1 + c));
+      *reinterpret_cast<float4*>(a2) = __ldg(reinterpret_cast<const float4*>(s2 + c));
+      if (beta) *reinterpret_cast<float4*>(be) = __ldg(reinterpret_cast<const float4*>(beta + c));
+    } else {
+      mu[0] = mean[c];
+      rsv[0] = rstd[c];
+      a1[0] = s1[c];
+      a2[0] = s2[c];
+      if (beta) be[0] = beta[c];
+    }
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       float gp = gg[i];
-      const float rs = rstd[c + i];
+      const float rs = rsv[i];
       float zv = zz[i];
       if (gbias) zv += gb[i];
-      if (relu && !((out ? oo[i] : fmaf(zv - mean[c + i], rs, beta[c + i])) > 0.f)) gp = 0.f;
-      const float zh = (zv - mean[c + i]) * rs;
-      gzv[i] = rs * (gp - s1[c + i] * inv_rows - zh * (s2[c + i] * inv_rows));
+      if (relu && !((out ? oo[i] : fmaf(zv - mu[i], rs, be[i])) > 0.f)) gp = 0.f;
+      const float zh = (zv - mu[i]) * rs;
+      gzv[i] = rs * (gp - a1[i] * inv_rows - zh * (a2[i] * inv_rows));
       gpv[i] = gp;
     }
     if (VEC == 4) {
@@ -458,7 +485,8 @@ extern "C" int dgcnn_bn_act_fwd_gb(const float* z, int64_t rows, int C, const fl
   if (rc) return rc;
   const int64_t total = rows * C;
   DG_REQUIRE(total < (1ll << 32), DGCNN_ERR_UNSUPPORTED, "bn_act_fwd: more than 2^32 elements");
-  const bool vec = (C & 3) == 0 && (((uintptr_t)z | (uintptr_t)out | (uintptr_t)residual | (uintptr_t)group_bias) & 15) == 0;
+  const bool vec = (C & 3) == 0 && (((uintptr_t)z | (uintptr_t)out | (uintptr_t)residual | (uintptr_t)group_bias |
+                                     (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta) & 15) == 0;
   if (vec)
     bn_act_fwd_kernel<4><<<ew_blocks(total / 4), 256, 0, st>>>(z, mean, rstd, beta, residual, relu, (uint32_t)(total / 4), C,
                                                                out, group_bias, group_rows);
@@ -495,7 +523,8 @@ extern "C" int dgcnn_bn_apply_fwd(const float* z, int64_t rows, int C, const flo
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = rows * C;
   DG_REQUIRE(total < (1ll << 32), DGCNN_ERR_UNSUPPORTED, "bn_apply_fwd: more than 2^32 elements");
-  const bool vec = (C & 3) == 0 && (((uintptr_t)z | (uintptr_t)out | (uintptr_t)residual | (uintptr_t)group_bias) & 15) == 0;
+  const bool vec = (C & 3) == 0 && (((uintptr_t)z | (uintptr_t)out | (uintptr_t)residual | (uintptr_t)group_bias |
+                                     (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta) & 15) == 0;
   if (vec)
     bn_act_fwd_kernel<4><<<ew_blocks(total / 4), 256, 0, st>>>(z, mean, rstd, beta, residual, relu, (uint32_t)(total / 4), C,
                                                                out, group_bias, group_rows);
@@ -564,7 +593,8 @@ static int bn_act_bwd_impl(const float* z, const float* out, const float* g_out,
   const int64_t total = rows * C;
   DG_REQUIRE(total < (1ll << 32), DGCNN_ERR_UNSUPPORTED, "bn_act_bwd: more than 2^32 elements");
   const bool vec = (C & 3) == 0 && (((uintptr_t)z | (uintptr_t)out | (uintptr_t)g_out | (uintptr_t)g_z | (uintptr_t)g_pre |
-                                     (uintptr_t)group_bias) & 15) == 0;
+                                     (uintptr_t)group_bias | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta |
+                                     (uintptr_t)g_beta | (uintptr_t)s2) & 15) == 0;
   DG_REQUIRE(vec || !g_z_planes, DGCNN_ERR_INVALID, "bn_act_bwd: plane output needs 16-byte aligned buffers, C %% 4 == 0");
   if (vec)
     bn_act_bwd_kernel<4><<<ew_blocks(total / 4), 256, 0, st>>>(z, out, g_out, mean, rstd, g_beta, s2, relu,
