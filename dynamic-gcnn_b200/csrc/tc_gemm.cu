@@ -255,12 +255,25 @@ static int tc_splits(int M, int N, int K) {
   return s < 1 ? 1 : s;
 }
 
-__global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ C, int64_t MN, int splits) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= MN) return;
+// C = sum over splits of part[z], in a fixed order: block = 32 consecutive outputs x 8 split lanes (warp w adds
+// splits w, w+8, ...: coalesced 128-byte reads), the 8 partial sums are then added in warp order; 8x the parallelism
+// of one thread per output, which matters because the weight-gradient shapes have few outputs and ~100 splits
+__global__ void __launch_bounds__(256)
+    tc_splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ C, int64_t MN, int splits) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t o = (int64_t)blockIdx.x * 32 + lane;
   float s = 0.0f;
-  for (int z = 0; z < splits; ++z) s += part[(size_t)z * MN + i];
-  C[i] = s;
+  if (o < MN)
+    for (int z = w; z < splits; z += 8) s += part[(size_t)z * MN + o];
+  red[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && o < MN) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += red[i][lane];
+    C[o] = t;
+  }
 }
 
 int launch_split_bf16(const float* x, int64_t rows, int cols, int64_t ldx, void* planes, int64_t ldo,
@@ -385,7 +398,7 @@ static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, in
     if (rc) return rc;
     if (wsplits > 1) {
       const int64_t MN = (int64_t)M * N;
-      tc_splitk_reduce_kernel<<<cdiv(MN, 256), 256, 0, st>>>(wo.C, C, MN, wsplits);
+      tc_splitk_reduce_kernel<<<cdiv(MN, 32), 256, 0, st>>>(wo.C, C, MN, wsplits);
       count_launch();
       DG_CUDA_LAUNCH_CHECK("tc_splitk_reduce_kernel");
     }
@@ -433,7 +446,7 @@ static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, in
   DG_CUDA_LAUNCH_CHECK("tc_gemm_kernel");
   if (splits > 1) {
     const int64_t MN = (int64_t)M * N;
-    tc_splitk_reduce_kernel<<<cdiv(MN, 256), 256, 0, st>>>(out, C, MN, splits);
+    tc_splitk_reduce_kernel<<<cdiv(MN, 32), 256, 0, st>>>(out, C, MN, splits);
     count_launch();
     DG_CUDA_LAUNCH_CHECK("tc_splitk_reduce_kernel");
   }
