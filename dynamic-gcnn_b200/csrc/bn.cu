@@ -656,3 +656,77 @@ extern "C" int dgcnn_group_max_bwd_add(const float* x, const float* out, const f
   DG_CUDA_LAUNCH_CHECK("group_max_bwd_add_kernel");
   return DGCNN_OK;
 }
+
+// ---- loss head: softmax + sparse cross-entropy (x weight) + accuracy + d loss / d logits in one pass ----------------
+// /root/reference/dgcnn/trainval.py:39-52: softmax, argmax == label accuracy, mean over all points of the (weighted)
+// per-point cross-entropy.  One thread per point; the gradient of the MEAN loss is written directly, so the
+// backward pass has nothing left to compute.  acc = {loss sum, correct count} (fp64), out = {loss, accuracy}.
+namespace dgcnn {
+__global__ void __launch_bounds__(256)
+    softmax_xent_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                        const float* __restrict__ weights, int64_t P, int K, float* __restrict__ grad,
+                        double* __restrict__ acc, unsigned int* __restrict__ counter, float* __restrict__ out) {
+  __shared__ double red[2][8];
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double loss = 0.0, correct = 0.0;
+  if (p < P) {
+    const float* l = logits + p * K;
+    float m = l[0];
+    int am = 0;
+    for (int c = 1; c < K; ++c)
+      if (l[c] > m) { m = l[c]; am = c; }          // first maximum, like argmax
+    float se = 0.f;
+    for (int c = 0; c < K; ++c) se += expf(l[c] - m);
+    const int y = (int)labels[p];
+    const float w = weights ? weights[p] : 1.0f;
+    const float lse = m + logf(se);
+    loss = (double)((lse - l[y]) * w);
+    correct = am == y ? 1.0 : 0.0;
+    const float gs = w / (float)P;
+    const float inv = 1.0f / se;
+    for (int c = 0; c < K; ++c) grad[p * K + c] = (expf(l[c] - m) * inv - (c == y ? 1.0f : 0.0f)) * gs;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    loss += __shfl_xor_sync(FULL, loss, o);
+    correct += __shfl_xor_sync(FULL, correct, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = loss;
+    red[1][threadIdx.x >> 5] = correct;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      loss += red[0][w];
+      correct += red[1][w];
+    }
+    atomicAdd(&acc[0], loss);
+    atomicAdd(&acc[1], correct);
+    __threadfence();
+    if (atomicAdd(counter, 1u) == gridDim.x - 1) {   // last block: publish the means
+      __threadfence();
+      out[0] = (float)(atomicAdd(&acc[0], 0.0) / (double)P);
+      out[1] = (float)(atomicAdd(&acc[1], 0.0) / (double)P);
+    }
+  }
+}
+}  // namespace dgcnn
+
+extern "C" size_t dgcnn_softmax_xent_workspace_bytes(void) { return 32; }
+
+extern "C" int dgcnn_softmax_xent(const float* logits, const int64_t* labels, const float* weights, int64_t P, int K,
+                                  float* grad, float* loss_acc, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
+  DG_REQUIRE(logits && labels && grad && loss_acc && ws, DGCNN_ERR_INVALID, "softmax_xent: null pointer");
+  DG_REQUIRE(P > 0 && K > 0 && K <= 4096, DGCNN_ERR_INVALID, "softmax_xent: bad shape P=%lld K=%d", (long long)P, K);
+  DG_REQUIRE(ws_bytes >= 32 && ((uintptr_t)ws & 7) == 0, DGCNN_ERR_WORKSPACE, "softmax_xent: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(ws, 0, 32, st) != cudaSuccess) return set_err(DGCNN_ERR_CUDA, "softmax_xent: memset failed");
+  const int64_t blocks = (P + 255) / 256;
+  DG_REQUIRE(blocks < (1ll << 31), DGCNN_ERR_UNSUPPORTED, "softmax_xent: too many points");
+  softmax_xent_kernel<<<(unsigned)blocks, 256, 0, st>>>(logits, labels, weights, P, K, grad, (double*)ws,
+                                                        reinterpret_cast<unsigned int*>((char*)ws + 16), loss_acc);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("softmax_xent_kernel");
+  return DGCNN_OK;
+}

@@ -58,6 +58,8 @@ SIGNATURES = {
     "dgcnn_group_max_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "dgcnn_group_max_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "dgcnn_group_max_bwd_add": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "dgcnn_softmax_xent_workspace_bytes": (_sz, []),
+    "dgcnn_softmax_xent": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _sz, _vp]),
     "dgcnn_adam_tf_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _vp]),
 }
 

@@ -522,6 +522,39 @@ def pool_and_pass(x: torch.Tensor):
     return x, x.amax(dim=1)
 
 
+class _SoftmaxXent(torch.autograd.Function):
+    """trainval.py:39-52 fused: (logits [P,K], labels [P] int64, weights [P] or None) -> (mean weighted cross-entropy,
+    accuracy); the gradient of the loss w.r.t. the logits is produced by the same kernel."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, weights):
+        logits = nv.require_cuda(logits, "logits")
+        labels = nv.require_cuda(labels, "labels", torch.int64)
+        weights = nv.require_cuda(weights, "weights") if weights is not None else None
+        P, K = logits.shape
+        dev = logits.device
+        L = nv.lib()
+        grad = torch.empty_like(logits)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        ws = torch.empty(L.dgcnn_softmax_xent_workspace_bytes(), dtype=torch.uint8, device=dev)
+        nv.check(L.dgcnn_softmax_xent(logits.data_ptr(), labels.data_ptr(), nv.ptr(weights), P, K, grad.data_ptr(),
+                                      out.data_ptr(), ws.data_ptr(), ws.numel(), nv.stream_ptr(dev)), "softmax_xent")
+        ctx.save_for_backward(grad)
+        loss, acc = out[0].clone(), out[1].clone()
+        ctx.mark_non_differentiable(acc)
+        return loss, acc
+
+    @staticmethod
+    def backward(ctx, gloss, gacc):
+        (grad,) = ctx.saved_tensors
+        return grad * gloss, None, None
+
+
+def softmax_xent(logits2d, labels1d, weights1d=None):
+    """-> (loss, accuracy) 0-d tensors; differentiable w.r.t. logits2d."""
+    return _SoftmaxXent.apply(logits2d, labels1d, weights1d)
+
+
 def global_max_pool(x: torch.Tensor) -> torch.Tensor:
     """x [B,N,C] -> [B,C]: hand-written kernels when C % 4 == 0, else torch.amax (same tie semantics)."""
     if x.shape[-1] % 4 == 0:

@@ -86,22 +86,22 @@ class trainval(object):
                       self._to_dev(weight[i], torch.float32) if weight is not None else None)
         return res
 
-    def _forward(self, points, labels, weights, dropout_mask=None):
+    def _forward(self, points, labels, weights, dropout_mask=None, want_softmax=True):
         old = set_default_store(self._store)
         try:
             with self._store.variable_scope("dgcnn"):
                 pred = _model.build(points, self._flags, dropout_mask=dropout_mask)      # trainval.py:38
         finally:
             set_default_store(old)
-        softmax = torch.softmax(pred, dim=-1)                                             # trainval.py:39
+        softmax = torch.softmax(pred, dim=-1) if want_softmax else None                   # trainval.py:39
         accuracy = loss = None
         if labels is not None:
-            accuracy = (pred.argmax(dim=2) == labels).to(torch.float32).mean()           # trainval.py:41-42
-            xent = torch.nn.functional.cross_entropy(pred.reshape(-1, pred.shape[-1]), labels.reshape(-1),
-                                                     reduction="none").reshape(labels.shape)
-            if weights is not None:                                                       # trainval.py:47-51
-                xent = xent * weights
-            loss = xent.mean()                                                            # trainval.py:52
+            # trainval.py:41-52: accuracy, per-point cross-entropy (x weight), mean -- one fused kernel that also
+            # leaves d loss / d logits behind
+            from . import ops as _ops
+            K = pred.shape[-1]
+            loss, accuracy = _ops.softmax_xent(pred.reshape(-1, K), labels.reshape(-1),
+                                               weights.reshape(-1) if weights is not None else None)
         return softmax, accuracy, loss
 
     # ------------------------------------------------------------------ reference API
@@ -140,7 +140,7 @@ class trainval(object):
         return a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))
 
     def _tower_step_eager(self, pts, lab, wgt, G):
-        _, acc, loss = self._forward(pts, lab, wgt)
+        _, acc, loss = self._forward(pts, lab, wgt, want_softmax=False)
         (loss / G).backward()                                   # grads mean over towers: trainval.py:64-69
         return acc.detach(), loss.detach()
 

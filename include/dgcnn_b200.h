@@ -200,6 +200,14 @@ int dgcnn_group_max_bwd(const float* x, const float* out, const float* cnt, cons
 int dgcnn_group_max_bwd_add(const float* x, const float* out, const float* cnt, const float* g_out, int groups, int rows,
                             int C, float* g_x_inout, dgcnn_stream_t stream);
 
+/* ---- loss head: trainval.py:39-52 in one pass -------------------------------------------------------------------
+ * logits [P,K], labels int64 [P], optional weights [P]:
+ *   loss_acc[0] = mean_p( xent(softmax(logits_p), label_p) * weight_p ), loss_acc[1] = mean_p( argmax_p == label_p ),
+ *   grad [P,K] = d loss_acc[0] / d logits.  Labels outside [0,K) are the caller's error (unchecked, like TF on GPU). */
+size_t dgcnn_softmax_xent_workspace_bytes(void);
+int dgcnn_softmax_xent(const float* logits, const int64_t* labels, const float* weights, int64_t P, int K, float* grad,
+                       float* loss_acc, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+
 /* ---- tf.train.AdamOptimizer update on a flat buffer: trainval.py:17,80 --------------------
  * g' = g*grad_scale; m = b1*m+(1-b1)g'; v = b2*v+(1-b2)g'^2; p -= lr_t*m/(sqrt(v)+eps),
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller (epsilon outside the bias correction). */

@@ -230,3 +230,26 @@ def test_knn_tensor_core_heavy_ties_and_offsets(dg, oracle, cuda):
         got = dg.ops.k_nn(torch.from_numpy(x).to(cuda), k).cpu().numpy()
         ref = oracle.k_nn(torch.from_numpy(x), k).numpy()
         assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("K,weighted", [(2, False), (5, True)])
+def test_fused_loss_head_matches_torch(dg, cuda, K, weighted):
+    """ops.softmax_xent (trainval.py:39-52 in one kernel): loss, accuracy and d loss / d logits vs torch in fp64."""
+    from dgcnn import ops
+    g = torch.Generator().manual_seed(K)
+    P = 3000
+    logits = torch.randn((P, K), generator=g) * 2
+    logits[:50] = 0.0                                   # exact ties: argmax takes the first maximum
+    labels = torch.randint(0, K, (P,), generator=g)
+    w = (torch.rand(P, generator=g) + 0.5) if weighted else None
+    a = logits.to(cuda).requires_grad_(True)
+    loss, acc = ops.softmax_xent(a, labels.to(cuda), w.to(cuda) if weighted else None)
+    (loss * 0.5).backward()
+    b = logits.double().requires_grad_(True)
+    xent = torch.nn.functional.cross_entropy(b, labels, reduction="none")
+    ref = (xent * w.double()).mean() if weighted else xent.mean()
+    (ref * 0.5).backward()
+    racc = (b.argmax(1) == labels).double().mean()
+    assert abs(loss.item() - ref.item()) < 2e-6 * max(1.0, abs(ref.item()))
+    assert abs(acc.item() - racc.item()) < 1e-6
+    assert torch.allclose(a.grad.cpu().double(), b.grad, atol=1e-9, rtol=1e-5)
