@@ -165,21 +165,61 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
 // output is a few hundred numbers but whose contraction runs over all B*N points (Final, and EdgeConv0's 3-channel
 // input).  The 128x64 tile kernel wastes >90 % of its lanes on them; these two are plain streaming kernels that keep
 // the sequential-in-k fmaf order per output (per k-chunk for the gradient, chunks then summed in a fixed order).
-// C[M,N] = A[M,K] . B[K,N], N <= 4, K % 128 == 0... (general K handled with a guarded tail): one warp per row, lanes
-// own interleaved k (coalesced 16-byte loads), a fixed shuffle tree adds the 32 partial dot products.  Deterministic;
-// NOT the sequential-in-k order of sgemm_kernel -- used only for the class-score layer, which no kNN graph depends on.
+// C[M,N] = A[M,K] . B[K,N], N <= 4: one warp per row, lanes own interleaved k (coalesced 16-byte loads), a fixed
+// shuffle tree adds the 32 partial dot products.  Deterministic; NOT the sequential-in-k order of sgemm_kernel -- used
+// only for the class-score layer, which no kNN graph depends on.  The lane's slice of B (K <= 512: at most 4 chunks of
+// 4 k's x 4 columns) is kept in registers across rows.
 __global__ void __launch_bounds__(256)
     sgemm_skinny_n_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C, int M, int N,
                           int K) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const bool vec = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+  if (vec && K <= 512) {
+    float bw[4][4][4];   // [chunk][k in chunk][n]
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const int k = q * 128 + lane * 4 + i;
+          bw[q][i][n] = (k < K && n < N) ? __ldg(Bm + (size_t)k * N + n) : 0.f;
+        }
+    for (int row = warp; row < M; row += nwarps) {
+      const float* ar = A + (size_t)row * K;
+      float a[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = q * 128 + lane * 4;
+        if (k < K) *reinterpret_cast<float4*>(a[q]) = __ldg(reinterpret_cast<const float4*>(ar + k));
+        else a[q][0] = a[q][1] = a[q][2] = a[q][3] = 0.f;
+      }
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int n = 0; n < 4; ++n) acc[n] = __fmaf_rn(a[q][i], bw[q][i][n], acc[n]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(FULL, acc[n], o);
+      }
+      if (lane == 0) {
+        for (int n = 0; n < N; ++n) C[(size_t)row * N + n] = acc[n];
+      }
+    }
+    return;
+  }
   for (int row = warp; row < M; row += nwarps) {
     const float* ar = A + (size_t)row * K;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int k = lane * 4; k < K; k += 128) {
       float a[4];
-      if (k + 3 < K && (K & 3) == 0) {
+      if (vec && k + 3 < K) {
         *reinterpret_cast<float4*>(a) = __ldg(reinterpret_cast<const float4*>(ar + k));
       } else {
 #pragma unroll
@@ -205,57 +245,79 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Weight gradient with one narrow operand (width <= 4) and one wide operand (width <= 256), contraction over K rows:
-//   out[w][s] = sum_k Wd[k][w] * Sd[k][s].  Threads own wide columns (coalesced loads of Wd rows), the narrow row is a
-// broadcast load; block-local row groups and the blocks' partials are summed in a fixed order.
-// part[block][wide][narrow]
+// Weight gradient with one narrow operand (width <= 4) and one wide operand (width 64 / 128 / 256), contraction over
+// K rows:  out[w][s] = sum_k Wd[k][w] * Sd[k][s].  A thread owns 4 consecutive wide columns (16-byte loads of the Wd
+// rows, two rows in flight), the narrow row is a broadcast load; the block's row groups are summed in a fixed order and
+// the block's partial is written in C's own [M][N] layout: part[block][m*N + n].
 __global__ void __launch_bounds__(256)
     sgemm_skinny_dw_kernel(const float* __restrict__ Wd, const float* __restrict__ Sd, float* __restrict__ part, int wide,
-                           int narrow, int K, int kper) {
-  __shared__ float red[256][4];
-  const int groups = 256 / wide;              // row groups per block (wide is 64, 128 or 256 -> 4, 2, 1)
-  const int w = threadIdx.x % wide, rg = threadIdx.x / wide;
+                           int narrow, int K, int kper, int wide_is_a) {
+  __shared__ float red[256][17];
+  const int tpr = wide >> 2;                    // threads per row
+  const int groups = 256 / tpr;                 // row groups per block
+  const int wv = threadIdx.x % tpr, rg = threadIdx.x / tpr;
   const int kbeg = blockIdx.x * kper, kend = min(K, kbeg + kper);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (rg < groups) {
-#pragma unroll 4
-    for (int k = kbeg + rg; k < kend; k += groups) {
-      const float x = __ldg(Wd + (size_t)k * wide + w);
+  float acc[4][4];
 #pragma unroll
-      for (int s2 = 0; s2 < 4; ++s2)
-        if (s2 < narrow) acc[s2] = __fmaf_rn(x, __ldg(Sd + (size_t)k * narrow + s2), acc[s2]);
-    }
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  auto step = [&](int k) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(Wd + (size_t)k * wide + wv * 4));
+    float sv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sv[j] = j < narrow ? __ldg(Sd + (size_t)k * narrow + j) : 0.f;
+    const float xx[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = __fmaf_rn(xx[i], sv[j], acc[i][j]);
+  };
+  int k = kbeg + rg;
+  for (; k + groups < kend; k += 2 * groups) {
+    step(k);
+    step(k + groups);
   }
+  if (k < kend) step(k);
 #pragma unroll
-  for (int s2 = 0; s2 < 4; ++s2) red[threadIdx.x][s2] = acc[s2];
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[threadIdx.x][i * 4 + j] = acc[i][j];
   __syncthreads();
-  if (threadIdx.x < wide) {
-    float* o = part + ((size_t)blockIdx.x * wide + threadIdx.x) * narrow;
-    for (int s2 = 0; s2 < narrow; ++s2) {
-      float t = 0.f;
-      for (int g = 0; g < groups; ++g) t += red[g * wide + threadIdx.x][s2];
-      o[s2] = t;
-    }
+  // thread t < wide * narrow: wide column t / narrow, narrow column t % narrow
+  for (int t = threadIdx.x; t < wide * narrow; t += 256) {
+    const int w = t / narrow, j = t - w * narrow;
+    float sum = 0.f;
+    for (int g = 0; g < groups; ++g) sum += red[g * tpr + (w >> 2)][(w & 3) * 4 + j];
+    const int m = wide_is_a ? w : j, n = wide_is_a ? j : w;
+    const int N = wide_is_a ? narrow : wide;
+    part[(size_t)blockIdx.x * wide * narrow + m * N + n] = sum;
   }
 }
 
-// C[m][n] = sum over blocks of part; `wide_is_a` : part is [wide = M][narrow = N], else [wide = N][narrow = M]
-__global__ void skinny_dw_reduce_kernel(const float* __restrict__ part, float* __restrict__ C, int M, int N, int nb,
-                                        int wide_is_a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M * N) return;
-  const int m = i / N, n = i - m * N;
-  const int src = wide_is_a ? m * N + n : n * M + m;
-  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-  int b = 0;
-  for (; b + 3 < nb; b += 4) {
-    t0 += part[(size_t)b * M * N + src];
-    t1 += part[(size_t)(b + 1) * M * N + src];
-    t2 += part[(size_t)(b + 2) * M * N + src];
-    t3 += part[(size_t)(b + 3) * M * N + src];
+// C = sum over blocks of part[b][M*N], fixed order: 32 consecutive outputs x 8 partial lanes per block
+__global__ void __launch_bounds__(256)
+    skinny_dw_reduce_kernel(const float* __restrict__ part, float* __restrict__ C, int MN, int nb) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + lane;
+  float s0 = 0.f, s1 = 0.f;
+  if (o < MN) {
+    int b = w;
+    for (; b + 8 < nb; b += 16) {
+      s0 += part[(size_t)b * MN + o];
+      s1 += part[(size_t)(b + 8) * MN + o];
+    }
+    if (b < nb) s0 += part[(size_t)b * MN + o];
   }
-  for (; b < nb; ++b) t0 += part[(size_t)b * M * N + src];
-  C[i] = (t0 + t1) + (t2 + t3);
+  red[w][lane] = s0 + s1;
+  __syncthreads();
+  if (w == 0 && o < MN) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += red[i][lane];
+    C[o] = t;
+  }
 }
 
 static inline bool skinny_n(int M, int N, int K, int transA, int transB) {
@@ -265,6 +327,7 @@ static inline bool skinny_wide_ok(int w) { return w == 64 || w == 128 || w == 25
 static inline bool skinny_dw(int M, int N, int K, int transA, int transB) {
   return transA && !transB && K >= 8192 && ((M <= 4 && skinny_wide_ok(N)) || (N <= 4 && skinny_wide_ok(M)));
 }
+// (the wide operand must be 16-byte aligned for the float4 loads: checked at launch)
 static inline int skinny_dw_blocks(int K) {
   int b = 2 * num_sms();
   const int maxb = cdiv(K, 64);
@@ -301,26 +364,25 @@ extern "C" int dgcnn_gemm(const float* A, const float* B, float* C, int M, int N
   DG_REQUIRE(M > 0 && N > 0 && K > 0, DGCNN_ERR_INVALID, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   DG_REQUIRE(((uintptr_t)C & 15) == 0, DGCNN_ERR_INVALID, "gemm: C must be 16-byte aligned");
   if (skinny_n(M, N, K, transA, transB)) {
-    const int blocks = cdiv(M, 8) < 8 * num_sms() ? cdiv(M, 8) : 8 * num_sms();
+    const int blocks = cdiv(M, 8) < 3 * num_sms() ? cdiv(M, 8) : 3 * num_sms();   // >= 14 rows per warp: B stays in registers
     sgemm_skinny_n_kernel<<<blocks, 256, 0, st>>>(A, B, C, M, N, K);
     count_launch();
     DG_CUDA_LAUNCH_CHECK("sgemm_skinny_n_kernel");
     return DGCNN_OK;
   }
-  if (skinny_dw(M, N, K, transA, transB)) {
+  if (skinny_dw(M, N, K, transA, transB) && (((uintptr_t)A | (uintptr_t)B) & 15) == 0) {
     const int nb = skinny_dw_blocks(K);
     const size_t need = (size_t)nb * M * N * sizeof(float);
     DG_REQUIRE(ws && ws_bytes >= need, DGCNN_ERR_WORKSPACE, "gemm: workspace %zu < %zu bytes", ws_bytes, need);
     const int kper = cdiv(K, nb);
     const bool wide_is_a = N <= 4 && skinny_wide_ok(M);
     if (wide_is_a)
-      sgemm_skinny_dw_kernel<<<nb, 256, 0, st>>>(A, B, reinterpret_cast<float*>(ws), M, N, K, kper);
+      sgemm_skinny_dw_kernel<<<nb, 256, 0, st>>>(A, B, reinterpret_cast<float*>(ws), M, N, K, kper, 1);
     else
-      sgemm_skinny_dw_kernel<<<nb, 256, 0, st>>>(B, A, reinterpret_cast<float*>(ws), N, M, K, kper);
+      sgemm_skinny_dw_kernel<<<nb, 256, 0, st>>>(B, A, reinterpret_cast<float*>(ws), N, M, K, kper, 0);
     count_launch();
     DG_CUDA_LAUNCH_CHECK("sgemm_skinny_dw_kernel");
-    skinny_dw_reduce_kernel<<<cdiv((int64_t)M * N, 128), 128, 0, st>>>(reinterpret_cast<float*>(ws), C, M, N, nb,
-                                                                        wide_is_a ? 1 : 0);
+    skinny_dw_reduce_kernel<<<cdiv((int64_t)M * N, 32), 256, 0, st>>>(reinterpret_cast<float*>(ws), C, M * N, nb);
     count_launch();
     DG_CUDA_LAUNCH_CHECK("skinny_dw_reduce_kernel");
     return DGCNN_OK;
