@@ -420,7 +420,11 @@ static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, in
     const char* e = getenv("DGCNN_TC_STAGES");
     forced = e ? atoi(e) : 0;
   }
-  const int stages = forced == 1 || forced == 3 ? forced : (kper >= 64 ? 3 : 1);
+  // deep ring when the k-loop is long, or when the grid leaves SMs idle anyway (split-K weight gradients: one CTA
+  // per SM at most, so the single-stage variant's 3-CTAs-per-SM overlap cannot happen and every k-block would
+  // expose a full TMA round trip)
+  const int64_t ctas = (int64_t)grid.x * grid.y * grid.z;
+  const int stages = forced == 1 || forced == 3 ? forced : ((kper >= 64 || (ctas <= num_sms() && kper >= 3)) ? 3 : 1);
 #define DG_TC_LAUNCH(AK_, BK_, ST_)                                                                          \
   do {                                                                                                       \
     static bool done_ = false;                                                                               \
