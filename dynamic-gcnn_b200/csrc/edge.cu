@@ -214,6 +214,11 @@ __global__ void __launch_bounds__(EC_THREADS)
     const float gm0 = gA0 * invk, gm1 = gA1 * invk;
     const float gx0 = ok0 ? gM0 / cnt[o + f0] : 0.f, gx1 = ok1 ? gM1 / cnt[o + f1] : 0.f;
     float gu0 = 0.f, gu1 = 0.f;
+    if (!APPLY && guv != nullptr) {   // statistics pass: clear this point's v half for the scatter-add of the apply pass
+      float* gvp = guv + (int64_t)p * 2 * a.F + a.F;
+      if (ok0) gvp[f0] = 0.f;
+      if (ok1) gvp[f1] = 0.f;
+    }
 #pragma unroll 4
     for (int j = 0; j < a.k; ++j) {
       const int64_t off = nbr_off(a, rows, j);
@@ -397,6 +402,15 @@ extern "C" int dgcnn_edgeconv_bwd_stats_packed(const float* uv, const int32_t* i
                                                const float* rstd, const float* beta, const float* g_max,
                                                const float* g_mean, const float* g_both, float* s1, float* s2,
                                                void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
+  return dgcnn_edgeconv_bwd_stats_packed_z(uv, idx, B, N, F, k, zmax, cnt, mean, rstd, beta, g_max, g_mean, g_both, s1, s2,
+                                           nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int dgcnn_edgeconv_bwd_stats_packed_z(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                                 const float* zmax, const float* cnt, const float* mean,
+                                                 const float* rstd, const float* beta, const float* g_max,
+                                                 const float* g_mean, const float* g_both, float* s1, float* s2,
+                                                 float* g_uv_clear, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
   int rc = ec_check(uv, idx, B, N, F, k);
   if (rc) return rc;
   DG_REQUIRE(zmax && cnt && mean && rstd && beta && s1 && s2 && ws, DGCNN_ERR_INVALID,
@@ -410,7 +424,7 @@ extern "C" int dgcnn_edgeconv_bwd_stats_packed(const float* uv, const int32_t* i
   rc = stats_acc_reset(ws, F, st);
   if (rc) return rc;
   ec_bwd_kernel<false><<<grid, EC_THREADS, 0, st>>>(a, zmax, cnt, mean, rstd, beta, g_max, g_mean, g_both, nullptr,
-                                                     nullptr, (double*)ws, nullptr);
+                                                     nullptr, (double*)ws, g_uv_clear);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("ec_bwd_kernel<stats>");
   return launch_finalize_sums((const double*)ws, F, s1, s2, st);
@@ -430,16 +444,28 @@ extern "C" int dgcnn_edgeconv_bwd_apply_packed(const float* uv, const int32_t* i
                                                const float* rstd, const float* beta, const float* g_max,
                                                const float* g_mean, const float* g_both, const float* s1,
                                                const float* s2, float* g_uv, dgcnn_stream_t stream) {
+  return dgcnn_edgeconv_bwd_apply_packed_z(uv, idx, B, N, F, k, zmax, cnt, mean, rstd, beta, g_max, g_mean, g_both, s1, s2,
+                                           g_uv, 0, stream);
+}
+
+extern "C" int dgcnn_edgeconv_bwd_apply_packed_z(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                                 const float* zmax, const float* cnt, const float* mean,
+                                                 const float* rstd, const float* beta, const float* g_max,
+                                                 const float* g_mean, const float* g_both, const float* s1,
+                                                 const float* s2, float* g_uv, int v_half_cleared,
+                                                 dgcnn_stream_t stream) {
   int rc = ec_check(uv, idx, B, N, F, k);
   if (rc) return rc;
   DG_REQUIRE(zmax && cnt && mean && rstd && beta && s1 && s2 && g_uv, DGCNN_ERR_INVALID,
              "edgeconv_bwd_apply: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   EcArgs a{uv, idx, B * N, N, F, k};
-  const int64_t PF = (int64_t)a.P * F;
-  zero_vhalf_kernel<<<cdiv(PF, 256), 256, 0, st>>>(g_uv, a.P, F);
-  count_launch();
-  DG_CUDA_LAUNCH_CHECK("zero_vhalf_kernel");
+  if (!v_half_cleared) {
+    const int64_t PF = (int64_t)a.P * F;
+    zero_vhalf_kernel<<<cdiv(PF, 256), 256, 0, st>>>(g_uv, a.P, F);
+    count_launch();
+    DG_CUDA_LAUNCH_CHECK("zero_vhalf_kernel");
+  }
   dim3 grid(stat_blocks(a.P), cdiv(F, 64));
   ec_bwd_kernel<true><<<grid, EC_THREADS, 0, st>>>(a, zmax, cnt, mean, rstd, beta, g_max, g_mean, g_both, s1, s2,
                                                     nullptr, g_uv);

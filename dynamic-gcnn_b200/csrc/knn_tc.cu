@@ -509,7 +509,14 @@ __global__ void __launch_bounds__(256)
       for (int c = 0; c < C; ++c) acc = __fmaf_rn(__ldg(xi + c), __ldg(xj + c), acc);
       d = __fadd_rn(__fsub_rn(__fadd_rn(si, sb[j]), __fmul_rn(2.0f, acc)), 0.0f);
     }
-    R.merge_batch(d, j >= 0 ? j : 0x7fffffff, k, lane);
+    int jj = j >= 0 ? j : 0x7fffffff;
+    if (base == 0) {      // the list is still empty: the sorted batch IS the list (saves the merge network)
+      warp_sort32(d, jj, lane);
+      R.d[0] = d;
+      R.j[0] = jj;
+    } else {
+      R.merge_batch(d, jj, k, lane);
+    }
   }
   if (staged) {
     cp_async_commit();

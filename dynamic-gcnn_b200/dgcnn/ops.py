@@ -407,9 +407,10 @@ class _EdgeConvGather(torch.autograd.Function):
         common = (uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(), cnt.data_ptr(), mean.data_ptr(),
                   rstd.data_ptr(), beta.data_ptr(), nv.ptr(gmax), nv.ptr(gmean), nv.ptr(gboth), s1.data_ptr(),
                   s2.data_ptr())
-        nv.check(L.dgcnn_edgeconv_bwd_stats_packed(*common, ws.data_ptr(), ws.numel(), st), "edgeconv_bwd_stats")
         guv = torch.empty_like(uv)
-        nv.check(L.dgcnn_edgeconv_bwd_apply_packed(*common, guv.data_ptr(), st), "edgeconv_bwd_apply")
+        nv.check(L.dgcnn_edgeconv_bwd_stats_packed_z(*common, guv.data_ptr(), ws.data_ptr(), ws.numel(), st),
+                 "edgeconv_bwd_stats")
+        nv.check(L.dgcnn_edgeconv_bwd_apply_packed_z(*common, guv.data_ptr(), 1, st), "edgeconv_bwd_apply")
         return guv, None, s1, None, None, None
 
 

@@ -147,6 +147,19 @@ int dgcnn_edgeconv_bwd_apply_packed(const float* uv, const int32_t* idx, int B, 
                                     const float* beta, const float* g_max, const float* g_mean, const float* g_both,
                                     const float* s1, const float* s2, float* g_uv, dgcnn_stream_t stream);
 
+/* ..._z: the statistics pass also clears the v half of g_uv (g_uv_clear, may be NULL) so that the apply pass, told so by
+ * v_half_cleared != 0, can scatter-add into it without a separate zeroing kernel.                               */
+int dgcnn_edgeconv_bwd_stats_packed_z(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                      const float* zmax, const float* cnt, const float* mean, const float* rstd,
+                                      const float* beta, const float* g_max, const float* g_mean, const float* g_both,
+                                      float* s1, float* s2, float* g_uv_clear, void* ws, size_t ws_bytes,
+                                      dgcnn_stream_t stream);
+int dgcnn_edgeconv_bwd_apply_packed_z(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                      const float* zmax, const float* cnt, const float* mean, const float* rstd,
+                                      const float* beta, const float* g_max, const float* g_mean, const float* g_both,
+                                      const float* s1, const float* s2, float* g_uv, int v_half_cleared,
+                                      dgcnn_stream_t stream);
+
 /* ---- train-mode BatchNorm (+residual) (+ReLU) on a [rows,C] per-point tensor ---------------
  * slim.batch_norm defaults (is_training=True, center=True, scale=False, eps=1e-3) after a 1x1 conv:
  * ops.py:53,68 ; residual add + relu: ops.py:134.
