@@ -139,6 +139,24 @@ def workload_config(n):
             "launch": "micro-step (fwd+bwd) replayed from a CUDA graph captured by dgcnn.trainval after 2 eager runs"}
 
 
+def edgeconv_entry(eev):
+    """EdgeConv forward after the uv GEMM (ops.py:45-58: gather, conv0 as u_i + v_j, BN, ReLU, max_k / mean_k, concat) =
+    ec_fwd_stats_kernel + finalize + ec_fwd_apply_kernel, on the 64-channel layers."""
+    ts = [a.elapsed_time(b) for (_, _, f, _, a, b) in eev]
+    if not ts:
+        return None
+    t = float(np.mean(ts)) * 1e-3
+    P_, E_ = B_PER_GPU * NPTS, B_PER_GPU * NPTS * KNN
+    hbm = (P_ * 128 + E_ + 3 * P_ * 64 + P_ * 128) * 4.0        # uv, idx, zmax/cnt, (max | mean): compulsory bytes
+    l2 = 2.0 * E_ * 64 * 4                                       # two gather passes over the L2-resident v rows
+    ref = (E_ * 128 * 4.0) * 2 + (E_ * 64 * 4.0) * 5             # the reference's edge tensor w+r, conv0 out w + BN r/w + max/mean r
+    return {"ms_per_call": t * 1e3, "calls_timed": len(ts), "bound": "L2 gather (E*F*4 bytes per pass) + fp32 ALU",
+            "compulsory_hbm_gbs": hbm / t / 1e9, "l2_gather_gbs": l2 / t / 1e9,
+            "effective_unfused_hbm_gbs": ref / t / 1e9,
+            "note": "effective = bytes the reference's op-by-op graph moves for the same layer (edge tensor, conv0 output, "
+                    "BN, max/mean passes) divided by this time; none of those tensors exists here"}
+
+
 def run_ours(args):
     import torch.distributed as dist
     import dgcnn
@@ -219,13 +237,14 @@ def run_ours(args):
     # per-kernel timing for the roofline entry: the same steps issued eagerly (a captured graph cannot carry timing
     # events), the kernels of interest bracketed by CUDA events on the launching stream
     os.environ["DGCNN_CUDA_GRAPH"] = "0"
-    ops._knn_events, ops._gemm_events = [], []
+    ops._knn_events, ops._gemm_events, ops._ec_events = [], [], []
     barrier()
     for i in range(3):
         step(i, False)
     barrier()
     ev, ops._knn_events = ops._knn_events, None
     gev, ops._gemm_events = ops._gemm_events, None
+    eev, ops._ec_events = ops._ec_events, None
     os.environ.pop("DGCNN_CUDA_GRAPH", None)
 
     pts_per_step = B_PER_GPU * NPTS * world
@@ -271,6 +290,7 @@ def run_ours(args):
                         "algorithmic_tflops": (2.0 * B_PER_GPU * NPTS * NPTS * 64 / (float(np.mean(knn64)) * 1e-3) / 1e12)
                         if knn64 else None},
                     "k_nn_fused_xyz": {"ms_per_call": float(np.mean(knn3)) if knn3 else None},
+                    "edgeconv_fwd_gather": edgeconv_entry(eev),
                     "knn_share_of_step": (sum(knn64) + sum(knn3)) / 3.0 / (ms_dev / args.steps)}}
 
     if rank == 0:

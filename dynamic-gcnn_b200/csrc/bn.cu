@@ -10,6 +10,15 @@
 namespace dgcnn {
 
 constexpr int BN_THREADS = 256;
+
+// up to two "plane sinks" of an apply pass: the output is also written as bf16 hi / lo planes into column slices of
+// tensor-core operands (row pitch ld, second plane `plane` elements later), so that no split pass reads it again
+struct BnSinks {
+  int n;
+  __nv_bfloat16* p[2];
+  int ld[2];
+  size_t plane[2];
+};
 constexpr int BN_BLOCKS_PER_SM = 8;
 
 static inline int bn_max_blocks() { return num_sms() * BN_BLOCKS_PER_SM; }
@@ -169,7 +178,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
     bn_act_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ rstd,
                       const float* __restrict__ beta, const float* __restrict__ res, int relu, uint32_t nvec, int C,
-                      float* __restrict__ out, const float* __restrict__ gbias, int grows) {
+                      float* __restrict__ out, const float* __restrict__ gbias, int grows, const BnSinks sinks) {
   const uint32_t cv = (uint32_t)C / VEC;
   for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
     const uint32_t r = v / cv;
@@ -203,10 +212,27 @@ __global__ void __launch_bounds__(256)
       if (res) t += rr[i];
       y[i] = relu ? fmaxf(t, 0.f) : t;
     }
-    if (VEC == 4)
+    if (VEC == 4) {
       *reinterpret_cast<float4*>(out + e) = *reinterpret_cast<float4*>(y);
-    else
+      if (sinks.n > 0) {
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          h[i] = __float2bfloat16_rn(y[i]);
+          l[i] = __float2bfloat16_rn(y[i] - __bfloat162float(h[i]));
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (q < sinks.n) {
+            const size_t se = (size_t)r * sinks.ld[q] + c;
+            *reinterpret_cast<uint2*>(sinks.p[q] + se) = *reinterpret_cast<uint2*>(h);
+            *reinterpret_cast<uint2*>(sinks.p[q] + sinks.plane[q] + se) = *reinterpret_cast<uint2*>(l);
+          }
+        }
+      }
+    } else {
       out[e] = y[0];
+    }
   }
 }
 
@@ -466,9 +492,49 @@ extern "C" int dgcnn_bn_act_fwd(const float* z, int64_t rows, int C, const float
   return dgcnn_bn_act_fwd_gb(z, rows, C, beta, residual, nullptr, 0, relu, out, mean, rstd, ws, ws_bytes, stream);
 }
 
+static int bn_make_sinks(BnSinks* sk, int n_sinks, void* const* sink_planes, const int* sink_lds,
+                         const int64_t* sink_plane_elems, int C) {
+  sk->n = 0;
+  DG_REQUIRE(n_sinks >= 0 && n_sinks <= 2, DGCNN_ERR_INVALID, "bn sinks: at most two");
+  for (int i = 0; i < n_sinks; ++i) {
+    DG_REQUIRE(sink_planes && sink_lds && sink_plane_elems && sink_planes[i] && sink_lds[i] >= C &&
+                   (sink_lds[i] & 3) == 0 && (sink_plane_elems[i] & 3) == 0 && ((uintptr_t)sink_planes[i] & 7) == 0,
+               DGCNN_ERR_INVALID, "bn sinks: bad geometry of sink %d", i);
+    sk->p[i] = (__nv_bfloat16*)sink_planes[i];
+    sk->ld[i] = sink_lds[i];
+    sk->plane[i] = (size_t)sink_plane_elems[i];
+  }
+  sk->n = n_sinks;
+  return DGCNN_OK;
+}
+
+static int bn_act_fwd_impl(const float* z, int64_t rows, int C, const float* beta, const float* residual,
+                           const float* group_bias, int group_rows, int relu, float* out, float* mean, float* rstd,
+                           void* ws, size_t ws_bytes, const BnSinks& sinks, dgcnn_stream_t stream);
+
 extern "C" int dgcnn_bn_act_fwd_gb(const float* z, int64_t rows, int C, const float* beta, const float* residual,
                                    const float* group_bias, int group_rows, int relu, float* out, float* mean,
                                    float* rstd, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
+  BnSinks sk;
+  sk.n = 0;
+  return bn_act_fwd_impl(z, rows, C, beta, residual, group_bias, group_rows, relu, out, mean, rstd, ws, ws_bytes, sk,
+                         stream);
+}
+
+extern "C" int dgcnn_bn_act_fwd_sinks(const float* z, int64_t rows, int C, const float* beta, const float* residual,
+                                      const float* group_bias, int group_rows, int relu, float* out, float* mean,
+                                      float* rstd, void* ws, size_t ws_bytes, int n_sinks, void* const* sink_planes,
+                                      const int* sink_lds, const int64_t* sink_plane_elems, dgcnn_stream_t stream) {
+  BnSinks sk;
+  int rc = bn_make_sinks(&sk, n_sinks, sink_planes, sink_lds, sink_plane_elems, C);
+  if (rc) return rc;
+  return bn_act_fwd_impl(z, rows, C, beta, residual, group_bias, group_rows, relu, out, mean, rstd, ws, ws_bytes, sk,
+                         stream);
+}
+
+static int bn_act_fwd_impl(const float* z, int64_t rows, int C, const float* beta, const float* residual,
+                           const float* group_bias, int group_rows, int relu, float* out, float* mean, float* rstd,
+                           void* ws, size_t ws_bytes, const BnSinks& sinks, dgcnn_stream_t stream) {
   DG_REQUIRE(!group_bias || (group_rows > 0 && rows % group_rows == 0), DGCNN_ERR_INVALID,
              "bn_act_fwd: rows=%lld is not a multiple of group_rows=%d", (long long)rows, group_rows);
   DG_REQUIRE(z && beta && out && mean && rstd && ws, DGCNN_ERR_INVALID, "bn_act_fwd: null pointer");
@@ -487,12 +553,13 @@ extern "C" int dgcnn_bn_act_fwd_gb(const float* z, int64_t rows, int C, const fl
   DG_REQUIRE(total < (1ll << 32), DGCNN_ERR_UNSUPPORTED, "bn_act_fwd: more than 2^32 elements");
   const bool vec = (C & 3) == 0 && (((uintptr_t)z | (uintptr_t)out | (uintptr_t)residual | (uintptr_t)group_bias |
                                      (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta) & 15) == 0;
+  DG_REQUIRE(vec || sinks.n == 0, DGCNN_ERR_INVALID, "bn_act_fwd: plane sinks need C %% 4 == 0 and 16-byte aligned buffers");
   if (vec)
     bn_act_fwd_kernel<4><<<ew_blocks(total / 4), 256, 0, st>>>(z, mean, rstd, beta, residual, relu, (uint32_t)(total / 4), C,
-                                                               out, group_bias, group_rows);
+                                                               out, group_bias, group_rows, sinks);
   else
     bn_act_fwd_kernel<1><<<ew_blocks(total), 256, 0, st>>>(z, mean, rstd, beta, residual, relu, (uint32_t)total, C, out,
-                                                           group_bias, group_rows);
+                                                           group_bias, group_rows, sinks);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_act_fwd_kernel");
   return DGCNN_OK;
@@ -516,6 +583,19 @@ extern "C" int dgcnn_bn_stats_from_tiles(const float* colstats, int tiles, int C
 extern "C" int dgcnn_bn_apply_fwd(const float* z, int64_t rows, int C, const float* beta, const float* residual,
                                   const float* group_bias, int group_rows, int relu, const float* mean,
                                   const float* rstd, float* out, dgcnn_stream_t stream) {
+  return dgcnn_bn_apply_fwd_sinks(z, rows, C, beta, residual, group_bias, group_rows, relu, mean, rstd, out, 0, nullptr,
+                                  nullptr, nullptr, stream);
+}
+
+extern "C" int dgcnn_bn_apply_fwd_sinks(const float* z, int64_t rows, int C, const float* beta, const float* residual,
+                                        const float* group_bias, int group_rows, int relu, const float* mean,
+                                        const float* rstd, float* out, int n_sinks, void* const* sink_planes,
+                                        const int* sink_lds, const int64_t* sink_plane_elems, dgcnn_stream_t stream) {
+  BnSinks sinks;
+  {
+    int rcs = bn_make_sinks(&sinks, n_sinks, sink_planes, sink_lds, sink_plane_elems, C);
+    if (rcs) return rcs;
+  }
   DG_REQUIRE(z && beta && out && mean && rstd, DGCNN_ERR_INVALID, "bn_apply_fwd: null pointer");
   DG_REQUIRE(rows > 0 && C > 0, DGCNN_ERR_INVALID, "bn_apply_fwd: bad shape rows=%lld C=%d", (long long)rows, C);
   DG_REQUIRE(!group_bias || (group_rows > 0 && rows % group_rows == 0), DGCNN_ERR_INVALID,
@@ -525,12 +605,13 @@ extern "C" int dgcnn_bn_apply_fwd(const float* z, int64_t rows, int C, const flo
   DG_REQUIRE(total < (1ll << 32), DGCNN_ERR_UNSUPPORTED, "bn_apply_fwd: more than 2^32 elements");
   const bool vec = (C & 3) == 0 && (((uintptr_t)z | (uintptr_t)out | (uintptr_t)residual | (uintptr_t)group_bias |
                                      (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta) & 15) == 0;
+  DG_REQUIRE(vec || sinks.n == 0, DGCNN_ERR_INVALID, "bn_apply_fwd: plane sinks need C %% 4 == 0 and 16-byte aligned buffers");
   if (vec)
     bn_act_fwd_kernel<4><<<ew_blocks(total / 4), 256, 0, st>>>(z, mean, rstd, beta, residual, relu, (uint32_t)(total / 4), C,
-                                                               out, group_bias, group_rows);
+                                                               out, group_bias, group_rows, sinks);
   else
     bn_act_fwd_kernel<1><<<ew_blocks(total), 256, 0, st>>>(z, mean, rstd, beta, residual, relu, (uint32_t)total, C, out,
-                                                           group_bias, group_rows);
+                                                           group_bias, group_rows, sinks);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_act_fwd_kernel");
   return DGCNN_OK;

@@ -6,6 +6,8 @@
 // Work split of the gather passes: one warp per point, lanes over channels (lane, lane+32 of a 64-channel
 // chunk; chunk = blockIdx.y), neighbours unrolled for memory-level parallelism.  v rows are 256 B and the
 // whole uv table (25 MB at B=24,N=2048,F=64) is L2-resident, so these passes run at L2 gather rate.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace dgcnn {
@@ -135,7 +137,8 @@ __global__ void finalize_sums_kernel(const double* __restrict__ acc, int C, floa
 __global__ void __launch_bounds__(EC_THREADS)
     ec_fwd_apply_kernel(EcArgs a, const float* __restrict__ zmax, const float* __restrict__ mean,
                         const float* __restrict__ rstd, const float* __restrict__ beta, float* __restrict__ omax,
-                        float* __restrict__ omean, int opitch) {
+                        float* __restrict__ omean, int opitch, __nv_bfloat16* __restrict__ sink, int sink_ld,
+                        size_t sink_plane) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int f0 = blockIdx.y * 64 + lane, f1 = f0 + 32;
   const bool ok0 = f0 < a.F, ok1 = f1 < a.F;
@@ -158,13 +161,27 @@ __global__ void __launch_bounds__(EC_THREADS)
       y1 += fmaxf(fmaf(z1 - mu1, r1, b1), 0.f);
     }
     const int64_t o = (int64_t)p * a.F, oo = (int64_t)p * opitch;
+    // optional plane sink: the same values as bf16 hi / lo planes at columns [0,F) (max) and [F,2F) (mean) of a
+    // tensor-core operand (the consumer's concat operand), so that no separate split pass reads them again
+    auto put = [&](int col, float v) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const size_t e = (size_t)p * sink_ld + col;
+      sink[e] = h;
+      sink[sink_plane + e] = __float2bfloat16_rn(v - __bfloat162float(h));
+    };
     if (ok0) {
-      omean[oo + f0] = y0 * invk;
-      omax[oo + f0] = fmaxf(fmaf(zmax[o + f0] - mu0, r0, b0), 0.f);  // BN(+)ReLU are monotone: max commutes
+      const float vm = y0 * invk;
+      const float vx = fmaxf(fmaf(zmax[o + f0] - mu0, r0, b0), 0.f);  // BN(+)ReLU are monotone: max commutes
+      omean[oo + f0] = vm;
+      omax[oo + f0] = vx;
+      if (sink) { put(f0, vx); put(a.F + f0, vm); }
     }
     if (ok1) {
-      omean[oo + f1] = y1 * invk;
-      omax[oo + f1] = fmaxf(fmaf(zmax[o + f1] - mu1, r1, b1), 0.f);
+      const float vm = y1 * invk;
+      const float vx = fmaxf(fmaf(zmax[o + f1] - mu1, r1, b1), 0.f);
+      omean[oo + f1] = vm;
+      omax[oo + f1] = vx;
+      if (sink) { put(f1, vx); put(a.F + f1, vm); }
     }
   }
 }
@@ -361,7 +378,7 @@ extern "C" int dgcnn_edgeconv_fwd_stats(const float* uv, const int32_t* idx, int
 
 static int ec_fwd_apply_impl(const float* uv, const int32_t* idx, int B, int N, int F, int k, const float* zmax,
                              const float* mean, const float* rstd, const float* beta, float* out_max, float* out_mean,
-                             int pitch, dgcnn_stream_t stream) {
+                             int pitch, void* sink, int sink_ld, int64_t sink_plane, dgcnn_stream_t stream) {
   int rc = ec_check(uv, idx, B, N, F, k);
   if (rc) return rc;
   DG_REQUIRE(zmax && mean && rstd && beta && out_max && out_mean, DGCNN_ERR_INVALID,
@@ -369,7 +386,8 @@ static int ec_fwd_apply_impl(const float* uv, const int32_t* idx, int B, int N, 
   EcArgs a{uv, idx, B * N, N, F, k};
   dim3 grid(stat_blocks(a.P), cdiv(F, 64));
   ec_fwd_apply_kernel<<<grid, EC_THREADS, 0, (cudaStream_t)stream>>>(a, zmax, mean, rstd, beta, out_max, out_mean,
-                                                                     pitch);
+                                                                     pitch, (__nv_bfloat16*)sink, sink_ld,
+                                                                     (size_t)sink_plane);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("ec_fwd_apply_kernel");
   return DGCNN_OK;
@@ -378,14 +396,26 @@ static int ec_fwd_apply_impl(const float* uv, const int32_t* idx, int B, int N, 
 extern "C" int dgcnn_edgeconv_fwd_apply(const float* uv, const int32_t* idx, int B, int N, int F, int k,
                                         const float* zmax, const float* mean, const float* rstd, const float* beta,
                                         float* out_max, float* out_mean, dgcnn_stream_t stream) {
-  return ec_fwd_apply_impl(uv, idx, B, N, F, k, zmax, mean, rstd, beta, out_max, out_mean, F, stream);
+  return ec_fwd_apply_impl(uv, idx, B, N, F, k, zmax, mean, rstd, beta, out_max, out_mean, F, nullptr, 0, 0, stream);
 }
 
 extern "C" int dgcnn_edgeconv_fwd_apply_packed(const float* uv, const int32_t* idx, int B, int N, int F, int k,
                                                const float* zmax, const float* mean, const float* rstd,
                                                const float* beta, float* out_both, dgcnn_stream_t stream) {
   DG_REQUIRE(out_both, DGCNN_ERR_INVALID, "edgeconv_fwd_apply_packed: null pointer");
-  return ec_fwd_apply_impl(uv, idx, B, N, F, k, zmax, mean, rstd, beta, out_both, out_both + F, 2 * F, stream);
+  return ec_fwd_apply_impl(uv, idx, B, N, F, k, zmax, mean, rstd, beta, out_both, out_both + F, 2 * F, nullptr, 0, 0,
+                           stream);
+}
+
+extern "C" int dgcnn_edgeconv_fwd_apply_packed_sink(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                                    const float* zmax, const float* mean, const float* rstd,
+                                                    const float* beta, float* out_both, void* sink_planes, int sink_ld,
+                                                    int64_t sink_plane_elems, dgcnn_stream_t stream) {
+  DG_REQUIRE(out_both, DGCNN_ERR_INVALID, "edgeconv_fwd_apply_packed_sink: null pointer");
+  DG_REQUIRE(!sink_planes || (sink_ld >= 2 * F && sink_plane_elems > 0), DGCNN_ERR_INVALID,
+             "edgeconv_fwd_apply_packed_sink: bad sink geometry");
+  return ec_fwd_apply_impl(uv, idx, B, N, F, k, zmax, mean, rstd, beta, out_both, out_both + F, 2 * F, sink_planes, sink_ld,
+                           sink_plane_elems, stream);
 }
 
 extern "C" int dgcnn_edgeconv_bwd_stats(const float* uv, const int32_t* idx, int B, int N, int F, int k,

@@ -49,6 +49,9 @@ SIGNATURES = {
     "dgcnn_edgeconv_bwd_apply_packed": (_i, [_vp, _vp, _i, _i, _i, _i] + [_vp] * 11 + [_vp]),
     "dgcnn_edgeconv_bwd_stats_packed_z": (_i, [_vp, _vp, _i, _i, _i, _i] + [_vp] * 10 + [_vp, _vp, _sz, _vp]),
     "dgcnn_edgeconv_bwd_apply_packed_z": (_i, [_vp, _vp, _i, _i, _i, _i] + [_vp] * 11 + [_i, _vp]),
+    "dgcnn_edgeconv_fwd_apply_packed_sink": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
+    "dgcnn_bn_act_fwd_sinks": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp, _vp, _vp, _vp]),
+    "dgcnn_bn_apply_fwd_sinks": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "dgcnn_bn_workspace_bytes": (_sz, [_i]),
     "dgcnn_bn_act_fwd": (_i, [_vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dgcnn_bn_act_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

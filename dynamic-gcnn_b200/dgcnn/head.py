@@ -30,9 +30,9 @@ def conv_bn_act(srcs: List[torch.Tensor], scope: str, cout: int, trainable: bool
     P = srcs[0].shape[0]
     if _ops._tc_ok(P, cout, *[t.shape[1] for t in srcs]):
         # the whole layer around one tcgen05 GEMM: BN statistics from its epilogue, gradients as bf16 planes
-        return _ops._ConvBnActTC.apply(w[cg:] if cg else w, b, gb, activation is not None, points_per_cloud, *srcs)
+        return _ops._ConvBnActTC.apply(w[cg:] if cg else w, b, gb, activation is not None, points_per_cloud, scope, *srcs)
     z = _ops.conv1x1(srcs, w[cg:] if cg else w)
-    return _ops._BnAct.apply(z, b, None, activation is not None, gb)
+    return _ops._BnAct.apply(z, b, None, activation is not None, gb, None)
 
 
 def conv_bn_relu_dense(net: torch.Tensor, scope: str, cout: int, trainable: bool, activation=_ops.relu) -> torch.Tensor:

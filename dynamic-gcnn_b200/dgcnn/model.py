@@ -35,15 +35,59 @@ def build(point_cloud, flags, dropout_mask=None):
         print("\n")
         print("Shape %s ... Name %s" % (tuple(net.shape), "points"))
 
+    if flags.MODEL_NAME not in ("dgcnn", "residual-dgcnn", "residual-dgcnn-nofc"):
+        print("Unsupported MODEL_NAME: %s" % flags.MODEL_NAME)
+        raise NotImplementedError
+    old_sinks = ops._sinks
+    ops._sinks = _make_sinks(flags, batch_size * num_point, net.device)
+    try:
+        return _build_body(net, flags, dropout_mask, num_edge_conv, num_edge_filters, num_fc, num_fc_filters, is_training,
+                           k, debug, num_class, batch_size, num_point)
+    finally:
+        ops._sinks = old_sinks
+
+
+def _make_sinks(flags, P, device):
+    """Pre-allocate the bf16 operand planes of MergedEdgeConv / FC0 / FC1 (model.py:60-63,83-88: the channel concats)
+    and tell every producer where its output goes in them, so that producers fill the operands directly."""
+    import os
+    if flags.MODEL_NAME == "residual-dgcnn-nofc" or os.environ.get("DGCNN_PLANE_SINKS", "1") == "0":
+        return None
+    L = int(flags.EDGE_CONV_LAYERS)
+    filt = [int(f) for f in ops._listify(flags.EDGE_CONV_FILTERS, L, "num_filters")]
+    nfc = int(flags.FC_LAYERS)
+    fcf = [int(f) for f in ops._listify(flags.FC_FILTERS, nfc, "num_filters")] if nfc else []
+    widths = []
+    for f in filt:
+        widths += [f, f, ops.CONV1_WIDTH]
+    if nfc == 0 or not ops._tc_ok(P, 1024, fcf[0], *widths):
+        return None
+    sk = ops.PlaneSinks()
+    k_merged = ops.CONV1_WIDTH * L
+    k_fc0 = sum(widths) + 1024
+    bf = dict(dtype=torch.bfloat16, device=device)
+    sk.planes["MergedEdgeConv"] = torch.empty((2, P, k_merged), **bf)
+    sk.planes["FC0"] = torch.empty((2, P, k_fc0), **bf)
+    col = 0
+    for i, f in enumerate(filt):
+        sk.targets[("ec", i, "both")] = [(sk.planes["FC0"], col)]
+        sk.targets[("ec", i, "net")] = [(sk.planes["FC0"], col + 2 * f), (sk.planes["MergedEdgeConv"], ops.CONV1_WIDTH * i)]
+        col += 2 * f + ops.CONV1_WIDTH
+    sk.targets[("layer", "MergedEdgeConv")] = [(sk.planes["FC0"], col)]
+    if nfc > 1 and ops._tc_ok(P, fcf[0], fcf[1]):
+        sk.planes["FC1"] = torch.empty((2, P, fcf[0]), **bf)
+        sk.targets[("layer", "FC0")] = [(sk.planes["FC1"], 0)]
+    return sk
+
+
+def _build_body(net, flags, dropout_mask, num_edge_conv, num_edge_filters, num_fc, num_fc_filters, is_training, k, debug,
+                num_class, batch_size, num_point):
     if flags.MODEL_NAME == "dgcnn":
         tensors = ops.repeat_edge_conv(net, repeat=num_edge_conv, k=k, num_filters=num_edge_filters,
                                        trainable=is_training, debug=debug)
-    elif flags.MODEL_NAME in ["residual-dgcnn", "residual-dgcnn-nofc"]:
+    else:
         tensors = ops.repeat_residual_edge_conv(net, repeat=num_edge_conv, k=k, num_filters=num_edge_filters,
                                                 trainable=is_training, debug=debug)
-    else:
-        print("Unsupported MODEL_NAME: %s" % flags.MODEL_NAME)
-        raise NotImplementedError
 
     if flags.MODEL_NAME == "residual-dgcnn-nofc":                      # model.py:45-58
         net = conv_bn_relu_dense(tensors[-1], "Final", num_class, True)

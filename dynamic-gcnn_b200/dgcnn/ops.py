@@ -21,6 +21,38 @@ import torch
 from . import _native as nv
 from .variables import default_store, variable_scope
 
+class PlaneSinks:
+    """Producer-side filling of the head's tensor-core operands (model.py:60-63,83-85: the concats).
+
+    dgcnn.model.build pre-allocates the bf16 hi/lo operand planes of MergedEdgeConv, FC0 and FC1 and publishes, per
+    producer, WHERE its output lives inside them.  The producing kernels (EdgeConv gather apply, BN apply) then write
+    their result there as well, and the consuming layer skips the split pass for every source that `done` lists.
+    `done` maps (data_ptr, columns, row stride) of a source tensor to (data_ptr of the operand planes, column)."""
+
+    def __init__(self):
+        self.targets = {}   # producer key -> list of (planes [2,P,K] bf16, column)
+        self.planes = {}    # consumer scope -> planes
+        self.done = {}
+        self.layer = 0
+
+    def sink_args(self, key):
+        """-> (n, ptr array, ld array, plane array) for the C ABI, plus the raw list"""
+        import ctypes
+        lst = self.targets.get(key, [])
+        n = len(lst)
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[pl.data_ptr() + 2 * col for pl, col in lst])
+        lds = (ctypes.c_int * max(n, 1))(*[pl.shape[2] for pl, _ in lst])
+        pes = (ctypes.c_int64 * max(n, 1))(*[pl.shape[1] * pl.shape[2] for pl, _ in lst])
+        return n, ptrs, lds, pes, lst
+
+    def mark(self, t2d_ptr, cols, ld, lst):
+        for pl, col in lst:
+            self.done[(t2d_ptr, cols, ld, pl.data_ptr())] = col
+
+
+_sinks = None   # set by dgcnn.model.build for the duration of one forward pass
+
+
 relu = "relu"  # stand-in for tf.nn.relu as the `activation` argument (None = linear, ops.py:121)
 
 BN_EPS = 1e-3
@@ -34,6 +66,7 @@ _knn_forced = None
 # launching stream (eager mode only: a captured graph cannot carry timing events)
 _knn_events = None
 _gemm_events = None
+_ec_events = None
 
 
 def _layer_knn(x, k, hint=None):
@@ -241,14 +274,21 @@ def _tc_dx_sources(pg, pw, P, K, Cout, widths, needs):
     return outs
 
 
-def _split_sources(srcs, w):
+def _split_sources(srcs, w, planes=None):
+    """sources -> column slices of one bf16 hi/lo operand.  `planes` (optional): a pre-allocated operand that some
+    producers may already have filled (PlaneSinks.done); those sources are skipped."""
     P = srcs[0].shape[0]
     widths = [int(t.shape[1]) for t in srcs]
     K = sum(widths)
-    planes = torch.empty((2, P, K), dtype=torch.bfloat16, device=w.device)
+    if planes is None or tuple(planes.shape) != (2, P, K) or _sinks is None:
+        planes = torch.empty((2, P, K), dtype=torch.bfloat16, device=w.device)
+        done = {}
+    else:
+        done = _sinks.done
     off = 0
     for t, c in zip(srcs, widths):
-        _split_into(t, planes, off)
+        if done.get((t.data_ptr(), c, t.stride(0), planes.data_ptr())) != off:
+            _split_into(t, planes, off)
         off += c
     return planes, widths, P, K
 
@@ -287,12 +327,14 @@ class _ConvBnActTC(torch.autograd.Function):
       backward: BN backward writes g_z directly as bf16 planes (the operand format of the dW / dX GEMMs)."""
 
     @staticmethod
-    def forward(ctx, w, beta, gb, relu_flag, grows, *srcs):
+    def forward(ctx, w, beta, gb, relu_flag, grows, scope, *srcs):
         w = nv.require_cuda(w, "conv weights")
         beta = nv.require_cuda(beta, "beta")
         gb = nv.require_cuda(gb, "group_bias") if gb is not None else None
         srcs = [nv.require_cuda_rows(t, "conv input") for t in srcs]
-        planes, widths, P, K = _split_sources(srcs, w)
+        sk = _sinks
+        planes, widths, P, K = _split_sources(srcs, w, sk.planes.get(scope) if sk is not None else None)
+        n_s, s_ptr, s_ld, s_pe, s_lst = sk.sink_args(("layer", scope)) if sk is not None else (0, None, None, None, [])
         Cout = w.shape[1]
         pw = _split(w)
         dev = w.device
@@ -317,15 +359,17 @@ class _ConvBnActTC(torch.autograd.Function):
                 _gemm_events.append((P, Cout, K, ev[0], ev[1]))
             nv.check(L.dgcnn_bn_stats_from_tiles(cs.data_ptr(), tiles, Cout, P, nv.ptr(gb), grows, mean.data_ptr(),
                                                  rstd.data_ptr(), st), "bn_stats_from_tiles")
-            nv.check(L.dgcnn_bn_apply_fwd(z.data_ptr(), P, Cout, beta.data_ptr(), 0, nv.ptr(gb), grows,
-                                          int(bool(relu_flag)), mean.data_ptr(), rstd.data_ptr(), out.data_ptr(), st),
-                     "bn_apply_fwd")
+            nv.check(L.dgcnn_bn_apply_fwd_sinks(z.data_ptr(), P, Cout, beta.data_ptr(), 0, nv.ptr(gb), grows,
+                                                int(bool(relu_flag)), mean.data_ptr(), rstd.data_ptr(), out.data_ptr(),
+                                                n_s, s_ptr, s_ld, s_pe, st), "bn_apply_fwd")
         else:
             z = _tc_gemm_raw(planes, pw, P, Cout, K, 0, 0)
             ws = nv.workspace(dev, L.dgcnn_bn_workspace_bytes(Cout), "stats")
-            nv.check(L.dgcnn_bn_act_fwd_gb(z.data_ptr(), P, Cout, beta.data_ptr(), 0, nv.ptr(gb), grows,
-                                           int(bool(relu_flag)), out.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                           ws.data_ptr(), ws.numel(), st), "bn_act_fwd")
+            nv.check(L.dgcnn_bn_act_fwd_sinks(z.data_ptr(), P, Cout, beta.data_ptr(), 0, nv.ptr(gb), grows,
+                                              int(bool(relu_flag)), out.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), n_s, s_ptr, s_ld, s_pe, st), "bn_act_fwd")
+        if n_s:
+            sk.mark(out.data_ptr(), Cout, Cout, s_lst)
         ctx.save_for_backward(planes, pw, z, beta, mean, rstd, gb)   # the ReLU mask is re-evaluated from z in backward
         ctx.widths, ctx.relu, ctx.grows = widths, bool(relu_flag), grows
         return out
@@ -348,7 +392,8 @@ class _ConvBnActTC(torch.autograd.Function):
                                            nv.stream_ptr(dev)), "bn_act_bwd_planes")
         gw = _tc_gemm_raw(planes, pg, K, Cout, P, 1, 0) if ctx.needs_input_grad[0] else None   # X^T . g_z
         ggb = gz.view(gb.shape[0], ctx.grows, Cout).sum(dim=1) if gb is not None else None
-        return tuple([gw, gbeta, ggb, None, None] + _tc_dx_sources(pg, pw, P, K, Cout, ctx.widths, ctx.needs_input_grad[5:]))
+        return tuple([gw, gbeta, ggb, None, None, None] +
+                     _tc_dx_sources(pg, pw, P, K, Cout, ctx.widths, ctx.needs_input_grad[6:]))
 
 
 def conv1x1(srcs, w) -> torch.Tensor:
@@ -366,7 +411,7 @@ class _EdgeConvGather(torch.autograd.Function):
     ops.py:58's concat(max, mean).  Backward sums the gradients of all three inside the gather kernels."""
 
     @staticmethod
-    def forward(ctx, uv, idx, beta, B, N, k):
+    def forward(ctx, uv, idx, beta, B, N, k, sink_key=None):
         uv = nv.require_cuda(uv, "uv")
         idx = nv.require_cuda(idx, "idx", torch.int32)
         beta = nv.require_cuda(beta, "beta")
@@ -380,13 +425,31 @@ class _EdgeConvGather(torch.autograd.Function):
         cnt = torch.empty((P, F), dtype=torch.float32, device=dev)
         mean = torch.empty(F, dtype=torch.float32, device=dev)
         rstd = torch.empty(F, dtype=torch.float32, device=dev)
+        ev = None
+        if _ec_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         nv.check(L.dgcnn_edgeconv_fwd_stats(uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(),
                                             cnt.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(),
                                             ws.numel(), st), "edgeconv_fwd_stats")
         both = torch.empty((P, 2 * F), dtype=torch.float32, device=dev)
-        nv.check(L.dgcnn_edgeconv_fwd_apply_packed(uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(),
-                                                   mean.data_ptr(), rstd.data_ptr(), beta.data_ptr(), both.data_ptr(),
-                                                   st), "edgeconv_fwd_apply")
+        sk = _sinks
+        lst = sk.targets.get(sink_key, []) if (sk is not None and sink_key is not None) else []
+        if len(lst) == 1 and tuple(lst[0][0].shape[:2]) == (2, P):
+            pl, col = lst[0]
+            nv.check(L.dgcnn_edgeconv_fwd_apply_packed_sink(uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(),
+                                                            mean.data_ptr(), rstd.data_ptr(), beta.data_ptr(),
+                                                            both.data_ptr(), pl.data_ptr() + 2 * col, pl.shape[2],
+                                                            pl.shape[1] * pl.shape[2], st), "edgeconv_fwd_apply")
+            sk.mark(both.data_ptr(), F, 2 * F, [(pl, col)])                       # the max view
+            sk.mark(both.data_ptr() + 4 * F, F, 2 * F, [(pl, col + F)])           # the mean view
+        else:
+            nv.check(L.dgcnn_edgeconv_fwd_apply_packed(uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(),
+                                                       mean.data_ptr(), rstd.data_ptr(), beta.data_ptr(),
+                                                       both.data_ptr(), st), "edgeconv_fwd_apply")
+        if ev is not None:
+            ev[1].record()
+            _ec_events.append((B, N, F, k, ev[0], ev[1]))
         ctx.save_for_backward(uv, idx, beta, zmax, cnt, mean, rstd)
         ctx.dims = (B, N, F, k)
         return both[:, :F], both[:, F:], both
@@ -411,7 +474,7 @@ class _EdgeConvGather(torch.autograd.Function):
         nv.check(L.dgcnn_edgeconv_bwd_stats_packed_z(*common, guv.data_ptr(), ws.data_ptr(), ws.numel(), st),
                  "edgeconv_bwd_stats")
         nv.check(L.dgcnn_edgeconv_bwd_apply_packed_z(*common, guv.data_ptr(), 1, st), "edgeconv_bwd_apply")
-        return guv, None, s1, None, None, None
+        return guv, None, s1, None, None, None, None
 
 
 class _BnAct(torch.autograd.Function):
@@ -419,7 +482,7 @@ class _BnAct(torch.autograd.Function):
     group_bias [G,C] (optional) is added to the rows of group r // (P/G) before the statistics."""
 
     @staticmethod
-    def forward(ctx, z, beta, residual, relu_flag, group_bias=None):
+    def forward(ctx, z, beta, residual, relu_flag, group_bias=None, sink_key=None):
         z = nv.require_cuda(z, "z")
         beta = nv.require_cuda(beta, "beta")
         res = nv.require_cuda(residual, "residual") if residual is not None else None
@@ -432,9 +495,18 @@ class _BnAct(torch.autograd.Function):
         out = torch.empty_like(z)
         mean = torch.empty(C, dtype=torch.float32, device=dev)
         rstd = torch.empty(C, dtype=torch.float32, device=dev)
-        nv.check(L.dgcnn_bn_act_fwd_gb(z.data_ptr(), P, C, beta.data_ptr(), nv.ptr(res), nv.ptr(gb), grows,
-                                       int(bool(relu_flag)), out.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                       ws.data_ptr(), ws.numel(), nv.stream_ptr(dev)), "bn_act_fwd")
+        sk = _sinks
+        n_s, s_ptr, s_ld, s_pe, s_lst = (0, None, None, None, [])
+        if sk is not None and sink_key is not None and C % 4 == 0:
+            n_s, s_ptr, s_ld, s_pe, s_lst = sk.sink_args(sink_key)
+            if any(tuple(pl.shape[:2]) != (2, P) for pl, _ in s_lst):
+                n_s, s_lst = 0, []
+        nv.check(L.dgcnn_bn_act_fwd_sinks(z.data_ptr(), P, C, beta.data_ptr(), nv.ptr(res), nv.ptr(gb), grows,
+                                          int(bool(relu_flag)), out.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), n_s, s_ptr, s_ld, s_pe, nv.stream_ptr(dev)),
+                 "bn_act_fwd")
+        if n_s:
+            sk.mark(out.data_ptr(), C, C, s_lst)
         ctx.save_for_backward(z, out, mean, rstd, gb)
         ctx.relu = bool(relu_flag)
         ctx.has_res = res is not None
@@ -457,7 +529,7 @@ class _BnAct(torch.autograd.Function):
                                        gbeta.data_ptr(), nv.ptr(gpre), ws.data_ptr(), ws.numel(), nv.stream_ptr(dev)),
                  "bn_act_bwd")
         ggb = gz.view(gb.shape[0], ctx.grows, C).sum(dim=1) if gb is not None else None
-        return gz, gbeta, gpre, None, ggb
+        return gz, gbeta, gpre, None, ggb, None
 
 
 class _GroupMax(torch.autograd.Function):
@@ -575,11 +647,11 @@ def _conv_bn_vars(scope: str, cin: int, cout: int, trainable: bool, device):
     return w, b
 
 
-def _conv_bn_act(net2d, scope, cout, trainable, activation, residual2d=None):
+def _conv_bn_act(net2d, scope, cout, trainable, activation, residual2d=None, sink_key=None):
     """1x1 conv + BN(train) [+ residual] + activation on a [P,Cin] tensor, all through the C ABI."""
     w, b = _conv_bn_vars(scope, net2d.shape[1], cout, trainable, net2d.device)
     z = _Conv1x1.apply(net2d, w)
-    return _BnAct.apply(z, b, residual2d, activation is not None)
+    return _BnAct.apply(z, b, residual2d, activation is not None, None, sink_key)
 
 
 def _dbg(debug, t, name):
@@ -613,14 +685,15 @@ def edge_conv(point_cloud, k, num_filters, trainable, activation=relu, debug=Fal
     w0, b0 = _conv_bn_vars("conv0", 2 * C, F, trainable, x.device)              # ops.py:47-54
     wp = torch.cat([w0[:C] - w0[C:], w0[C:]], dim=1)                            # [C, 2F] = [Wa-Wb | Wb]
     uv = _Conv1x1.apply(x.reshape(B * N, C), wp)   # exact fp32 SIMT: the next layer's kNN is built on these features
-    net_max, net_mean, net = _EdgeConvGather.apply(uv, idx, b0, B, N, k)        # ops.py:53-58 (net = concat, in place)
+    li = _sinks.layer if _sinks is not None else -1
+    net_max, net_mean, net = _EdgeConvGather.apply(uv, idx, b0, B, N, k, ("ec", li, "both"))   # ops.py:53-58
     if debug: _dbg(debug, torch.empty(B, N, k, F, device="meta"), _cur_scope() + "/conv0 (never materialised)")
     _dbg(debug, net_max.view(B, N, 1, F), _cur_scope() + "/Max")
     _dbg(debug, net_mean.view(B, N, 1, F), _cur_scope() + "/Mean")
     _dbg(debug, net.view(B, N, 1, 2 * F), _cur_scope() + "/concat")
     res2d = _residual.reshape(B * N, CONV1_WIDTH) if _residual is not None else None
     act = relu if (_residual is not None) else activation
-    net = _conv_bn_act(net, "conv1", CONV1_WIDTH, trainable, act, res2d)        # ops.py:62-70 (+134)
+    net = _conv_bn_act(net, "conv1", CONV1_WIDTH, trainable, act, res2d, ("ec", li, "net"))   # ops.py:62-70 (+134)
     _dbg(debug, net.view(B, N, 1, CONV1_WIDTH), _cur_scope() + "/conv1")
     return [net_max.view(B, N, 1, F), net_mean.view(B, N, 1, F), net.view(B, N, 1, CONV1_WIDTH)]
 
@@ -643,6 +716,8 @@ def repeat_edge_conv(point_cloud, repeat, k, num_filters, trainable, debug=False
     tensors = []
     graph = []  # previous layer's neighbour lists warm-start the next layer's selection (same result)
     for i in range(repeat):
+        if _sinks is not None:
+            _sinks.layer = i
         with variable_scope("EdgeConv%d" % i):
             tensors += edge_conv(net, k[i], num_filters[i], trainable, debug=debug,
                                  _knn_hint=graph[-1] if graph else None, _knn_out=graph)
@@ -660,6 +735,8 @@ def repeat_residual_edge_conv(point_cloud, repeat, k, num_filters, trainable, de
     shortcut = None
     graph = []
     for i in range(repeat):
+        if _sinks is not None:
+            _sinks.layer = i
         with variable_scope("EdgeConv%d" % i):
             if shortcut is None:
                 tensors += edge_conv(net, k[i], num_filters[i], trainable, debug=debug, _knn_out=graph)

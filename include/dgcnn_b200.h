@@ -147,6 +147,13 @@ int dgcnn_edgeconv_bwd_apply_packed(const float* uv, const int32_t* idx, int B, 
                                     const float* beta, const float* g_max, const float* g_mean, const float* g_both,
                                     const float* s1, const float* s2, float* g_uv, dgcnn_stream_t stream);
 
+/* ..._sink: the forward apply pass additionally writes (max | mean) as bf16 hi / lo planes into columns [0,2F) of a
+ * tensor-core operand starting at sink_planes (row pitch sink_ld elements, second plane sink_plane_elems later):
+ * the consumer's concat operand (model.py:83-85) is filled by the producer, no split pass re-reads the tensor.      */
+int dgcnn_edgeconv_fwd_apply_packed_sink(const float* uv, const int32_t* idx, int B, int N, int F, int k,
+                                         const float* zmax, const float* mean, const float* rstd, const float* beta,
+                                         float* out_both, void* sink_planes, int sink_ld, int64_t sink_plane_elems,
+                                         dgcnn_stream_t stream);
 /* ..._z: the statistics pass also clears the v half of g_uv (g_uv_clear, may be NULL) so that the apply pass, told so by
  * v_half_cleared != 0, can scatter-add into it without a separate zeroing kernel.                               */
 int dgcnn_edgeconv_bwd_stats_packed_z(const float* uv, const int32_t* idx, int B, int N, int F, int k,
@@ -196,6 +203,17 @@ int dgcnn_bn_stats_from_tiles(const float* colstats, int tiles, int C, int64_t r
 int dgcnn_bn_apply_fwd(const float* z, int64_t rows, int C, const float* beta, const float* residual,
                        const float* group_bias, int group_rows, int relu, const float* mean, const float* rstd,
                        float* out, dgcnn_stream_t stream);
+/* ..._sinks: the same forward passes with up to two plane sinks (host arrays of n_sinks entries: device pointer of the
+ * first element of the column slice, row pitch, distance of the lo plane in elements): the output is also written as
+ * bf16 hi / lo planes into the operands of the layers that consume it.                                             */
+int dgcnn_bn_act_fwd_sinks(const float* z, int64_t rows, int C, const float* beta, const float* residual,
+                           const float* group_bias, int group_rows, int relu, float* out, float* mean, float* rstd,
+                           void* ws, size_t ws_bytes, int n_sinks, void* const* sink_planes, const int* sink_lds,
+                           const int64_t* sink_plane_elems, dgcnn_stream_t stream);
+int dgcnn_bn_apply_fwd_sinks(const float* z, int64_t rows, int C, const float* beta, const float* residual,
+                             const float* group_bias, int group_rows, int relu, const float* mean, const float* rstd,
+                             float* out, int n_sinks, void* const* sink_planes, const int* sink_lds,
+                             const int64_t* sink_plane_elems, dgcnn_stream_t stream);
 int dgcnn_bn_act_bwd_planes(const float* z, const float* out, const float* beta, const float* g_out, int64_t rows, int C,
                             const float* mean, const float* rstd, const float* group_bias, int group_rows, int relu,
                             float* g_z, void* g_z_planes, float* g_beta, void* ws, size_t ws_bytes,

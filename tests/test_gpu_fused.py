@@ -147,7 +147,7 @@ def test_edgeconv_packed_gradient_sources(dg, cuda):
     wm, wa, wb = (torch.randn((P, F), generator=g), torch.randn((P, F), generator=g), torch.randn((P, 2 * F), generator=g))
     uv = uv0.to(cuda).requires_grad_(True)
     beta = beta0.to(cuda).requires_grad_(True)
-    mx, mn, both = ops._EdgeConvGather.apply(uv, idx.to(cuda), beta, B, N, k)
+    mx, mn, both = ops._EdgeConvGather.apply(uv, idx.to(cuda), beta, B, N, k, None)
     assert torch.equal(both[:, :F], mx) and torch.equal(both[:, F:], mn)
     ((mx * wm.to(cuda)).sum() + (mn * wa.to(cuda)).sum() + (both * wb.to(cuda)).sum()).backward()
     # fp64 reference
@@ -253,3 +253,30 @@ def test_fused_loss_head_matches_torch(dg, cuda, K, weighted):
     assert abs(loss.item() - ref.item()) < 2e-6 * max(1.0, abs(ref.item()))
     assert abs(acc.item() - racc.item()) < 1e-6
     assert torch.allclose(a.grad.cpu().double(), b.grad, atol=1e-9, rtol=1e-5)
+
+
+def test_plane_sinks_do_not_change_the_model(dg, cuda, monkeypatch):
+    """model.build with producer-filled operand planes (ops.PlaneSinks) == the same build with separate split passes:
+    identical logits and gradients (the sinks only move where the bf16 hi/lo planes are written)."""
+    from dgcnn import model as M
+    B, N = 2, 512
+    mask = torch.ones((B, N, 1, 256), device=cuda) * M.DROPOUT_KEEP
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand((B, N, 3), generator=g)
+    y = torch.randint(0, 2, (B, N), generator=g)
+    orig = M.build
+    monkeypatch.setattr(M, "build", lambda pc, fl, dropout_mask=None: orig(pc, fl, dropout_mask=mask))
+    monkeypatch.setenv("DGCNN_CUDA_GRAPH", "0")
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DGCNN_PLANE_SINKS", mode)
+        tr = dg.trainval(_train_flags(B, N))
+        tr.initialize()
+        tr.zero_gradients(None)
+        r = tr.accum_gradient(None, [x], [y])
+        sm = tr.inference(None, [x], [y])
+        res[mode] = (tr.variables.flat_grad.clone(), r[2], torch.from_numpy(sm[0]))
+    assert torch.equal(res["1"][2], res["0"][2])                       # forward: bit-identical softmax
+    assert abs(res["1"][1] - res["0"][1]) < 1e-7
+    scale = res["0"][0].abs().max().item()
+    assert (res["1"][0] - res["0"][0]).abs().max().item() <= 2e-4 * scale    # backward: fp32 atomics reorder sums
