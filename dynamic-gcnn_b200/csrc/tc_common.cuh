@@ -85,6 +85,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn tensor_map_encoder();
 // bf16 planes [2][rows][cols] row-major -> 3-D map with a {64, box_rows, 1} box, 128B swizzle, zero OOB fill
 int make_plane_map(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, uint32_t box_rows);
+int make_plane_map_ld(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, int64_t ld, int64_t plane_elems,
+                      uint32_t box_rows);
 
 // ---- wide (128x256, persistent) GEMM variant: tc_gemm_wide.cu ----
 struct WideOut {

@@ -227,10 +227,16 @@ EncodeTiledFn tensor_map_encoder() {
 }
 
 int make_plane_map(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, uint32_t box_rows) {
+  return make_plane_map_ld(tm, planes, rows, cols, cols, rows * cols, box_rows);
+}
+
+// column slice of a wider operand: row pitch ld elements, second plane plane_elems elements after the first
+int make_plane_map_ld(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, int64_t ld, int64_t plane_elems,
+                      uint32_t box_rows) {
   EncodeTiledFn fn = tensor_map_encoder();
   if (!fn) return set_err(DGCNN_ERR_CUDA, "tensor map: cuTensorMapEncodeTiled unavailable");
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
-  cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * (cuuint64_t)cols * 2};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_elems * 2};
   cuuint32_t box[3] = {64, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(planes), dims, strides, box, estr,
@@ -309,7 +315,7 @@ extern "C" size_t dgcnn_tc_gemm_workspace_bytes(int M, int N, int K) {
 
 static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
                         int transB, void* ws, size_t ws_bytes, const OutGroups& og, float* colstats,
-                        dgcnn_stream_t stream);
+                        dgcnn_stream_t stream, int64_t a_ld = 0, int64_t a_plane_elems = 0);
 
 extern "C" int dgcnn_tc_gemm(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
                              int transB, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
@@ -317,6 +323,19 @@ extern "C" int dgcnn_tc_gemm(const void* a_planes, const void* b_planes, float* 
   OutGroups og;
   og.n = 0;
   return tc_gemm_impl(a_planes, b_planes, C, M, N, K, transA, transB, ws, ws_bytes, og, nullptr, stream);
+}
+
+extern "C" int dgcnn_tc_gemm_a_slice(const void* a_planes, int64_t a_ld, int64_t a_plane_elems, const void* b_planes,
+                                     float* C, int M, int N, int K, int transA, int transB, void* ws, size_t ws_bytes,
+                                     dgcnn_stream_t stream) {
+  DG_REQUIRE(C, DGCNN_ERR_INVALID, "tc_gemm_a_slice: null output");
+  const int64_t a_cols = transA ? M : K;
+  DG_REQUIRE(a_ld >= a_cols && (a_ld & 7) == 0 && a_plane_elems > 0 && (a_plane_elems & 7) == 0, DGCNN_ERR_INVALID,
+             "tc_gemm_a_slice: bad pitch %lld / plane distance %lld", (long long)a_ld, (long long)a_plane_elems);
+  OutGroups og;
+  og.n = 0;
+  return tc_gemm_impl(a_planes, b_planes, C, M, N, K, transA, transB, ws, ws_bytes, og, nullptr, stream, a_ld,
+                      a_plane_elems);
 }
 
 extern "C" int dgcnn_tc_gemm_stats_supported(int M, int N, int K) {
@@ -358,7 +377,7 @@ extern "C" int dgcnn_tc_gemm_grouped(const void* a_planes, const void* b_planes,
 
 static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
                         int transB, void* ws, size_t ws_bytes, const OutGroups& og, float* colstats,
-                        dgcnn_stream_t stream) {
+                        dgcnn_stream_t stream, int64_t a_ld, int64_t a_plane_elems) {
   cudaStream_t st = (cudaStream_t)stream;
   DG_REQUIRE(a_planes && b_planes && C, DGCNN_ERR_INVALID, "tc_gemm: null pointer");
   DG_REQUIRE(M > 0 && N > 0 && K > 0, DGCNN_ERR_INVALID, "tc_gemm: bad shape M=%d N=%d K=%d", M, N, K);
@@ -370,7 +389,8 @@ static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, in
   // transB, [N,K] (K-major).
   const bool a_k = !transA, b_k = transB != 0;
   CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, a_planes, a_k ? M : K, a_k ? K : M, a_k);
+  int rc = a_ld > 0 ? make_plane_map_ld(&tmA, a_planes, a_k ? M : K, a_k ? K : M, a_ld, a_plane_elems, a_k ? 128u : 64u)
+                    : make_map(&tmA, a_planes, a_k ? M : K, a_k ? K : M, a_k);
   if (rc) return rc;
   rc = make_map(&tmB, b_planes, b_k ? N : K, b_k ? K : N, b_k);
   if (rc) return rc;

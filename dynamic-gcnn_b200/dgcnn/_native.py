@@ -36,6 +36,7 @@ SIGNATURES = {
     "dgcnn_split_bf16": (_i, [_vp, _i64, _i, _i64, _vp, _i64, _i64, _vp]),
     "dgcnn_tc_gemm_workspace_bytes": (_sz, [_i, _i, _i]),
     "dgcnn_tc_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "dgcnn_tc_gemm_a_slice": (_i, [_vp, _i64, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "dgcnn_tc_gemm_stats_supported": (_i, [_i, _i, _i]),
     "dgcnn_tc_gemm_stats": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "dgcnn_tc_gemm_grouped": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

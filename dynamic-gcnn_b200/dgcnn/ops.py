@@ -33,6 +33,7 @@ class PlaneSinks:
         self.targets = {}   # producer key -> list of (planes [2,P,K] bf16, column)
         self.planes = {}    # consumer scope -> planes
         self.done = {}
+        self.where = {}     # (data_ptr, columns, row stride) -> (planes, column) of one operand that holds the tensor
         self.layer = 0
 
     def sink_args(self, key):
@@ -48,6 +49,11 @@ class PlaneSinks:
     def mark(self, t2d_ptr, cols, ld, lst):
         for pl, col in lst:
             self.done[(t2d_ptr, cols, ld, pl.data_ptr())] = col
+            self.where[(t2d_ptr, cols, ld)] = (pl, col)
+
+    def find(self, t2d):
+        """-> (planes, column) if some operand already holds the bf16 planes of this [rows, cols] tensor"""
+        return self.where.get((t2d.data_ptr(), t2d.shape[1], t2d.stride(0)))
 
 
 _sinks = None   # set by dgcnn.model.build for the duration of one forward pass
@@ -192,6 +198,8 @@ class _Conv1x1(torch.autograd.Function):
         a = nv.require_cuda(a, "conv input")
         w = nv.require_cuda(w, "conv weights")
         ctx.save_for_backward(a, w)
+        # if a producer already wrote this input as bf16 planes into some head operand, the weight gradient reuses them
+        ctx.a_planes = _sinks.find(a) if _sinks is not None else None
         return _gemm_raw(a, w, a.shape[0], w.shape[1], a.shape[1], 0, 0)
 
     @staticmethod
@@ -208,7 +216,18 @@ class _Conv1x1(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 ga = _tc_gemm_raw(pg, _split(w), P, Cin, Cout, 0, 1)
             if ctx.needs_input_grad[1]:
-                gw = _tc_gemm_raw(_split(a), pg, Cin, Cout, P, 1, 0)
+                if ctx.a_planes is not None:
+                    pl, col = ctx.a_planes
+                    L = nv.lib()
+                    gw = torch.empty((Cin, Cout), dtype=torch.float32, device=pg.device)
+                    need = L.dgcnn_tc_gemm_workspace_bytes(Cin, Cout, P)
+                    ws = nv.workspace(pg.device, need, "gemm") if need else None
+                    nv.check(L.dgcnn_tc_gemm_a_slice(pl.data_ptr() + 2 * col, pl.shape[2], pl.shape[1] * pl.shape[2],
+                                                     pg.data_ptr(), gw.data_ptr(), Cin, Cout, P, 1, 0, nv.ptr(ws),
+                                                     ws.numel() if ws is not None else 0, nv.stream_ptr(pg.device)),
+                             "tc_gemm_a_slice")
+                else:
+                    gw = _tc_gemm_raw(_split(a), pg, Cin, Cout, P, 1, 0)
             return ga, gw
         if ctx.needs_input_grad[0]:
             ga = _gemm_raw(g, w, P, Cin, Cout, 0, 1)  # g . W^T
@@ -443,6 +462,7 @@ class _EdgeConvGather(torch.autograd.Function):
                                                             pl.shape[1] * pl.shape[2], st), "edgeconv_fwd_apply")
             sk.mark(both.data_ptr(), F, 2 * F, [(pl, col)])                       # the max view
             sk.mark(both.data_ptr() + 4 * F, F, 2 * F, [(pl, col + F)])           # the mean view
+            sk.mark(both.data_ptr(), 2 * F, 2 * F, [(pl, col)])                   # the concat itself (conv1's input)
         else:
             nv.check(L.dgcnn_edgeconv_fwd_apply_packed(uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(),
                                                        mean.data_ptr(), rstd.data_ptr(), beta.data_ptr(),

@@ -90,6 +90,12 @@ size_t dgcnn_tc_gemm_workspace_bytes(int M, int N, int K);
 int dgcnn_tc_gemm(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA, int transB,
                   void* ws, size_t ws_bytes, dgcnn_stream_t stream);
 
+/* Same product with op(A) taken from a column slice of a wider pair of planes: a_planes points at the first element
+ * of the slice, rows are a_ld elements apart and the lo plane starts a_plane_elems elements after the hi plane (the
+ * operand a producer already filled for another layer is reused, e.g. for a weight gradient X^T.g).              */
+int dgcnn_tc_gemm_a_slice(const void* a_planes, int64_t a_ld, int64_t a_plane_elems, const void* b_planes, float* C,
+                          int M, int N, int K, int transA, int transB, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+
 /* Same product plus, from the accumulator, the per-column sum and sum of squares of every 128-row tile:
  * colstats [ceil(M/128)][2][N] fp32 (train-mode BatchNorm statistics of the layer output, slim.batch_norm at
  * ops.py:53,158 / model.py:71, without a second pass over C).  Only for shapes the 128x256 persistent kernel takes
