@@ -71,35 +71,76 @@ __device__ __forceinline__ int64_t nbr_off(const EcArgs& a, const int (&rows)[2]
   return (int64_t)r * (2 * a.F) + a.F;
 }
 
+// A lane owns the channel PAIR (f0, f0+1), f0 = 64*chunk + 2*lane: one 8-byte load per gathered row (and one 8-byte
+// vector atomic per scattered row) instead of two 4-byte ones.  `pair` = both channels exist and F is even (8-byte
+// alignment of every row start); otherwise element-wise with guards.
+struct EcLane {
+  int f0, f1;
+  bool ok0, ok1, pair;
+  __device__ __forceinline__ EcLane(int F, int chunk, int lane) {
+    f0 = chunk * 64 + 2 * lane;
+    f1 = f0 + 1;
+    ok0 = f0 < F;
+    ok1 = f1 < F;
+    pair = ok1 && ((F & 1) == 0);
+  }
+  __device__ __forceinline__ void ld(const float* __restrict__ base, float& x0, float& x1) const {
+    if (pair) {
+      const float2 t = __ldg(reinterpret_cast<const float2*>(base + f0));
+      x0 = t.x;
+      x1 = t.y;
+    } else {
+      x0 = ok0 ? __ldg(base + f0) : 0.f;
+      x1 = ok1 ? __ldg(base + f1) : 0.f;
+    }
+  }
+  __device__ __forceinline__ void st(float* __restrict__ base, float x0, float x1) const {
+    if (pair) {
+      *reinterpret_cast<float2*>(base + f0) = make_float2(x0, x1);
+    } else {
+      if (ok0) base[f0] = x0;
+      if (ok1) base[f1] = x1;
+    }
+  }
+  __device__ __forceinline__ void red(float* __restrict__ base, float x0, float x1) const {
+    if (pair) {
+      atomicAdd(reinterpret_cast<float2*>(base + f0), make_float2(x0, x1));
+    } else {
+      if (ok0) atomicAdd(base + f0, x0);
+      if (ok1) atomicAdd(base + f1, x1);
+    }
+  }
+};
+
 // pass 1 forward: zmax, tie count, per-block partial sum / sum of squares
 __global__ void __launch_bounds__(EC_THREADS)
     ec_fwd_stats_kernel(EcArgs a, float* __restrict__ zmax, float* __restrict__ cnt, double* __restrict__ acc) {
   __shared__ float red[2][EC_WARPS][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int f0 = blockIdx.y * 64 + lane, f1 = f0 + 32;
-  const bool ok0 = f0 < a.F, ok1 = f1 < a.F;
+  const EcLane L(a.F, blockIdx.y, lane);
   float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
   for (int p = blockIdx.x * EC_WARPS + warp; p < a.P; p += gridDim.x * EC_WARPS) {
     int rows[2];
     load_nbrs(a, p, lane, rows);
-    const float* up = a.uv + (int64_t)p * 2 * a.F;
-    const float u0 = ok0 ? up[f0] : 0.f, u1 = ok1 ? up[f1] : 0.f;
+    float u0, u1;
+    L.ld(a.uv + (int64_t)p * 2 * a.F, u0, u1);
     float m0 = -INFINITY, m1 = -INFINITY, c0 = 0.f, c1 = 0.f;
 #pragma unroll 4
     for (int j = 0; j < a.k; ++j) {
-      const float* vp = a.uv + nbr_off(a, rows, j);
-      const float z0 = u0 + (ok0 ? __ldg(vp + f0) : 0.f);
-      const float z1 = u1 + (ok1 ? __ldg(vp + f1) : 0.f);
+      float v0, v1;
+      L.ld(a.uv + nbr_off(a, rows, j), v0, v1);
+      const float z0 = u0 + v0;
+      const float z1 = u1 + v1;
       s0 += z0; q0 = fmaf(z0, z0, q0);
       s1 += z1; q1 = fmaf(z1, z1, q1);
       if (z0 > m0) { m0 = z0; c0 = 1.f; } else if (z0 == m0) c0 += 1.f;
       if (z1 > m1) { m1 = z1; c1 = 1.f; } else if (z1 == m1) c1 += 1.f;
     }
-    if (ok0) { zmax[(int64_t)p * a.F + f0] = m0; cnt[(int64_t)p * a.F + f0] = c0; }
-    if (ok1) { zmax[(int64_t)p * a.F + f1] = m1; cnt[(int64_t)p * a.F + f1] = c1; }
+    L.st(zmax + (int64_t)p * a.F, m0, m1);
+    L.st(cnt + (int64_t)p * a.F, c0, c1);
   }
-  red[0][warp][lane] = s0; red[0][warp][lane + 32] = s1;
-  red[1][warp][lane] = q0; red[1][warp][lane + 32] = q1;
+  red[0][warp][2 * lane] = s0; red[0][warp][2 * lane + 1] = s1;
+  red[1][warp][2 * lane] = q0; red[1][warp][2 * lane + 1] = q1;
   __syncthreads();
   if (threadIdx.x < 128) {
     const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
@@ -140,8 +181,9 @@ __global__ void __launch_bounds__(EC_THREADS)
                         float* __restrict__ omean, int opitch, __nv_bfloat16* __restrict__ sink, int sink_ld,
                         size_t sink_plane) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int f0 = blockIdx.y * 64 + lane, f1 = f0 + 32;
-  const bool ok0 = f0 < a.F, ok1 = f1 < a.F;
+  const EcLane L(a.F, blockIdx.y, lane);
+  const int f0 = L.f0, f1 = L.f1;
+  const bool ok0 = L.ok0, ok1 = L.ok1;
   const float mu0 = ok0 ? mean[f0] : 0.f, mu1 = ok1 ? mean[f1] : 0.f;
   const float r0 = ok0 ? rstd[f0] : 0.f, r1 = ok1 ? rstd[f1] : 0.f;
   const float b0 = ok0 ? beta[f0] : 0.f, b1 = ok1 ? beta[f1] : 0.f;
@@ -149,39 +191,39 @@ __global__ void __launch_bounds__(EC_THREADS)
   for (int p = blockIdx.x * EC_WARPS + warp; p < a.P; p += gridDim.x * EC_WARPS) {
     int rows[2];
     load_nbrs(a, p, lane, rows);
-    const float* up = a.uv + (int64_t)p * 2 * a.F;
-    const float u0 = ok0 ? up[f0] : 0.f, u1 = ok1 ? up[f1] : 0.f;
+    float u0, u1;
+    L.ld(a.uv + (int64_t)p * 2 * a.F, u0, u1);
     float y0 = 0.f, y1 = 0.f;
 #pragma unroll 4
     for (int j = 0; j < a.k; ++j) {
-      const float* vp = a.uv + nbr_off(a, rows, j);
-      const float z0 = u0 + (ok0 ? __ldg(vp + f0) : 0.f);
-      const float z1 = u1 + (ok1 ? __ldg(vp + f1) : 0.f);
+      float v0, v1;
+      L.ld(a.uv + nbr_off(a, rows, j), v0, v1);
+      const float z0 = u0 + v0;
+      const float z1 = u1 + v1;
       y0 += fmaxf(fmaf(z0 - mu0, r0, b0), 0.f);
       y1 += fmaxf(fmaf(z1 - mu1, r1, b1), 0.f);
     }
     const int64_t o = (int64_t)p * a.F, oo = (int64_t)p * opitch;
+    // BN(+)ReLU are monotone, so the max commutes with them
+    float zm0, zm1;
+    L.ld(zmax + o, zm0, zm1);
+    const float vx0 = fmaxf(fmaf(zm0 - mu0, r0, b0), 0.f), vx1 = fmaxf(fmaf(zm1 - mu1, r1, b1), 0.f);
+    const float vm0 = y0 * invk, vm1 = y1 * invk;
+    L.st(omax + oo, vx0, vx1);
+    L.st(omean + oo, vm0, vm1);
     // optional plane sink: the same values as bf16 hi / lo planes at columns [0,F) (max) and [F,2F) (mean) of a
     // tensor-core operand (the consumer's concat operand), so that no separate split pass reads them again
-    auto put = [&](int col, float v) {
-      const __nv_bfloat16 h = __float2bfloat16_rn(v);
-      const size_t e = (size_t)p * sink_ld + col;
-      sink[e] = h;
-      sink[sink_plane + e] = __float2bfloat16_rn(v - __bfloat162float(h));
-    };
-    if (ok0) {
-      const float vm = y0 * invk;
-      const float vx = fmaxf(fmaf(zmax[o + f0] - mu0, r0, b0), 0.f);  // BN(+)ReLU are monotone: max commutes
-      omean[oo + f0] = vm;
-      omax[oo + f0] = vx;
-      if (sink) { put(f0, vx); put(a.F + f0, vm); }
-    }
-    if (ok1) {
-      const float vm = y1 * invk;
-      const float vx = fmaxf(fmaf(zmax[o + f1] - mu1, r1, b1), 0.f);
-      omean[oo + f1] = vm;
-      omax[oo + f1] = vx;
-      if (sink) { put(f1, vx); put(a.F + f1, vm); }
+    if (sink != nullptr && L.pair) {
+      auto put = [&](int col, float x0, float x1) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+        const float2 hf = __bfloat1622float2(h);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+        const size_t e = (size_t)p * sink_ld + col;
+        *reinterpret_cast<__nv_bfloat162*>(sink + e) = h;
+        *reinterpret_cast<__nv_bfloat162*>(sink + sink_plane + e) = l;
+      };
+      put(f0, vx0, vx1);
+      put(a.F + f0, vm0, vm1);
     }
   }
 }
@@ -198,8 +240,9 @@ __global__ void __launch_bounds__(EC_THREADS)
                   float* __restrict__ guv) {
   __shared__ float red[2][EC_WARPS][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int f0 = blockIdx.y * 64 + lane, f1 = f0 + 32;
-  const bool ok0 = f0 < a.F, ok1 = f1 < a.F;
+  const EcLane L(a.F, blockIdx.y, lane);
+  const int f0 = L.f0, f1 = L.f1;
+  const bool ok0 = L.ok0, ok1 = L.ok1;
   const float mu0 = ok0 ? mean[f0] : 0.f, mu1 = ok1 ? mean[f1] : 0.f;
   const float r0 = ok0 ? rstd[f0] : 0.f, r1 = ok1 ? rstd[f1] : 0.f;
   const float b0 = ok0 ? beta[f0] : 0.f, b1 = ok1 ? beta[f1] : 0.f;
@@ -214,34 +257,36 @@ __global__ void __launch_bounds__(EC_THREADS)
   for (int p = blockIdx.x * EC_WARPS + warp; p < a.P; p += gridDim.x * EC_WARPS) {
     int rows[2];
     load_nbrs(a, p, lane, rows);
-    const float* up = a.uv + (int64_t)p * 2 * a.F;
     const int64_t o = (int64_t)p * a.F;
-    const float u0 = ok0 ? up[f0] : 0.f, u1 = ok1 ? up[f1] : 0.f;
-    const float zm0 = ok0 ? zmax[o + f0] : 0.f, zm1 = ok1 ? zmax[o + f1] : 0.f;
+    float u0, u1, zm0, zm1, cn0, cn1;
+    L.ld(a.uv + (int64_t)p * 2 * a.F, u0, u1);
+    L.ld(zmax + o, zm0, zm1);
+    L.ld(cnt + o, cn0, cn1);
     // the gradients of max / mean arrive from up to two consumers: separate [P,F] tensors and/or one packed
     // [P,2F] = (max | mean) tensor (the conv1 operand); summed here instead of in a separate pass
     float gM0 = 0.f, gM1 = 0.f, gA0 = 0.f, gA1 = 0.f;
-    if (gmax) { if (ok0) gM0 = gmax[o + f0]; if (ok1) gM1 = gmax[o + f1]; }
-    if (gmean) { if (ok0) gA0 = gmean[o + f0]; if (ok1) gA1 = gmean[o + f1]; }
+    if (gmax) L.ld(gmax + o, gM0, gM1);
+    if (gmean) L.ld(gmean + o, gA0, gA1);
     if (gboth) {
       const float* gb = gboth + (int64_t)p * 2 * a.F;
-      if (ok0) { gM0 += gb[f0]; gA0 += gb[a.F + f0]; }
-      if (ok1) { gM1 += gb[f1]; gA1 += gb[a.F + f1]; }
+      float t0, t1;
+      L.ld(gb, t0, t1);
+      gM0 += t0; gM1 += t1;
+      L.ld(gb + a.F, t0, t1);
+      gA0 += t0; gA1 += t1;
     }
     const float gm0 = gA0 * invk, gm1 = gA1 * invk;
-    const float gx0 = ok0 ? gM0 / cnt[o + f0] : 0.f, gx1 = ok1 ? gM1 / cnt[o + f1] : 0.f;
+    const float gx0 = ok0 ? gM0 / cn0 : 0.f, gx1 = ok1 ? gM1 / cn1 : 0.f;
     float gu0 = 0.f, gu1 = 0.f;
-    if (!APPLY && guv != nullptr) {   // statistics pass: clear this point's v half for the scatter-add of the apply pass
-      float* gvp = guv + (int64_t)p * 2 * a.F + a.F;
-      if (ok0) gvp[f0] = 0.f;
-      if (ok1) gvp[f1] = 0.f;
-    }
+    if (!APPLY && guv != nullptr)     // statistics pass: clear this point's v half for the scatter-add of the apply pass
+      L.st(guv + (int64_t)p * 2 * a.F + a.F, 0.f, 0.f);
 #pragma unroll 4
     for (int j = 0; j < a.k; ++j) {
       const int64_t off = nbr_off(a, rows, j);
-      const float* vp = a.uv + off;
-      const float z0 = u0 + (ok0 ? __ldg(vp + f0) : 0.f);
-      const float z1 = u1 + (ok1 ? __ldg(vp + f1) : 0.f);
+      float v0, v1;
+      L.ld(a.uv + off, v0, v1);
+      const float z0 = u0 + v0;
+      const float z1 = u1 + v1;
       const float zh0 = (z0 - mu0) * r0, zh1 = (z1 - mu1) * r1;
       const bool act0 = fmaf(z0 - mu0, r0, b0) > 0.f, act1 = fmaf(z1 - mu1, r1, b1) > 0.f;
       const float gp0 = act0 ? gm0 + (z0 == zm0 ? gx0 : 0.f) : 0.f;
@@ -253,19 +298,14 @@ __global__ void __launch_bounds__(EC_THREADS)
         const float gz0 = r0 * (gp0 - m10 - zh0 * m20);
         const float gz1 = r1 * (gp1 - m11 - zh1 * m21);
         gu0 += gz0; gu1 += gz1;
-        if (ok0) atomicAdd(guv + off + f0, gz0);   // scatter-add into the v half (tf.gather grad)
-        if (ok1) atomicAdd(guv + off + f1, gz1);
+        L.red(guv + off, gz0, gz1);                // scatter-add into the v half (tf.gather grad)
       }
     }
-    if (APPLY) {
-      float* gup = guv + (int64_t)p * 2 * a.F;
-      if (ok0) gup[f0] = gu0;
-      if (ok1) gup[f1] = gu1;
-    }
+    if (APPLY) L.st(guv + (int64_t)p * 2 * a.F, gu0, gu1);
   }
   if (!APPLY) {
-    red[0][warp][lane] = a0; red[0][warp][lane + 32] = a1;
-    red[1][warp][lane] = q0; red[1][warp][lane + 32] = q1;
+    red[0][warp][2 * lane] = a0; red[0][warp][2 * lane + 1] = a1;
+    red[1][warp][2 * lane] = q0; red[1][warp][2 * lane + 1] = q1;
     __syncthreads();
     if (threadIdx.x < 128) {
       const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
@@ -412,8 +452,9 @@ extern "C" int dgcnn_edgeconv_fwd_apply_packed_sink(const float* uv, const int32
                                                     const float* beta, float* out_both, void* sink_planes, int sink_ld,
                                                     int64_t sink_plane_elems, dgcnn_stream_t stream) {
   DG_REQUIRE(out_both, DGCNN_ERR_INVALID, "edgeconv_fwd_apply_packed_sink: null pointer");
-  DG_REQUIRE(!sink_planes || (sink_ld >= 2 * F && sink_plane_elems > 0), DGCNN_ERR_INVALID,
-             "edgeconv_fwd_apply_packed_sink: bad sink geometry");
+  DG_REQUIRE(!sink_planes || (sink_ld >= 2 * F && sink_plane_elems > 0 && (F & 1) == 0 && (sink_ld & 1) == 0 &&
+                              (sink_plane_elems & 1) == 0 && ((uintptr_t)sink_planes & 3) == 0),
+             DGCNN_ERR_INVALID, "edgeconv_fwd_apply_packed_sink: bad sink geometry (F, pitch, plane distance must be even)");
   return ec_fwd_apply_impl(uv, idx, B, N, F, k, zmax, mean, rstd, beta, out_both, out_both + F, 2 * F, sink_planes, sink_ld,
                            sink_plane_elems, stream);
 }

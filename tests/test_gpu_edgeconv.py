@@ -40,7 +40,8 @@ def test_edges_bit_exact_and_grad(dg, oracle, cuda, B, N, C, k):
     assert torch.allclose(xc.grad.cpu(), xr.grad, atol=1e-4, rtol=1e-4)
 
 
-@pytest.mark.parametrize("B,N,C,k,F", [(2, 256, 3, 20, 64), (2, 100, 64, 16, 64), (1, 130, 4, 40, 32), (2, 96, 7, 5, 96)])
+@pytest.mark.parametrize("B,N,C,k,F", [(2, 256, 3, 20, 64), (2, 100, 64, 16, 64), (1, 130, 4, 40, 32), (2, 96, 7, 5, 96),
+                                         (1, 70, 3, 6, 33)])
 def test_edge_conv_forward_backward(dg, oracle, cuda, B, N, C, k, F):
     rng = np.random.RandomState(C + k)
     x = torch.from_numpy(rng.rand(B, N, C).astype(np.float32))
