@@ -135,6 +135,8 @@ class trainval(object):
     # with the same input shapes (lazy workspaces and function attributes are then in place) the micro-step is
     # captured once into a CUDA graph on static input buffers and replayed.  DGCNN_CUDA_GRAPH=0 disables it.
     GRAPH_WARMUP = 2
+    GRAPH_MAX = 4      # captured graphs kept alive (each owns its activations); least recently used is dropped.
+                       # Ragged data (-np -1: a different N per batch) therefore cannot grow memory without bound.
 
     def _as_tensor(self, a):
         return a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))
@@ -150,8 +152,11 @@ class trainval(object):
         src_p = self._as_tensor(data_i)
         key = (tuple(src_p.shape), weight_i is not None)
         if not hasattr(self, "_graphs"):
-            self._graphs, self._graph_seen = {}, {}
+            from collections import OrderedDict
+            self._graphs, self._graph_seen = OrderedDict(), {}
         ent = self._graphs.get(key) if use_graph else None
+        if ent is not None:
+            self._graphs.move_to_end(key)
         if ent is None:
             pts = self._to_dev(data_i, torch.float32)
             lab = self._to_dev(label_i, torch.int64)
@@ -169,6 +174,12 @@ class trainval(object):
                 acc, loss = self._tower_step_eager(ent["pts"], ent["lab"], ent["wgt"], G)
             ent.update(graph=graph, acc=acc, loss=loss, launches=nv.launch_count() - n0)
             self._graphs[key] = ent
+            gmax = int(os.environ.get("DGCNN_CUDA_GRAPH_MAX", self.GRAPH_MAX))
+            while len(self._graphs) > max(gmax, 1):
+                _, old = self._graphs.popitem(last=False)     # least recently used: frees its private memory pool
+                del old
+            if len(self._graph_seen) > 4096:                   # bounded bookkeeping for never-repeating shapes
+                self._graph_seen.clear()
             # a capture records but does not execute: fall through to the replay below
         else:
             pass

@@ -280,3 +280,23 @@ def test_plane_sinks_do_not_change_the_model(dg, cuda, monkeypatch):
     assert abs(res["1"][1] - res["0"][1]) < 1e-7
     scale = res["0"][0].abs().max().item()
     assert (res["1"][0] - res["0"][0]).abs().max().item() <= 2e-4 * scale    # backward: fp32 atomics reorder sums
+
+
+def test_cuda_graph_cache_is_bounded(dg, cuda, monkeypatch):
+    """Ragged data (a different N per batch, reference production mode -np -1) must not accumulate captured graphs:
+    the trainer keeps at most DGCNN_CUDA_GRAPH_MAX of them (LRU) and keeps producing finite losses."""
+    monkeypatch.setenv("DGCNN_CUDA_GRAPH", "1")
+    monkeypatch.setenv("DGCNN_CUDA_GRAPH_MAX", "2")
+    tr = dg.trainval(_train_flags(2, 512))
+    tr.initialize()
+    g = torch.Generator().manual_seed(9)
+    for N in (512, 640, 768, 512, 640):
+        x = torch.rand((2, N, 3), generator=g)
+        y = torch.randint(0, 2, (2, N), generator=g)
+        for _ in range(4):                                   # 2 eager + capture + replay per shape
+            tr.zero_gradients(None)
+            r = tr.accum_gradient(None, [x], [y])
+            tr.apply_gradient(None)
+            assert np.isfinite(r[2])
+        assert len(tr._graphs) <= 2
+    assert list(tr._graphs.keys())[-1][0] == (2, 640, 3)
