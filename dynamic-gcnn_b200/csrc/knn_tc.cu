@@ -441,11 +441,15 @@ __global__ void __launch_bounds__(256)
   const float* xi = x + p * C;
   const float si = sb[row];
   const bool staged = (C & 3) == 0 && C >= 16;
-  const int pitch = C + 4;
-  float* stg = rf_smem + (size_t)warp * 33 * pitch;
+  // CT > 0: the candidate rows are staged in two halves of CT/2 channels ([32][CT/2 + 4] floats + the query row:
+  // half the shared memory per warp = twice the resident warps; the fmaf chain simply continues across the halves)
+  constexpr int HC = CT > 0 ? CT / 2 : 0;
+  const int pitch = CT > 0 ? HC + 4 : C + 4;
+  float* stg = CT > 0 ? rf_smem + (size_t)warp * (CT + 32 * (HC + 4)) + CT : rf_smem + (size_t)warp * 33 * pitch;
+  float* xq = CT > 0 ? stg - CT : stg + 32 * pitch;   // the query row
   const int cpr = C >> 2;   // 16-byte chunks per row
   if (staged) {
-    for (int c4 = lane; c4 < cpr; c4 += 32) cp_async16(stg + 32 * pitch + c4 * 4, xi + c4 * 4);
+    for (int c4 = lane; c4 < cpr; c4 += 32) cp_async16(xq + c4 * 4, xi + c4 * 4);
   }
   const uint16_t* cl = cand + (size_t)4 * p * cap;
   RowSel<KS> R;
@@ -462,20 +466,41 @@ __global__ void __launch_bounds__(256)
     float d = __int_as_float(0x7f800000);
     if (staged) {
       if (CT > 0) {
-        // lanes 0..15 / 16..31 fetch the 16-byte chunks of two candidate rows per pass (CT/4 == 16 chunks per row)
-        constexpr int CPR = CT > 0 ? CT / 4 : 1;                       // 16-byte chunks per row
-        constexpr int RPP = 32 / CPR > 0 ? 32 / CPR : 1;               // rows per pass
+        constexpr int CPH = HC >= 4 ? HC / 4 : 1;                      // 16-byte chunks per half row
+        constexpr int RPP = 32 / CPH > 0 ? 32 / CPH : 1;               // rows per pass
         constexpr int LPR = 32 / RPP;                                  // lanes per row
         const int sub = lane / LPR, c4l = lane - sub * LPR;
-#pragma unroll 4
-        for (int r = 0; r < 32; r += RPP) {
-          const int jr = __shfl_sync(FULL, j, r + sub);
-          if (jr >= 0) {
+        float acc = 0.0f;
 #pragma unroll
-            for (int c4 = c4l; c4 < CPR; c4 += LPR)
-              cp_async16(stg + (r + sub) * pitch + c4 * 4, xb + (int64_t)jr * CT + c4 * 4);
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll 4
+          for (int r = 0; r < 32; r += RPP) {
+            const int jr = __shfl_sync(FULL, j, r + sub);
+            if (jr >= 0) {
+#pragma unroll
+              for (int c4 = c4l; c4 < CPH; c4 += LPR)
+                cp_async16(stg + (r + sub) * pitch + c4 * 4, xb + (int64_t)jr * CT + h * HC + c4 * 4);
+            }
           }
+          cp_async_commit();
+          cp_async_wait<0>();
+          __syncwarp();
+          if (j >= 0) {
+            const float* a = xq + h * HC;
+            const float* bb = stg + lane * pitch;
+#pragma unroll 4
+            for (int c = 0; c < HC; c += 4) {
+              const float4 a4 = *reinterpret_cast<const float4*>(a + c);
+              const float4 b4 = *reinterpret_cast<const float4*>(bb + c);
+              acc = __fmaf_rn(a4.x, b4.x, acc);
+              acc = __fmaf_rn(a4.y, b4.y, acc);
+              acc = __fmaf_rn(a4.z, b4.z, acc);
+              acc = __fmaf_rn(a4.w, b4.w, acc);
+            }
+          }
+          __syncwarp();
         }
+        if (j >= 0) d = __fadd_rn(__fsub_rn(__fadd_rn(si, sb[j]), __fmul_rn(2.0f, acc)), 0.0f);
       } else {
         const int total = 32 * cpr;
         for (int q = lane; q < total; q += 32) {
@@ -483,26 +508,26 @@ __global__ void __launch_bounds__(256)
           const int jr = __shfl_sync(FULL, j, r);
           if (jr >= 0) cp_async16(stg + r * pitch + c4 * 4, xb + (int64_t)jr * C + c4 * 4);
         }
-      }
-      cp_async_commit();
-      cp_async_wait<0>();
-      __syncwarp();
-      if (j >= 0) {
-        float acc = 0.0f;
-        const float* a = stg + 32 * pitch;
-        const float* bb = stg + lane * pitch;
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        if (j >= 0) {
+          float acc = 0.0f;
+          const float* a = xq;
+          const float* bb = stg + lane * pitch;
 #pragma unroll 4
-        for (int c = 0; c < C; c += 4) {
-          const float4 a4 = *reinterpret_cast<const float4*>(a + c);
-          const float4 b4 = *reinterpret_cast<const float4*>(bb + c);
-          acc = __fmaf_rn(a4.x, b4.x, acc);
-          acc = __fmaf_rn(a4.y, b4.y, acc);
-          acc = __fmaf_rn(a4.z, b4.z, acc);
-          acc = __fmaf_rn(a4.w, b4.w, acc);
+          for (int c = 0; c < C; c += 4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(a + c);
+            const float4 b4 = *reinterpret_cast<const float4*>(bb + c);
+            acc = __fmaf_rn(a4.x, b4.x, acc);
+            acc = __fmaf_rn(a4.y, b4.y, acc);
+            acc = __fmaf_rn(a4.z, b4.z, acc);
+            acc = __fmaf_rn(a4.w, b4.w, acc);
+          }
+          d = __fadd_rn(__fsub_rn(__fadd_rn(si, sb[j]), __fmul_rn(2.0f, acc)), 0.0f);
         }
-        d = __fadd_rn(__fsub_rn(__fadd_rn(si, sb[j]), __fmul_rn(2.0f, acc)), 0.0f);
+        __syncwarp();
       }
-      __syncwarp();
     } else if (j >= 0) {
       const float* xj = xb + (int64_t)j * C;
       float acc = 0.0f;
@@ -832,7 +857,7 @@ int knn_tc_run(const float* x, int32_t* idx, int B, int N, int C, int k, void* w
   count_launch();
   DG_CUDA_LAUNCH_CHECK("knn_tc_filter_kernel");
   const bool staged = (C & 3) == 0 && C >= 16;
-  const size_t rsm = staged ? (size_t)8 * 33 * (C + 4) * 4 : 0;
+  const size_t rsm = !staged ? 0 : (C == 64 ? (size_t)8 * (64 + 32 * 36) * 4 : (size_t)8 * 33 * (C + 4) * 4);
   const int fb_grid = 4 * num_sms();
   if (k <= 32) {
     if (C == 64)

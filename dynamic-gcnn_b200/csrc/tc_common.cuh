@@ -93,7 +93,7 @@ struct WideOut {
   float* C;            // [splits][M][N] (splits > 1: partial sums in the workspace)
   float* colstats;     // [m_tiles][2][N] per-column sum / sum of squares of each 128-row tile, or null
   int n_groups;        // > 0: column ranges go to separate dense buffers (gradient of a concat operand)
-  int dbg_nostore;     // tuning aid (DGCNN_WIDE_NOSTORE=1): skip the global stores of the epilogue
+  int dbg_nostore;     // profiling experiments only (always 0 in the library): skip the global stores of the epilogue
   int start[32];
   int width[32];
   float* ptr[32];

@@ -401,9 +401,7 @@ static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, in
     wo.C = C;
     wo.colstats = colstats;
     wo.n_groups = og.n;
-    static int nostore = -1;
-    if (nostore < 0) nostore = getenv("DGCNN_WIDE_NOSTORE") ? atoi(getenv("DGCNN_WIDE_NOSTORE")) : 0;
-    wo.dbg_nostore = nostore;
+    wo.dbg_nostore = 0;
     for (int g = 0; g < og.n; ++g) {
       wo.start[g] = og.start[g];
       wo.width[g] = og.width[g];
