@@ -6,12 +6,13 @@ With --gpus N (launched under torchrun) every rank keeps 24 clouds (weak scaling
 N=8 is configs[3]) and the step ends with ONE NCCL all-reduce of the flat gradient buffer.
 
 A "step" = zero_gradients + accum_gradient (fwd+bwd of the rank's 24 clouds) + apply_gradient through the
-reference-facing trainer API (dgcnn.trainval).  Two timings:
+reference-facing trainer API (dgcnn.trainval); the trainer replays the micro-step from a CUDA graph.  Two timings:
   value : inputs already resident in HBM, no host read inside the loop; CUDA events, max over ranks.
   e2e   : the same call with pinned HOST inputs (H2D copy every step) and a device->host read of the loss
           every step.
-roofline    : the fused k_nn launch on the [24,2048,64] feature clouds (dominant hand-written kernel), timed
-              live with CUDA events on the launching stream inside the timed steps.
+roofline    : the largest single launch of the step, tc_gemm_wide_kernel on the FC0 layer (tensor bound), timed live
+              with CUDA events on the launching stream in three extra eagerly-issued steps (a captured graph cannot
+              carry timing events); the fused k_nn and the EdgeConv gather passes are reported beside it.
 cpu_baseline: the oracle (reference-equivalent CPU restatement; TF1 cannot be installed) on a bounded sample.
 --impl reference : that CPU arm alone, with all host threads.
 """
