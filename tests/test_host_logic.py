@@ -156,3 +156,36 @@ def test_two_rank_allreduce_equals_tower_mean_summed_over_microsteps():
         assert torch.allclose(got[r][:6], w.grad.reshape(-1), atol=1e-6)
         assert torch.allclose(got[r][-2], total.detach(), atol=1e-6)
     assert torch.equal(got[0], got[1])
+
+
+def test_plane_sink_layout_matches_the_concat_order():
+    """model._make_sinks: the column each producer is told to fill equals the position of its tensor in the
+    reference's concats (model.py:60-63 MergedEdgeConv input; model.py:83-85 FC0 input = tensors ++ merged)."""
+    import torch
+    from types import SimpleNamespace
+    from dgcnn import model as M, ops
+    fl = SimpleNamespace(MODEL_NAME="dgcnn", EDGE_CONV_LAYERS=3, EDGE_CONV_FILTERS=[64, 32, 64], FC_LAYERS=2,
+                         FC_FILTERS=[512, 256])
+    P = 2048
+    sk = M._make_sinks(fl, P, torch.device("meta"))
+    assert sk is not None
+    widths = [64, 64, 64, 32, 32, 64, 64, 64, 64]                 # (max, mean, net) per layer
+    assert tuple(sk.planes["FC0"].shape) == (2, P, sum(widths) + 1024)
+    assert tuple(sk.planes["MergedEdgeConv"].shape) == (2, P, 3 * 64)
+    assert tuple(sk.planes["FC1"].shape) == (2, P, 512)
+    col = 0
+    for i, f in enumerate([64, 32, 64]):
+        (pl, c), = sk.targets[("ec", i, "both")]
+        assert pl is sk.planes["FC0"] and c == col                # max | mean adjacent
+        (p0, c0), (p1, c1) = sk.targets[("ec", i, "net")]
+        assert p0 is sk.planes["FC0"] and c0 == col + 2 * f
+        assert p1 is sk.planes["MergedEdgeConv"] and c1 == 64 * i
+        col += 2 * f + 64
+    assert sk.targets[("layer", "MergedEdgeConv")] == [(sk.planes["FC0"], col)]
+    assert sk.targets[("layer", "FC0")] == [(sk.planes["FC1"], 0)]
+    # no FC head / tiny clouds: producers keep their separate split passes
+    fl.MODEL_NAME = "residual-dgcnn-nofc"
+    assert M._make_sinks(fl, P, torch.device("meta")) is None
+    fl.MODEL_NAME = "dgcnn"
+    assert M._make_sinks(fl, 512, torch.device("meta")) is None
+    assert ops._sinks is None
