@@ -54,9 +54,10 @@ int dgcnn_knn(const float* x, int32_t* idx, int B, int N, int C, int k, void* ws
               dgcnn_stream_t stream);
 /* Same result as dgcnn_knn, bit for bit, with a warm start: hint [B,N,k] int32 holds, per row, k DISTINCT
  * in-range column indices (typically the previous EdgeConv layer's neighbours of the same clouds: the reference
- * recomputes the graph per layer, ops.py:91-96).  Their exact distances bound the k-th smallest from above, so
- * the threshold filter starts tight instead of at +inf.  hint == NULL is dgcnn_knn.  A hint row with duplicate
- * indices violates the precondition (the bound would be invalid).                                           */
+ * recomputes the graph per layer, ops.py:91-96).  Their exact distances bound the k-th smallest from above.  Only the
+ * SIMT path (clouds of fewer than 256 points, or more than 64 channels) uses it; the tensor-core path derives a tighter
+ * bound from its own first sweep and ignores the hint.  hint == NULL is dgcnn_knn.  A hint row with duplicate indices
+ * violates the precondition (the bound would be invalid).                                                      */
 int dgcnn_knn_hinted(const float* x, const int32_t* hint, int32_t* idx, int B, int N, int C, int k, void* ws,
                      size_t ws_bytes, dgcnn_stream_t stream);
 /* ops.py:18 on a materialised matrix: D [rows,N] -> idx [rows,k] (k smallest, same tie rule) */
