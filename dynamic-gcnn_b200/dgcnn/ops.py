@@ -91,7 +91,8 @@ def k_nn(points: torch.Tensor, k: int, hint: Optional[torch.Tensor] = None) -> t
     (only the indices are used downstream, ops.py:19,34).
 
     hint (optional, [B,N,>=k] int32, DISTINCT indices per row -- e.g. the previous layer's result) warm-starts the
-    selection threshold; the result is identical with or without it."""
+    selection threshold of the SIMT path (small clouds / more than 64 channels); the tensor-core path derives a tighter
+    bound from its own first sweep.  The result is identical with or without it."""
     x = nv.require_cuda(points.detach(), "points")
     if x.dim() != 3:
         raise ValueError("k_nn: points must be [B,N,C]")
