@@ -29,7 +29,9 @@ int num_sms();
 void count_launch(int n = 1);
 // per-channel fp64 accumulators acc[2][C] filled by the statistics kernels with atomics (edge.cu)
 int stats_acc_reset(void* ws, int C, cudaStream_t st);
-int launch_finalize_stats(const double* acc, int C, double count, float eps, float* mean, float* rstd, cudaStream_t st);
+// pivot (optional, [C]): the totals are those of (z - pivot)
+int launch_finalize_stats(const double* acc, int C, double count, float eps, float* mean, float* rstd, cudaStream_t st,
+                          const float* pivot = nullptr);
 int launch_finalize_sums(const double* acc, int C, float* s1, float* s2, cudaStream_t st);
 
 constexpr unsigned FULL = 0xffffffffu;

@@ -41,16 +41,10 @@ SIGNATURES = {
     "dgcnn_tc_gemm_stats": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "dgcnn_tc_gemm_grouped": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dgcnn_edgeconv_workspace_bytes": (_sz, [_i]),
-    "dgcnn_edgeconv_fwd_stats": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "dgcnn_edgeconv_fwd_apply": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "dgcnn_edgeconv_bwd_stats": (_i, [_vp, _vp, _i, _i, _i, _i] + [_vp] * 9 + [_vp, _sz, _vp]),
-    "dgcnn_edgeconv_bwd_apply": (_i, [_vp, _vp, _i, _i, _i, _i] + [_vp] * 10 + [_vp]),
-    "dgcnn_edgeconv_fwd_apply_packed": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "dgcnn_edgeconv_bwd_stats_packed": (_i, [_vp, _vp, _i, _i, _i, _i] + [_vp] * 10 + [_vp, _sz, _vp]),
-    "dgcnn_edgeconv_bwd_apply_packed": (_i, [_vp, _vp, _i, _i, _i, _i] + [_vp] * 11 + [_vp]),
-    "dgcnn_edgeconv_bwd_stats_packed_z": (_i, [_vp, _vp, _i, _i, _i, _i] + [_vp] * 10 + [_vp, _vp, _sz, _vp]),
-    "dgcnn_edgeconv_bwd_apply_packed_z": (_i, [_vp, _vp, _i, _i, _i, _i] + [_vp] * 11 + [_i, _vp]),
-    "dgcnn_edgeconv_fwd_apply_packed_sink": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
+    "dgcnn_edgeconv_fwd_stats": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "dgcnn_edgeconv_fwd_apply": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
+    "dgcnn_edgeconv_bwd_stats": (_i, [_vp] * 6 + [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dgcnn_edgeconv_bwd_apply": (_i, [_vp, _i, _vp, _i, _i, _i, _i] + [_vp] * 10 + [_i, _vp]),
     "dgcnn_bn_act_fwd_sinks": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp, _vp, _vp, _vp]),
     "dgcnn_bn_apply_fwd_sinks": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "dgcnn_bn_workspace_bytes": (_sz, [_i]),
@@ -70,6 +64,7 @@ SIGNATURES = {
 }
 
 ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = -1, -2, -3, -4
+DT_F32, DT_BF16 = 0, 1   # DGCNN_F32 / DGCNN_BF16
 
 
 def lib():

@@ -73,6 +73,7 @@ _knn_forced = None
 _knn_events = None
 _gemm_events = None
 _ec_events = None
+_ec_bwd_events = None
 
 
 def _layer_knn(x, k, hint=None):
@@ -428,11 +429,12 @@ def conv1x1(srcs, w) -> torch.Tensor:
 class _EdgeConvGather(torch.autograd.Function):
     """ops.py:45-58 after the algebraic split z_ij = u_i + v_idx(i,j): BN(train)+ReLU+max_k/mean_k.
     -> (max [P,F], mean [P,F], both [P,2F]); max and mean are the two column halves of `both`, which therefore IS
-    ops.py:58's concat(max, mean).  Backward sums the gradients of all three inside the gather kernels."""
+    ops.py:58's concat(max, mean).  Two gather passes forward (statistics, apply), ONE backward: the backward BN sums
+    follow from per-point quantities (csrc/edge.cu), and the gather pass sums the gradients of all three outputs."""
 
     @staticmethod
     def forward(ctx, uv, idx, beta, B, N, k, sink_key=None):
-        uv = nv.require_cuda(uv, "uv")
+        uv = nv.require_cuda(uv, "uv", uv.dtype if uv.dtype in (torch.float32, torch.bfloat16) else torch.float32)
         idx = nv.require_cuda(idx, "idx", torch.int32)
         beta = nv.require_cuda(beta, "beta")
         P, F2 = uv.shape
@@ -440,45 +442,49 @@ class _EdgeConvGather(torch.autograd.Function):
         dev = uv.device
         L = nv.lib()
         st = nv.stream_ptr(dev)
+        dt = nv.DT_BF16 if uv.dtype == torch.bfloat16 else nv.DT_F32
         ws = nv.workspace(dev, L.dgcnn_edgeconv_workspace_bytes(F), "stats")
-        zmax = torch.empty((P, F), dtype=torch.float32, device=dev)
-        cnt = torch.empty((P, F), dtype=torch.float32, device=dev)
         mean = torch.empty(F, dtype=torch.float32, device=dev)
         rstd = torch.empty(F, dtype=torch.float32, device=dev)
+        need_bwd = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
+        npos = torch.empty((P, F), dtype=torch.uint8, device=dev) if need_bwd else None
+        zmax = torch.empty((P, F), dtype=torch.float32, device=dev) if need_bwd else None
         ev = None
         if _ec_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        nv.check(L.dgcnn_edgeconv_fwd_stats(uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(),
-                                            cnt.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(),
-                                            ws.numel(), st), "edgeconv_fwd_stats")
+        nv.check(L.dgcnn_edgeconv_fwd_stats(uv.data_ptr(), dt, idx.data_ptr(), B, N, F, k, mean.data_ptr(),
+                                            rstd.data_ptr(), ws.data_ptr(), ws.numel(), st), "edgeconv_fwd_stats")
         both = torch.empty((P, 2 * F), dtype=torch.float32, device=dev)
         sk = _sinks
         lst = sk.targets.get(sink_key, []) if (sk is not None and sink_key is not None) else []
-        if len(lst) == 1 and tuple(lst[0][0].shape[:2]) == (2, P):
-            pl, col = lst[0]
-            nv.check(L.dgcnn_edgeconv_fwd_apply_packed_sink(uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(),
-                                                            mean.data_ptr(), rstd.data_ptr(), beta.data_ptr(),
-                                                            both.data_ptr(), pl.data_ptr() + 2 * col, pl.shape[2],
-                                                            pl.shape[1] * pl.shape[2], st), "edgeconv_fwd_apply")
+        sink = None
+        if len(lst) == 1 and tuple(lst[0][0].shape[1:2]) == (P,) and F % 4 == 0:
+            sink = lst[0]
+        sp, sld, spe = (0, 0, 0)
+        if sink is not None:
+            pl, col = sink
+            sp, sld = pl.data_ptr() + 2 * col, pl.shape[2]
+            spe = pl.shape[1] * pl.shape[2] if pl.shape[0] == 2 else 0
+        nv.check(L.dgcnn_edgeconv_fwd_apply(uv.data_ptr(), dt, idx.data_ptr(), B, N, F, k, mean.data_ptr(),
+                                            rstd.data_ptr(), beta.data_ptr(), both.data_ptr(), nv.ptr(zmax), nv.ptr(npos), sp,
+                                            sld, spe, st), "edgeconv_fwd_apply")
+        if sink is not None:
+            pl, col = sink
             sk.mark(both.data_ptr(), F, 2 * F, [(pl, col)])                       # the max view
             sk.mark(both.data_ptr() + 4 * F, F, 2 * F, [(pl, col + F)])           # the mean view
             sk.mark(both.data_ptr(), 2 * F, 2 * F, [(pl, col)])                   # the concat itself (conv1's input)
-        else:
-            nv.check(L.dgcnn_edgeconv_fwd_apply_packed(uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(),
-                                                       mean.data_ptr(), rstd.data_ptr(), beta.data_ptr(),
-                                                       both.data_ptr(), st), "edgeconv_fwd_apply")
         if ev is not None:
             ev[1].record()
             _ec_events.append((B, N, F, k, ev[0], ev[1]))
-        ctx.save_for_backward(uv, idx, beta, zmax, cnt, mean, rstd)
-        ctx.dims = (B, N, F, k)
+        ctx.save_for_backward(uv, idx, beta, mean, rstd, zmax, npos, both)
+        ctx.dims = (B, N, F, k, dt)
         return both[:, :F], both[:, F:], both
 
     @staticmethod
     def backward(ctx, gmax, gmean, gboth):
-        uv, idx, beta, zmax, cnt, mean, rstd = ctx.saved_tensors
-        B, N, F, k = ctx.dims
+        uv, idx, beta, mean, rstd, zmax, npos, both = ctx.saved_tensors
+        B, N, F, k, dt = ctx.dims
         dev = uv.device
         L = nv.lib()
         st = nv.stream_ptr(dev)
@@ -488,13 +494,22 @@ class _EdgeConvGather(torch.autograd.Function):
         ws = nv.workspace(dev, L.dgcnn_edgeconv_workspace_bytes(F), "stats")
         s1 = torch.empty(F, dtype=torch.float32, device=dev)
         s2 = torch.empty(F, dtype=torch.float32, device=dev)
-        common = (uv.data_ptr(), idx.data_ptr(), B, N, F, k, zmax.data_ptr(), cnt.data_ptr(), mean.data_ptr(),
-                  rstd.data_ptr(), beta.data_ptr(), nv.ptr(gmax), nv.ptr(gmean), nv.ptr(gboth), s1.data_ptr(),
-                  s2.data_ptr())
-        guv = torch.empty_like(uv)
-        nv.check(L.dgcnn_edgeconv_bwd_stats_packed_z(*common, guv.data_ptr(), ws.data_ptr(), ws.numel(), st),
-                 "edgeconv_bwd_stats")
-        nv.check(L.dgcnn_edgeconv_bwd_apply_packed_z(*common, guv.data_ptr(), 1, st), "edgeconv_bwd_apply")
+        guv = torch.empty((uv.shape[0], 2 * F), dtype=torch.float32, device=dev)
+        ev = None
+        if _ec_bwd_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        nv.check(L.dgcnn_edgeconv_bwd_stats(both.data_ptr(), npos.data_ptr(), beta.data_ptr(), nv.ptr(gmax),
+                                            nv.ptr(gmean), nv.ptr(gboth), B, N, F, k, s1.data_ptr(), s2.data_ptr(),
+                                            guv.data_ptr(), ws.data_ptr(), ws.numel(), st), "edgeconv_bwd_stats")
+        nv.check(L.dgcnn_edgeconv_bwd_apply(uv.data_ptr(), dt, idx.data_ptr(), B, N, F, k, mean.data_ptr(),
+                                            rstd.data_ptr(), beta.data_ptr(), zmax.data_ptr(), nv.ptr(gmax), nv.ptr(gmean),
+                                            nv.ptr(gboth), s1.data_ptr(), s2.data_ptr(), guv.data_ptr(), 1, st), "edgeconv_bwd_apply")
+        if ev is not None:
+            ev[1].record()
+            _ec_bwd_events.append((B, N, F, k, ev[0], ev[1]))
+        if uv.dtype != torch.float32:
+            guv = guv.to(uv.dtype)
         return guv, None, s1, None, None, None, None
 
 

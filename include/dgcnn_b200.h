@@ -112,67 +112,42 @@ int dgcnn_tc_gemm_grouped(const void* a_planes, const void* b_planes, int M, int
                           int n_groups, const int* starts, const int* widths, float* const* outs,
                           dgcnn_stream_t stream);
 
-/* ---- fused EdgeConv core: ops.py:45-57 (edges -> conv0 -> BN(train) -> ReLU -> max_k, mean_k)
+/* ---- fused EdgeConv core: ops.py:45-57 (edges -> conv0 -> BN(train) -> ReLU -> max_k, mean_k) ; ops.py:58 concat
  * Uses [x_i, x_j - x_i].[Wa;Wb] = x_i.(Wa-Wb) + x_j.Wb: the caller first forms
- * uv[P, 2F] = x[P,C] . [Wa-Wb | Wb] with dgcnn_gemm (P = B*N), so that z_ij = u_i + v_{idx(i,j)}
- * and the [B,N,k,2C] / [B,N,k,F] tensors are never materialised.
- *   fwd_stats : gather pass 1 -> zmax[P,F] = max_j z_ij, cnt[P,F] = #{j: z_ij == zmax},
- *               BN batch statistics mean[F], rstd[F] = 1/sqrt(var_biased + 1e-3) over all B*N*k
- *   fwd_apply : gather pass 2 -> out_max[P,F] = relu((zmax-mean)*rstd+beta),
- *               out_mean[P,F] = mean_j relu((z_ij-mean)*rstd+beta)
- *   bwd_stats : s1[F] = sum g_pre (= d beta), s2[F] = sum g_pre*zhat
- *   bwd_apply : g_uv[P,2F] (u half written, v half scatter-added; zeroed inside)             */
+ * uv[P, 2F] = x[P,C] . [Wa-Wb | Wb] (P = B*N), so that z_ij = u_i + v_{idx(i,j)} and the [B,N,k,2C] / [B,N,k,F]
+ * tensors are never materialised.  uv is fp32 (uv_dtype DGCNN_F32) or bf16 (DGCNN_BF16, the reduced-precision
+ * variant: half the gather bytes; all arithmetic and every other tensor stay fp32); 16-byte aligned.
+ * Three gather passes per layer (two forward, one backward):
+ *   fwd_stats : BN batch statistics of z over all B*N*k edges: mean[F], rstd[F] = 1/sqrt(var_biased + 1e-3)
+ *   fwd_apply : out_both[P,2F] = ( relu(bn(max_j z_ij)) | mean_j relu(bn(z_ij)) )  -- ops.py:58's concat in place;
+ *               zmax[P,F] = max_j z_ij and npos[P,F] (uint8) = #{j : relu input > 0}: what the backward passes need
+ *               (both NULL when no backward follows);
+ *               sink_planes (may be NULL): the same values also as bf16 hi / lo planes in columns [0,2F) of a
+ *               tensor-core operand (row pitch sink_ld elements, lo plane sink_plane_elems later; 0 = hi plane only):
+ *               the consumer's concat operand (model.py:83-85) is filled by the producer
+ *   bwd_stats : s1[F] = sum g_pre (= d beta), s2[F] = sum g_pre*zhat, from per-point quantities only (no gather): the
+ *               forward outputs, npos, and the incoming gradients, which may arrive as separate [P,F] tensors (g_max,
+ *               g_mean; either may be NULL) and/or as one packed [P,2F] tensor g_both (may be NULL); they are summed
+ *               on the fly.  g_uv_clear (may be NULL): the v half of that [P,2F] buffer is zeroed for bwd_apply.
+ *   bwd_apply : the only backward gather pass.  g_uv[P,2F]: u half written, v half scatter-added with 16-byte vector
+ *               atomics (tf.gather's gradient; zeroed here unless v_half_cleared != 0).  The max gradient is shared
+ *               equally among exact ties (tf.reduce_max's gradient).                                             */
+#define DGCNN_F32 0
+#define DGCNN_BF16 1
 size_t dgcnn_edgeconv_workspace_bytes(int F);
-int dgcnn_edgeconv_fwd_stats(const float* uv, const int32_t* idx, int B, int N, int F, int k, float* zmax,
-                             float* cnt, float* mean, float* rstd, void* ws, size_t ws_bytes,
+int dgcnn_edgeconv_fwd_stats(const void* uv, int uv_dtype, const int32_t* idx, int B, int N, int F, int k, float* mean,
+                             float* rstd, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+int dgcnn_edgeconv_fwd_apply(const void* uv, int uv_dtype, const int32_t* idx, int B, int N, int F, int k,
+                             const float* mean, const float* rstd, const float* beta, float* out_both, float* zmax,
+                             uint8_t* npos, void* sink_planes, int sink_ld, int64_t sink_plane_elems,
                              dgcnn_stream_t stream);
-int dgcnn_edgeconv_fwd_apply(const float* uv, const int32_t* idx, int B, int N, int F, int k,
-                             const float* zmax, const float* mean, const float* rstd, const float* beta,
-                             float* out_max, float* out_mean, dgcnn_stream_t stream);
-int dgcnn_edgeconv_bwd_stats(const float* uv, const int32_t* idx, int B, int N, int F, int k,
-                             const float* zmax, const float* cnt, const float* mean, const float* rstd,
-                             const float* beta, const float* g_max, const float* g_mean, float* s1,
-                             float* s2, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
-int dgcnn_edgeconv_bwd_apply(const float* uv, const int32_t* idx, int B, int N, int F, int k,
-                             const float* zmax, const float* cnt, const float* mean, const float* rstd,
-                             const float* beta, const float* g_max, const float* g_mean, const float* s1,
-                             const float* s2, float* g_uv, dgcnn_stream_t stream);
-
-/* Packed variants for the layer as the model uses it (ops.py:58: conv1 consumes concat(max, mean)):
- *   fwd_apply_packed : out_both [P,2F] = (out_max | out_mean), i.e. the concat is produced in place
- *   bwd_*_packed     : the gradients of max and mean may arrive as separate [P,F] tensors (g_max, g_mean; either may
- *                      be NULL) and/or as one packed [P,2F] tensor g_both (may be NULL); they are summed on the fly */
-int dgcnn_edgeconv_fwd_apply_packed(const float* uv, const int32_t* idx, int B, int N, int F, int k,
-                                    const float* zmax, const float* mean, const float* rstd, const float* beta,
-                                    float* out_both, dgcnn_stream_t stream);
-int dgcnn_edgeconv_bwd_stats_packed(const float* uv, const int32_t* idx, int B, int N, int F, int k,
-                                    const float* zmax, const float* cnt, const float* mean, const float* rstd,
-                                    const float* beta, const float* g_max, const float* g_mean, const float* g_both,
-                                    float* s1, float* s2, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
-int dgcnn_edgeconv_bwd_apply_packed(const float* uv, const int32_t* idx, int B, int N, int F, int k,
-                                    const float* zmax, const float* cnt, const float* mean, const float* rstd,
-                                    const float* beta, const float* g_max, const float* g_mean, const float* g_both,
-                                    const float* s1, const float* s2, float* g_uv, dgcnn_stream_t stream);
-
-/* ..._sink: the forward apply pass additionally writes (max | mean) as bf16 hi / lo planes into columns [0,2F) of a
- * tensor-core operand starting at sink_planes (row pitch sink_ld elements, second plane sink_plane_elems later):
- * the consumer's concat operand (model.py:83-85) is filled by the producer, no split pass re-reads the tensor.      */
-int dgcnn_edgeconv_fwd_apply_packed_sink(const float* uv, const int32_t* idx, int B, int N, int F, int k,
-                                         const float* zmax, const float* mean, const float* rstd, const float* beta,
-                                         float* out_both, void* sink_planes, int sink_ld, int64_t sink_plane_elems,
-                                         dgcnn_stream_t stream);
-/* ..._z: the statistics pass also clears the v half of g_uv (g_uv_clear, may be NULL) so that the apply pass, told so by
- * v_half_cleared != 0, can scatter-add into it without a separate zeroing kernel.                               */
-int dgcnn_edgeconv_bwd_stats_packed_z(const float* uv, const int32_t* idx, int B, int N, int F, int k,
-                                      const float* zmax, const float* cnt, const float* mean, const float* rstd,
-                                      const float* beta, const float* g_max, const float* g_mean, const float* g_both,
-                                      float* s1, float* s2, float* g_uv_clear, void* ws, size_t ws_bytes,
-                                      dgcnn_stream_t stream);
-int dgcnn_edgeconv_bwd_apply_packed_z(const float* uv, const int32_t* idx, int B, int N, int F, int k,
-                                      const float* zmax, const float* cnt, const float* mean, const float* rstd,
-                                      const float* beta, const float* g_max, const float* g_mean, const float* g_both,
-                                      const float* s1, const float* s2, float* g_uv, int v_half_cleared,
-                                      dgcnn_stream_t stream);
+int dgcnn_edgeconv_bwd_stats(const float* out_both, const uint8_t* npos, const float* beta, const float* g_max,
+                             const float* g_mean, const float* g_both, int B, int N, int F, int k, float* s1, float* s2,
+                             float* g_uv_clear, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+int dgcnn_edgeconv_bwd_apply(const void* uv, int uv_dtype, const int32_t* idx, int B, int N, int F, int k,
+                             const float* mean, const float* rstd, const float* beta, const float* zmax,
+                             const float* g_max, const float* g_mean, const float* g_both, const float* s1,
+                             const float* s2, float* g_uv, int v_half_cleared, dgcnn_stream_t stream);
 
 /* ---- train-mode BatchNorm (+residual) (+ReLU) on a [rows,C] per-point tensor ---------------
  * slim.batch_norm defaults (is_training=True, center=True, scale=False, eps=1e-3) after a 1x1 conv:

@@ -61,7 +61,9 @@ def test_invalid_arguments_return_codes_not_aborts(dg):
     assert lib.dgcnn_knn(p, p, 1, 8, 3, 2, p, 16, None) == _native.ERR_WORKSPACE
     assert lib.dgcnn_topk_rows(p, p, 4, 8, 0, None) == _native.ERR_INVALID
     assert lib.dgcnn_gemm(p, p, p, 0, 4, 4, 0, 0, None, 0, None) == _native.ERR_INVALID
-    assert lib.dgcnn_edgeconv_fwd_stats(p, p, 1, 8, 64, 9, p, p, p, p, p, 1 << 20, None) == _native.ERR_INVALID
+    assert lib.dgcnn_edgeconv_fwd_stats(p, 0, p, 1, 8, 64, 9, p, p, p, 1 << 20, None) == _native.ERR_INVALID      # k > N
+    assert lib.dgcnn_edgeconv_fwd_stats(p, 7, p, 1, 8, 64, 4, p, p, p, 1 << 20, None) == _native.ERR_INVALID      # dtype
+    assert lib.dgcnn_edgeconv_fwd_stats(p, 0, p, 1, 8, 64, 4, p, p, p, 8, None) == _native.ERR_WORKSPACE
     assert lib.dgcnn_bn_act_fwd(p, 0, 4, p, None, 1, p, p, p, p, 1 << 20, None) == _native.ERR_INVALID
     assert lib.dgcnn_adam_tf_step(p, p, p, p, 0, 0.1, 0.9, 0.999, 1e-8, 1.0, None) == _native.ERR_INVALID
     with pytest.raises(ValueError):
