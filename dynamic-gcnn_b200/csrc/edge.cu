@@ -22,9 +22,14 @@ namespace dgcnn {
 
 constexpr int EC_THREADS = 256;          // 8 warps
 constexpr int EC_WARPS = EC_THREADS / 32;
-constexpr int EC_MIN_BLOCKS = 3;         // register cap of the gather kernels: 3 x 8 warps per SM
-constexpr int EC_MIN_BLOCKS_BWD = 2;     // the backward pass keeps more state (no spills at 128 registers)
-constexpr int EC_GROUP = 5;              // gathered rows in flight per half-warp
+#ifndef EC_MIN_BLOCKS_V
+#define EC_MIN_BLOCKS_V 3
+#define EC_MIN_BLOCKS_BWD_V 3
+#define EC_GROUP_V 5
+#endif
+constexpr int EC_MIN_BLOCKS = EC_MIN_BLOCKS_V;         // register cap of the gather kernels: 3 x 8 warps per SM
+constexpr int EC_MIN_BLOCKS_BWD = EC_MIN_BLOCKS_BWD_V;     // the backward pass keeps more state (no spills at 128 registers)
+constexpr int EC_GROUP = EC_GROUP_V;              // gathered rows in flight per half-warp
 
 // ------------------------------------------------------------------------------------------ edges()
 __global__ void edge_feature_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx,

@@ -13,7 +13,7 @@ from typing import Dict, Tuple
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libdgcnn_b200.so"))
+LIB_PATH = os.environ.get("DGCNN_LIB_PATH") or os.path.normpath(os.path.join(_HERE, "..", "lib", "libdgcnn_b200.so"))
 
 _lib = None
 
