@@ -158,5 +158,11 @@ def workspace(dev: torch.device, nbytes: int, tag: str) -> torch.Tensor:
     return buf
 
 
+def workspaces_snapshot():
+    """References to every scratch buffer currently in the cache (see trainval._tower_step: a captured CUDA graph must
+    keep the buffers it was recorded with alive)."""
+    return list(_ws_cache.values())
+
+
 def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()

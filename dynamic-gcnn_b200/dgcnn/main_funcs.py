@@ -80,6 +80,11 @@ def prepare(flags):
         sys.exit(1)
     _maybe_init_distributed()
 
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not flags.TRAIN and getattr(flags, "OUTPUT_FILE", ""):
+        # every rank would write the same file, each with only its own towers' predictions
+        sys.stderr.write("inference with --output_file runs in ONE process (towers then run back to back on one GPU)\n")
+        raise NotImplementedError
+
     handlers.data_io = dgcnn.io_factory(flags)
     handlers.data_io.initialize()
     handlers.data_io.next()
@@ -120,7 +125,9 @@ def _slices(flags, arr, current_idx):
 
 
 def _prune_checkpoints(prefix, keep):
-    files = sorted(glob.glob(prefix + "-*"), key=lambda p: iteration_from_filename(p))
+    import re
+    pat = re.compile(re.escape(prefix) + r"-\d+$")           # only PREFIX-<iteration>: not prefix-100.bak, prefix-final
+    files = sorted((f for f in glob.glob(prefix + "-*") if pat.match(f)), key=iteration_from_filename)
     for p in files[:-int(keep)] if keep and len(files) > int(keep) else []:
         os.remove(p)
 
@@ -162,7 +169,12 @@ def train_loop(flags, handlers):
         tsum_train += tspent_train
         tspent_summary = 0.0
 
-        loss, accuracy = float(np.mean(loss_v)), float(np.mean(accuracy_v))
+        if trainer._world > 1:
+            # the tower mean the reference logs (trainval.py:59-60): loss / accuracy rode through the all-reduce
+            loss = float(trainer.last_loss) / len(loss_v)
+            accuracy = float(trainer.last_accuracy) / len(loss_v)
+        else:
+            loss, accuracy = float(np.mean(loss_v)), float(np.mean(accuracy_v))
         epoch = handlers.iteration * float(flags.BATCH_SIZE) / handlers.data_io.num_entries()
         tspent_save = 0.0
         if checkpt_step and trainer._rank == 0:
@@ -228,6 +240,7 @@ def inference_loop(flags, handlers):
         tsum_inference += tspent_inference
 
         if flags.OUTPUT_FILE:
+            # softmax_vv holds, per micro-step, one array per tower this process ran (all of them: single process)
             idx_ctr = 0
             for softmax_v in softmax_vv:
                 for softmax in softmax_v:

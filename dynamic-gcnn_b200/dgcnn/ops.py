@@ -67,6 +67,7 @@ CONV1_WIDTH = 64  # ops.py:63
 
 # test hooks (never set by the product): _knn_trace collects each layer's kNN indices; _knn_forced supplies them
 _knn_trace = None
+_knn_input_trace = None   # collects the tensor each layer's kNN was computed on (the GPU's own activations)
 _knn_forced = None
 # bench.py hooks: when a list, k_nn() / the head's forward GEMM bracket their C-ABI call with CUDA events on the
 # launching stream (eager mode only: a captured graph cannot carry timing events)
@@ -83,6 +84,8 @@ def _layer_knn(x, k, hint=None):
         idx = k_nn(x, k, hint=hint)
     if _knn_trace is not None:
         _knn_trace.append(idx)
+    if _knn_input_trace is not None:
+        _knn_input_trace.append(x.detach())
     return idx
 
 

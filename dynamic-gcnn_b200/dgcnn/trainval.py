@@ -49,6 +49,12 @@ class trainval(object):
         # towers this rank executes (main_funcs.py:145-152 cuts one slice per entry of flags.GPUS)
         self._towers = tower_assignment(len(f.GPUS), self._world, self._rank)
         seed = int(getattr(f, "SEED", 0))
+        if self._world > 1:
+            # flags.py resolves SEED=-1 to time() separately in every process: all ranks take rank 0's value
+            t = torch.tensor([seed], dtype=torch.int64, device=self._device)
+            dist.broadcast(t, src=0)
+            seed = int(t.item())
+            f.SEED = seed
         self._store = VariableStore(device=self._device, seed=seed if seed >= 0 else 0)
         old = set_default_store(self._store)
         try:
@@ -62,8 +68,23 @@ class trainval(object):
             self._adam_m = torch.zeros(n, dtype=torch.float32, device=self._device)
             self._adam_v = torch.zeros(n, dtype=torch.float32, device=self._device)
             self._adam_t = 0
+        self._sync_replicas()
         self.last_loss = None
         self.last_accuracy = None
+
+    def _sync_replicas(self):
+        """Every rank starts from rank 0's variables (and optimizer state): replicas that differ would apply the averaged
+        gradient to diverging weights.  Also called after restore()."""
+        if self._world <= 1:
+            return
+        st = self._store
+        if getattr(st, "flat_param", None) is not None:
+            dist.broadcast(st.flat_param, src=0)
+            dist.broadcast(self._adam_m, src=0)
+            dist.broadcast(self._adam_v, src=0)
+        else:
+            for name in sorted(st.vars):
+                dist.broadcast(st.vars[name].data, src=0)
 
     @property
     def variables(self) -> VariableStore:
@@ -172,7 +193,11 @@ class trainval(object):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 acc, loss = self._tower_step_eager(ent["pts"], ent["lab"], ent["wgt"], G)
-            ent.update(graph=graph, acc=acc, loss=loss, launches=nv.launch_count() - n0)
+            # the captured kernels have the current scratch buffers' addresses baked in: the entry keeps them alive, so
+            # that a later, larger request (another N, an eager inference call) that replaces a buffer in the cache
+            # cannot hand this graph's scratch to the allocator while the graph can still be replayed
+            ent.update(graph=graph, acc=acc, loss=loss, launches=nv.launch_count() - n0,
+                       workspaces=nv.workspaces_snapshot())
             self._graphs[key] = ent
             gmax = int(os.environ.get("DGCNN_CUDA_GRAPH_MAX", self.GRAPH_MAX))
             while len(self._graphs) > max(gmax, 1):
@@ -257,3 +282,4 @@ class trainval(object):
             self._adam_m.copy_(blob["adam_m"])
             self._adam_v.copy_(blob["adam_v"])
             self._adam_t = int(blob["adam_t"])
+        self._sync_replicas()
