@@ -1,18 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- points/sec, forward+backward+Adam, of the full DGCNN segmentation model on synthetic clouds.
+"""bench.py -- points/sec, forward+backward+Adam, of the DGCNN segmentation model on synthetic clouds.
 
-Workload (BASELINE.json configs[1]): 4 EdgeConv layers + FC head, N=2048, k=20, C=3, 24 clouds per GPU, fp32.
-With --gpus N (launched under torchrun) every rank keeps 24 clouds (weak scaling: global batch 24*N, which at
-N=8 is configs[3]) and the step ends with ONE NCCL all-reduce of the flat gradient buffer.
+--config 1 (default; BASELINE.json configs[1], the configuration the metric is quoted on): 4 EdgeConv layers + FC head,
+            N=2048, k=20, C=3, 24 clouds per GPU, fp32.  With --gpus N (under torchrun) every rank keeps 24 clouds (weak
+            scaling: at N=8 this is configs[3], global batch 192) and the step ends with ONE NCCL all-reduce.
+--config 2 (configs[2]): residual-dgcnn, 6 layers, N=4096, k=40, 24 clouds, bf16 (operating point of the reference's
+            scripts/lsf/train_dgcnn.sh:4,8,9,28); --dtype f32 runs the same shape on the fp32 path.
+--config 4 (configs[4]): N=16384, k=20, 8 clouds per GPU, 4 layers, fp32 (per-cloud distance matrix 1.07 GB >> L2);
+            --gpus N gives its weak-scaling sweep.
 
-A "step" = zero_gradients + accum_gradient (fwd+bwd of the rank's 24 clouds) + apply_gradient through the
-reference-facing trainer API (dgcnn.trainval); the trainer replays the micro-step from a CUDA graph.  Two timings:
+A "step" = zero_gradients + accum_gradient (fwd+bwd of the rank's clouds) + apply_gradient through the reference-facing
+trainer API (dgcnn.trainval); the trainer replays the micro-step from a CUDA graph.  Two timings:
   value : inputs already resident in HBM, no host read inside the loop; CUDA events, max over ranks.
-  e2e   : the same call with pinned HOST inputs (H2D copy every step) and a device->host read of the loss
-          every step.
-roofline    : the largest single launch of the step, tc_gemm_wide_kernel on the FC0 layer (tensor bound), timed live
-              with CUDA events on the launching stream in three extra eagerly-issued steps (a captured graph cannot
-              carry timing events); the fused k_nn and the EdgeConv gather passes are reported beside it.
+  e2e   : the same call with pinned HOST inputs (H2D copy every step) and a device->host read of the loss every step.
+roofline*   : per-kernel entries timed live with CUDA events in extra eagerly-issued steps; each such step starts with a
+              device-side sleep so that the host is ahead of the device and no launch gap falls between the events.
+              `roofline` = the largest single launch (FC0 forward GEMM, tensor bound); `roofline_knn`,
+              `roofline_edgeconv_fwd`, `roofline_edgeconv_bwd` = the hot path north_star names (HBM / L2 bound).
 cpu_baseline: the oracle (reference-equivalent CPU restatement; TF1 cannot be installed) on a bounded sample.
 --impl reference : that CPU arm alone, with all host threads.
 """
@@ -32,17 +36,25 @@ for _p in (ROOT, PKG):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-B_PER_GPU, NPTS, KNN, CH, LAYERS, FILT, FCF, NCLS = 24, 2048, 20, 3, 4, 64, [512, 256], 2
 METRIC = "points/sec fwd+bwd, B=24 N=2048 k=20, at 1/2/4/8 B200; EdgeConv HBM GB/s"
-CPU_SAMPLE_B = 4  # clouds per CPU-baseline step (BN statistics are per micro-batch, cost is linear in clouds)
+CH, FILT, FCF, NCLS = 3, 64, [512, 256], 2
+CONFIGS = {
+    1: dict(tag="configs[1]", model="dgcnn", B=24, N=2048, k=20, L=4, dtype="f32", cpu_sample=4,
+            what="full DGCNN seg, 4 EdgeConv + FC(512,256) head"),
+    2: dict(tag="configs[2]", model="residual-dgcnn", B=24, N=4096, k=40, L=6, dtype="bf16", cpu_sample=1,
+            what="residual-EdgeConv variant, 6 EdgeConv (operating point of scripts/lsf/train_dgcnn.sh) + FC(512,256) head"),
+    4: dict(tag="configs[4]", model="dgcnn", B=8, N=16384, k=20, L=4, dtype="f32", cpu_sample=1,
+            what="large clouds (per-cloud distance matrix 1.07 GB >> L2), 4 EdgeConv + FC(512,256) head"),
+}
 
 
-def make_flags(n_gpus):
+def make_flags(n_gpus, cfg, dtype=None):
     from types import SimpleNamespace
-    return SimpleNamespace(NUM_CLASS=NCLS, MODEL_NAME="dgcnn", TRAIN=True, KVALUE=KNN, DEBUG=False,
-                           EDGE_CONV_LAYERS=LAYERS, EDGE_CONV_FILTERS=FILT, FC_LAYERS=len(FCF), FC_FILTERS=list(FCF),
-                           LEARNING_RATE=1e-3, GPUS=list(range(n_gpus)), MINIBATCH_SIZE=B_PER_GPU,
-                           NUM_CHANNEL=CH, WEIGHT_KEY="", SEED=0, BATCH_SIZE=B_PER_GPU * n_gpus, NUM_POINT=NPTS)
+    return SimpleNamespace(NUM_CLASS=NCLS, MODEL_NAME=cfg["model"], TRAIN=True, KVALUE=cfg["k"], DEBUG=False,
+                           EDGE_CONV_LAYERS=cfg["L"], EDGE_CONV_FILTERS=FILT, FC_LAYERS=len(FCF), FC_FILTERS=list(FCF),
+                           LEARNING_RATE=1e-3, GPUS=list(range(n_gpus)), MINIBATCH_SIZE=cfg["B"], NUM_CHANNEL=CH,
+                           WEIGHT_KEY="", SEED=0, BATCH_SIZE=cfg["B"] * n_gpus, NUM_POINT=cfg["N"],
+                           DTYPE=dtype or cfg["dtype"])
 
 
 def peaks():
@@ -84,7 +96,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def summary(self):
         s = sorted(self.samples)
@@ -92,73 +104,157 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def cpu_baseline_run(steps, warmup):
+def cpu_baseline_run(steps, warmup, cfg):
     """Reference-equivalent CPU restatement (oracle) timed on the host cores: TF-literal graph (materialised
-    [B,N,N] distances, top_k, gathered edge tensor, 1x1 convs as matmuls, train-mode BN, autograd backward)."""
+    [B,N,N] distances, top_k, gathered edge tensor, 1x1 convs as matmuls, train-mode BN, autograd backward) plus the
+    TF-form Adam update, on a bounded sample of the workload's clouds."""
     from oracle import dgcnn_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    fl = O.make_flags(EDGE_CONV_LAYERS=LAYERS, EDGE_CONV_FILTERS=FILT, KVALUE=KNN, FC_FILTERS=list(FCF), NUM_CLASS=NCLS,
-                      TRAIN=True)
+    fl = O.make_flags(EDGE_CONV_LAYERS=cfg["L"], EDGE_CONV_FILTERS=FILT, KVALUE=cfg["k"], FC_FILTERS=list(FCF),
+                      NUM_CLASS=NCLS, TRAIN=True, MODEL_NAME=cfg["model"])
     P = O.init_params(fl, CH, seed=0)
+    m = {n: torch.zeros_like(t) for n, t in P.items()}
+    v = {n: torch.zeros_like(t) for n, t in P.items()}
+    sb, N = cfg["cpu_sample"], cfg["N"]
     g = torch.Generator().manual_seed(1234)
-    x = torch.rand((CPU_SAMPLE_B, NPTS, CH), generator=g)
-    y = torch.randint(0, NCLS, (CPU_SAMPLE_B, NPTS), generator=g)
+    x = torch.rand((sb, N, CH), generator=g)
+    y = torch.randint(0, NCLS, (sb, N), generator=g)
+    t_step = [0]
+
+    def one():
+        _, _, grads = O.train_step_reference(x, y, fl, P)
+        t_step[0] += 1
+        with torch.no_grad():
+            for n, t in P.items():
+                O.adam_tf_step(t, grads[n], m[n], v[n], t_step[0], lr=1e-3)
+
     for _ in range(warmup):
-        O.train_step_reference(x, y, fl, P)
+        one()
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.train_step_reference(x, y, fl, P)
+        one()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return {"value": CPU_SAMPLE_B * NPTS / dt, "unit": "points/s", "cores": cores, "kind": "port",
-            "sample": "%d of %d clouds per step (N=%d k=%d L=%d, fwd+bwd, no optimizer), %d steps after %d warm-up; "
-                      "torch-CPU restatement of the TF1 graph (TF1 not installable)" % (CPU_SAMPLE_B, B_PER_GPU, NPTS,
-                                                                                       KNN, LAYERS, steps, warmup),
+    return {"value": sb * N / dt, "unit": "points/s", "cores": cores, "kind": "port",
+            "sample": "%d of %d clouds per step (%s, N=%d k=%d L=%d, fp32, fwd+bwd+Adam), %d steps after %d warm-up; "
+                      "torch-CPU restatement of the TF1 graph (TF1 not installable); BN statistics are per micro-batch and "
+                      "the cost is linear in clouds" % (sb, cfg["B"], cfg["model"], N, cfg["k"], cfg["L"], steps, warmup),
             "ms_per_step": dt * 1e3}
 
 
-def run_reference(args):
+def workload_config(n, cfg, dtype):
+    return {"workload": "%s: %s, N=%d k=%d C=%d, %d clouds per GPU, %s, fwd+bwd+Adam" % (
+                cfg["tag"], cfg["what"], cfg["N"], cfg["k"], CH, cfg["B"], dtype) +
+            ("" if n == 1 else "; %d GPUs = global batch %d, one NCCL grad all-reduce" % (n, n * cfg["B"])),
+            "clouds_per_gpu": cfg["B"], "global_batch": cfg["B"] * n, "points": cfg["N"], "k": cfg["k"], "channels": CH,
+            "edge_conv_layers": cfg["L"], "model_name": cfg["model"], "parallelism": "dp%d" % n}
+
+
+def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline_run(args.steps, args.warmup)
+    cb = cpu_baseline_run(args.steps, args.warmup, cfg)
+    conf = workload_config(args.gpus, cfg, "f32")
+    conf["reference_run"] = {"what": "CPU oracle port on rank 0's host cores only (no GPU, no collective)",
+                             "clouds_per_step": cfg["cpu_sample"], "optimizer": "TF-form Adam", "launch": "torch CPU eager",
+                             "cores": cb["cores"]}
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "points/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus), "cpu_baseline": cb,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": conf,
+            "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n):
-    return {"workload": "configs[1]: full DGCNN seg, 4 EdgeConv + FC(512,256) head, N=2048 k=20 C=3, 24 clouds per GPU, "
-                        "fwd+bwd+Adam" + ("" if n == 1 else "; %d GPUs = global batch %d, one NCCL grad all-reduce" %
-                                          (n, n * B_PER_GPU)),
-            "clouds_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * n, "points": NPTS, "k": KNN, "channels": CH,
-            "edge_conv_layers": LAYERS, "parallelism": "dp%d" % n,
-            "l2": "no explicit flush: one step streams >2 GB of activations per GPU, far beyond the 126 MB L2",
-            "launch": "micro-step (fwd+bwd) replayed from a CUDA graph captured by dgcnn.trainval after 2 eager runs"}
+def _mean_ms(pairs):
+    ts = [a.elapsed_time(b) for a, b in pairs]
+    return float(np.mean(ts)) if ts else None
 
 
-def edgeconv_entry(eev):
-    """EdgeConv forward after the uv GEMM (ops.py:45-58: gather, conv0 as u_i + v_j, BN, ReLU, max_k / mean_k, concat) =
-    ec_fwd_stats_kernel + finalize + ec_fwd_apply_kernel, on the 64-channel layers."""
-    ts = [a.elapsed_time(b) for (_, _, f, _, a, b) in eev]
-    if not ts:
-        return None
-    t = float(np.mean(ts)) * 1e-3
-    P_, E_ = B_PER_GPU * NPTS, B_PER_GPU * NPTS * KNN
-    hbm = (P_ * 128 + E_ + 3 * P_ * 64 + P_ * 128) * 4.0        # uv, idx, zmax/cnt, (max | mean): compulsory bytes
-    l2 = 2.0 * E_ * 64 * 4                                       # two gather passes over the L2-resident v rows
-    ref = (E_ * 128 * 4.0) * 2 + (E_ * 64 * 4.0) * 5             # the reference's edge tensor w+r, conv0 out w + BN r/w + max/mean r
-    return {"ms_per_call": t * 1e3, "calls_timed": len(ts), "bound": "L2 gather (E*F*4 bytes per pass) + fp32 ALU",
-            "compulsory_hbm_gbs": hbm / t / 1e9, "l2_gather_gbs": l2 / t / 1e9,
-            "effective_unfused_hbm_gbs": ref / t / 1e9,
-            "note": "effective = bytes the reference's op-by-op graph moves for the same layer (edge tensor, conv0 output, "
-                    "BN, max/mean passes) divided by this time; none of those tensors exists here"}
+def roofline_entries(cfg, dtype, pk, pk_kind, gev, kev, eev, bev, ms_step):
+    """First-class roofline objects (SURVEY.md section 8d figures scaled to the configuration)."""
+    B, N, k, F = cfg["B"], cfg["N"], cfg["k"], FILT
+    P_, E_ = B * N, B * N * k
+    hbm = pk["hbm_gbs"]
+    tpk = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    out = {}
+    # ---- the largest single launch: FC0 forward GEMM
+    fc0 = [(a, b) for (m, n, kk, a, b) in gev if n == FCF[0] and m == P_]
+    kfc0 = max([kk for (m, n, kk, a, b) in gev if n == FCF[0] and m == P_], default=0)
+    if fc0:
+        t_ms = _mean_ms(fc0)
+        mmas = 1 if dtype == "bf16" else 3
+        flops = 2.0 * P_ * FCF[0] * kfc0
+        ach = flops / (t_ms * 1e-3) / 1e12
+        esz = 2 * (1 if dtype == "bf16" else 2)
+        out["roofline"] = {
+            "kernel": "tc_gemm_wide_kernel on FC0 forward: [%d x %d] . [%d x %d], persistent 128x256 tiles, TMA -> smem ring "
+                      "-> tcgen05.mma (%s, fp32 accumulate in TMEM, double-buffered) -> epilogue with BN column statistics"
+                      % (P_, kfc0, kfc0, FCF[0], "1 bf16 MMA per k-slice" if mmas == 1 else
+                         "3 bf16 MMAs per k-slice: hi.hi + hi.lo + lo.hi"),
+            "bound": "tensor", "achieved": ach, "peak": tpk, "unit": "TFLOP/s", "frac": ach / tpk,
+            "traffic": None if (cfg["tag"] != "configs[1]" or dtype != "f32") else 438.2e6,
+            "traffic_source": "ncu --set full of this launch at configs[1] fp32 (profiles/): dram read 362.8 MB + write "
+                              "75.4 MB; algorithmic: operand planes %.0f MB + fp32 output %.0f MB"
+                              % (P_ * kfc0 * esz / 1e6, P_ * FCF[0] * 4 / 1e6),
+            "peak_source": pk_kind + " bf16 sustained (kernel timed inside the step)", "ms_per_launch": t_ms,
+            "launches_timed": len(fc0), "algorithmic_flops": flops, "executed_tensor_flops": mmas * flops,
+            "executed_frac_of_peak": mmas * ach / tpk, "share_of_step": t_ms / ms_step,
+            "note": "achieved counts ONE multiply-add per product (the fp32 GEMM the reference runs)"}
+    # ---- k_nn (ops.py:8-19), feature-space layers
+    k64 = [(a, b) for (_, _, c, _, a, b) in kev if c == 64]
+    k3 = [(a, b) for (_, _, c, _, a, b) in kev if c == CH]
+    if k64:
+        t = _mean_ms(k64) * 1e-3
+        unfused = (P_ * 64 * 4 + B * N * N * 4.0) + (B * N * N * 4.0 + E_ * 4)          # K1 + K2 algorithmic bytes
+        tflops = 2.0 * B * N * N * 64 / t / 1e12
+        tmem_floor = 2.0 * B * N * N * 4 / (64.0 * 148 * 1.9e9)                         # 2 sweeps at 64 B/clk/SM
+        out["roofline_knn"] = {
+            "kernel": "dgcnn_knn on [%d,%d,64]: range + prep + knn_tc_filter_kernel (fp16 tcgen05 distances, two sweeps over "
+                      "TMEM accumulators) + exact fp32 refine; the [B,N,N] matrix never leaves the SM" % (B, N),
+            "bound": "hbm", "achieved": unfused / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": unfused / t / 1e9 / hbm,
+            "traffic": None, "ms_per_call": t * 1e3, "calls_timed": len(k64), "algorithmic_bytes": unfused,
+            "compulsory_bytes": P_ * 64 * 4.0 + E_ * 4.0,
+            "note": "EFFECTIVE rate: bytes of the unfused pairwise_distance + top_k pair (SURVEY 8d) over the fused call's "
+                    "time; the fused kernel's real bound is the TMEM read port",
+            "tensor_tflops": tflops, "tensor_frac_of_peak": tflops / tpk, "tmem_read_floor_ms": tmem_floor * 1e3,
+            "frac_of_tmem_floor": tmem_floor / t, "share_of_step": (len(k64) // max(len(k3), 1)) * t * 1e3 / ms_step,
+            "xyz_layer_ms_per_call": _mean_ms(k3)}
+    # ---- EdgeConv forward gather passes (ops.py:45-58) on the 64-channel layers
+    esz = 2 if dtype == "bf16" else 4
+    if eev:
+        t = _mean_ms([(a, b) for (_, _, _, _, a, b) in eev]) * 1e-3
+        comp = P_ * 2 * F * esz + E_ * 4.0 + P_ * 2 * F * 4.0 + P_ * F * 4.0 + P_ * F      # uv, idx, (max|mean), zmax, npos
+        l2 = 2.0 * E_ * F * esz
+        ref = (E_ * 128 * 4.0) * 2 + (E_ * 64 * 4.0) * 5
+        out["roofline_edgeconv_fwd"] = {
+            "kernel": "ec_fwd_stats_kernel + ec_fwd_apply_kernel: gather -> conv0 (z = u_i + v_j) -> BN(train) -> ReLU -> "
+                      "max_k / mean_k -> concat, two gather passes over the L2-resident uv table",
+            "bound": "hbm", "achieved": comp / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": comp / t / 1e9 / hbm,
+            "traffic": None, "ms_per_call": t * 1e3, "calls_timed": len(eev), "algorithmic_bytes": comp,
+            "l2_gather_bytes": l2, "l2_gather_gbs": l2 / t / 1e9, "effective_unfused_hbm_gbs": ref / t / 1e9,
+            "share_of_step": cfg["L"] * t * 1e3 / ms_step,
+            "note": "compulsory HBM bytes over time; the passes are bound by the L2 gather rate of 256-byte rows (see "
+                    "l2_gather_gbs; measured ceiling of this access pattern ~7.5 TB/s, profiles/); effective = what the "
+                    "reference's op-by-op graph moves for the same layer"}
+    if bev:
+        t = _mean_ms([(a, b) for (_, _, _, _, a, b) in bev]) * 1e-3
+        comp = (P_ * 2 * F * esz + E_ * 4.0 + 2 * P_ * 2 * F * 4.0 + P_ * 2 * F * 4.0 + P_ * F * 4.0 + P_ * F +
+                P_ * 2 * F * 4.0)                    # uv, idx, g_both + (g_max, g_mean), both, zmax, npos, g_uv
+        out["roofline_edgeconv_bwd"] = {
+            "kernel": "ec_bwd_stats_kernel (no gather) + ec_bwd_apply_kernel: one gather / scatter pass, 16-byte vector "
+                      "atomics into g_v",
+            "bound": "hbm", "achieved": comp / t / 1e9, "peak": hbm, "unit": "GB/s", "frac": comp / t / 1e9 / hbm,
+            "traffic": None, "ms_per_call": t * 1e3, "calls_timed": len(bev), "algorithmic_bytes": comp,
+            "l2_atomic_bytes": E_ * F * 4.0, "l2_atomic_gbs": E_ * F * 4.0 / t / 1e9,
+            "share_of_step": cfg["L"] * t * 1e3 / ms_step,
+            "note": "bound by the L2 atomic units: E*F*4 bytes of fp32 adds at ~5 TB/s (profiles/scripts/scatter_bench.cu: "
+                    "50 us for this shape with nothing else running) plus the gather"}
+    return out
 
 
-def run_ours(args):
+def run_ours(args, cfg):
     import torch.distributed as dist
     import dgcnn
     from dgcnn import _native, ops
@@ -173,7 +269,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, "--gpus %d but WORLD_SIZE=%d (launch with torchrun)" % (args.gpus, world)
 
-    fl = make_flags(world)
+    dtype = args.dtype or cfg["dtype"]
+    B, N = cfg["B"], cfg["N"]
+    fl = make_flags(world, cfg, dtype)
     tr = dgcnn.trainval(fl)
     tr.initialize()
     tower = tr._towers[0]
@@ -181,8 +279,8 @@ def run_ours(args):
     # synthetic inputs: a small ring of distinct batches, pinned on the host and mirrored on the device
     g = torch.Generator().manual_seed(1234 + rank)
     ring = 4
-    h_pts = [torch.rand((B_PER_GPU, NPTS, CH), generator=g).pin_memory() for _ in range(ring)]
-    h_lab = [torch.randint(0, NCLS, (B_PER_GPU, NPTS), generator=g, dtype=torch.int64).pin_memory() for _ in range(ring)]
+    h_pts = [torch.rand((B, N, CH), generator=g).pin_memory() for _ in range(ring)]
+    h_lab = [torch.randint(0, NCLS, (B, N), generator=g, dtype=torch.int64).pin_memory() for _ in range(ring)]
     d_pts = [t.to(dev) for t in h_pts]
     d_lab = [t.to(dev) for t in h_lab]
 
@@ -206,16 +304,11 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         n0 = _native.launch_count()
-        prof = (not host) and os.environ.get("DGCNN_PROFILE") == "1"   # ncu --profile-from-start off
-        if prof:
-            torch.cuda.profiler.start()
         e0.record()
         for i in range(steps):
             step(i, host)
         e1.record()
         barrier()
-        if prof:
-            torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         t = torch.tensor([ms], device=dev)
         if world > 1:
@@ -235,74 +328,44 @@ def run_ours(args):
     sampler.join(timeout=2)
     ms_e2e, _ = timed(True, args.steps)
 
-    # per-kernel timing for the roofline entry: the same steps issued eagerly (a captured graph cannot carry timing
-    # events), the kernels of interest bracketed by CUDA events on the launching stream
+    # per-kernel timing for the roofline entries: the same steps issued eagerly (a captured graph cannot carry timing
+    # events), the kernels of interest bracketed by CUDA events on the launching stream.  Every such step begins with a
+    # device-side sleep: the host enqueues the whole step while the device waits, so no launch gap sits between events.
     os.environ["DGCNN_CUDA_GRAPH"] = "0"
-    ops._knn_events, ops._gemm_events, ops._ec_events = [], [], []
+    ops._knn_events, ops._gemm_events, ops._ec_events, ops._ec_bwd_events = [], [], [], []
     barrier()
+    sleep_cycles = int(6e-3 * 1.9e9)
     for i in range(3):
+        torch.cuda._sleep(sleep_cycles)
         step(i, False)
+        torch.cuda.synchronize()
     barrier()
-    ev, ops._knn_events = ops._knn_events, None
+    kev, ops._knn_events = ops._knn_events, None
     gev, ops._gemm_events = ops._gemm_events, None
     eev, ops._ec_events = ops._ec_events, None
+    bev, ops._ec_bwd_events = ops._ec_bwd_events, None
     os.environ.pop("DGCNN_CUDA_GRAPH", None)
-
-    pts_per_step = B_PER_GPU * NPTS * world
+    eev = [e for e in eev if True][:]            # layer 0 has the same F: all layers are 64-channel gathers
+    pts_per_step = B * N * world
     value = pts_per_step * args.steps / (ms_dev * 1e-3)
     e2e = pts_per_step * args.steps / (ms_e2e * 1e-3)
-
-    # Roofline of the dominant kernel: tc_gemm_wide_kernel on the FC0 layer (ops.py:151-160: the 1x1 conv over the
-    # 1792 non-broadcast channels of model.py:83-85's concat -> 512), the largest single launch of the step.
     pk, pk_kind = peaks()
-    P_ = B_PER_GPU * NPTS
-    fc0 = [a.elapsed_time(b) for (m, n, k, a, b) in gev if n == FCF[0] and m == P_]
-    kfc0 = max([k for (m, n, k, a, b) in gev if n == FCF[0] and m == P_], default=0)
-    knn64 = [a.elapsed_time(b) for (_, _, c, _, a, b) in ev if c == 64]
-    knn3 = [a.elapsed_time(b) for (_, _, c, _, a, b) in ev if c == CH]
-    roof = None
-    if fc0:
-        t_ms = float(np.mean(fc0))
-        flops = 2.0 * P_ * FCF[0] * kfc0                     # algorithmic: one fp32 multiply-add per (row, col, k)
-        ach = flops / (t_ms * 1e-3) / 1e12
-        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-        roof = {"kernel": "tc_gemm_wide_kernel<A K-major, B MN-major> on FC0 forward: [%d x %d] . [%d x %d], persistent "
-                          "128x256 tiles, TMA -> 2-stage smem ring -> tcgen05.mma (3 bf16 MMAs per k-slice: hi.hi + hi.lo + "
-                          "lo.hi, fp32 accumulate in TMEM, double-buffered) -> epilogue with BN column statistics"
-                          % (P_, kfc0, kfc0, FCF[0]),
-                "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": 438.2e6, "traffic_source": "profiles/r01e_top_kernels_ncu_full.csv: ncu --set full of this launch, "
-                                                       "dram read 362.8 MB + write 75.4 MB (algorithmic: bf16 hi/lo operand "
-                                                       "planes 352 MB + weights 3.7 MB + fp32 output 100.7 MB)",
-                "peak_source": pk_kind + " bf16 sustained (kernel timed inside the step)",
-                "ms_per_launch": t_ms, "launches_timed": len(fc0),
-                "algorithmic_flops": flops, "executed_tensor_flops": 3 * flops,
-                "executed_frac_of_peak": 3 * ach / peak,
-                "note": "achieved counts ONE multiply-add per product (the fp32 GEMM the reference runs); the kernel "
-                        "executes three bf16 MMAs per product to stay within the 1e-3 logits bound, so the tensor pipe "
-                        "itself runs at executed_frac_of_peak of the measured cuBLAS bf16 rate",
-                "other_kernels": {
-                    "k_nn_fused_64ch": {
-                        "what": "dgcnn_knn on [24,2048,64]: range + prep + knn_tc_filter_kernel (fp16 tcgen05 pass, two "
-                                "sweeps over TMEM accumulators) + exact refine; the [B,N,N] matrix never leaves the SM",
-                        "ms_per_call": float(np.mean(knn64)) if knn64 else None,
-                        "bound": "TMEM read port (64 B/clk/SM): 2 sweeps x 402.7 MB of fp32 accumulators",
-                        "effective_unfused_hbm_gbs": (821.9e6 / (float(np.mean(knn64)) * 1e-3) / 1e9) if knn64 else None,
-                        "algorithmic_tflops": (2.0 * B_PER_GPU * NPTS * NPTS * 64 / (float(np.mean(knn64)) * 1e-3) / 1e12)
-                        if knn64 else None},
-                    "k_nn_fused_xyz": {"ms_per_call": float(np.mean(knn3)) if knn3 else None},
-                    "edgeconv_fwd_gather": edgeconv_entry(eev),
-                    "knn_share_of_step": (sum(knn64) + sum(knn3)) / 3.0 / (ms_dev / args.steps)}}
+    roofs = roofline_entries(cfg, dtype, pk, pk_kind, gev, kev, eev, bev, ms_dev / args.steps)
 
     if rank == 0:
-        cb = cpu_baseline_run(3, 1) if (world == 1 and not args.no_cpu_baseline) else None
+        cb = cpu_baseline_run(3, 1, cfg) if (world == 1 and not args.no_cpu_baseline) else None
+        conf = workload_config(world, cfg, dtype)
+        conf["l2"] = "no explicit flush: one step streams >2 GB of activations per GPU, far beyond the 126 MB L2"
+        conf["launch"] = "micro-step (fwd+bwd) replayed from a CUDA graph captured by dgcnn.trainval after 2 eager runs"
         line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+                "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": conf,
                 "e2e": {"value": e2e, "unit": "points/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": int(h_pts[0].numel() * 4 + h_lab[0].numel() * 8),
                         "d2h_bytes_per_step": 8},
-                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}
+                "gpu_launches": int(launches), "clocks": sampler.summary()}
+        line.update(roofs)
+        line.setdefault("roofline", None)
         if cb is not None:
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
@@ -317,12 +380,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS), help="BASELINE.json configs[] index")
+    ap.add_argument("--dtype", default=None, choices=["f32", "bf16"], help="default: the configuration's own")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, cfg)
     else:
-        run_ours(args)
+        run_ours(args, cfg)
 
 
 if __name__ == "__main__":

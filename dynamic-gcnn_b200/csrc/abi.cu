@@ -37,6 +37,6 @@ int num_sms() {
 
 }  // namespace dgcnn
 
-extern "C" int dgcnn_abi_version(void) { return 1; }
+extern "C" int dgcnn_abi_version(void) { return 2; }
 extern "C" const char* dgcnn_last_error(void) { return dgcnn::err_buf(); }
 extern "C" uint64_t dgcnn_launch_count(void) { return dgcnn::g_launches.load(); }

@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256)
           if (q < sinks.n) {
             const size_t se = (size_t)r * sinks.ld[q] + c;
             *reinterpret_cast<uint2*>(sinks.p[q] + se) = *reinterpret_cast<uint2*>(h);
-            *reinterpret_cast<uint2*>(sinks.p[q] + sinks.plane[q] + se) = *reinterpret_cast<uint2*>(l);
+            if (sinks.plane[q]) *reinterpret_cast<uint2*>(sinks.p[q] + sinks.plane[q] + se) = *reinterpret_cast<uint2*>(l);
           }
         }
       }
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256)
           l[i] = __float2bfloat16_rn(gzv[i] - __bfloat162float(h[i]));
         }
         *reinterpret_cast<uint2*>(gz_planes + e) = *reinterpret_cast<uint2*>(h);
-        *reinterpret_cast<uint2*>(gz_planes + plane_elems + e) = *reinterpret_cast<uint2*>(l);
+        if (plane_elems) *reinterpret_cast<uint2*>(gz_planes + plane_elems + e) = *reinterpret_cast<uint2*>(l);
       }
     } else {
       if (gz) gz[e] = gzv[0];
@@ -620,17 +620,18 @@ extern "C" int dgcnn_bn_apply_fwd_sinks(const float* z, int64_t rows, int C, con
 static int bn_act_bwd_impl(const float* z, const float* out, const float* g_out, int64_t rows, int C, const float* mean,
                            const float* rstd, const float* group_bias, int group_rows, int relu, float* g_z,
                            void* g_z_planes, float* g_beta, float* g_pre, const float* beta, void* ws, size_t ws_bytes,
-                           dgcnn_stream_t stream);
+                           dgcnn_stream_t stream, int n_planes = 2);
 
 extern "C" int dgcnn_bn_act_bwd_planes(const float* z, const float* out, const float* beta, const float* g_out,
                                        int64_t rows, int C, const float* mean, const float* rstd,
                                        const float* group_bias, int group_rows, int relu, float* g_z, void* g_z_planes,
-                                       float* g_beta, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
+                                       int n_planes, float* g_beta, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
   DG_REQUIRE(!relu || out || beta, DGCNN_ERR_INVALID, "bn_act_bwd_planes: relu backward needs out or beta");
+  DG_REQUIRE(n_planes == 1 || n_planes == 2, DGCNN_ERR_INVALID, "bn_act_bwd_planes: n_planes must be 1 or 2");
   DG_REQUIRE(g_z_planes && (C & 3) == 0 && ((uintptr_t)g_z_planes & 7) == 0, DGCNN_ERR_INVALID,
              "bn_act_bwd_planes: needs a plane buffer and C %% 4 == 0");
   return bn_act_bwd_impl(z, out, g_out, rows, C, mean, rstd, group_bias, group_rows, relu, g_z, g_z_planes, g_beta,
-                         nullptr, out ? nullptr : beta, ws, ws_bytes, stream);
+                         nullptr, out ? nullptr : beta, ws, ws_bytes, stream, n_planes);
 }
 
 extern "C" int dgcnn_bn_act_bwd(const float* z, const float* out, const float* g_out, int64_t rows, int C,
@@ -652,7 +653,7 @@ extern "C" int dgcnn_bn_act_bwd_gb(const float* z, const float* out, const float
 static int bn_act_bwd_impl(const float* z, const float* out, const float* g_out, int64_t rows, int C, const float* mean,
                            const float* rstd, const float* group_bias, int group_rows, int relu, float* g_z,
                            void* g_z_planes, float* g_beta, float* g_pre, const float* beta, void* ws, size_t ws_bytes,
-                           dgcnn_stream_t stream) {
+                           dgcnn_stream_t stream, int n_planes) {
   DG_REQUIRE(!group_bias || (group_rows > 0 && rows % group_rows == 0), DGCNN_ERR_INVALID,
              "bn_act_bwd: rows=%lld is not a multiple of group_rows=%d", (long long)rows, group_rows);
   DG_REQUIRE(z && g_out && mean && rstd && (g_z || g_z_planes) && g_beta && ws, DGCNN_ERR_INVALID,
@@ -681,7 +682,7 @@ static int bn_act_bwd_impl(const float* z, const float* out, const float* g_out,
     bn_act_bwd_kernel<4><<<ew_blocks(total / 4), 256, 0, st>>>(z, out, g_out, mean, rstd, g_beta, s2, relu,
                                                                (uint32_t)(total / 4), C, 1.0f / (float)rows, g_z, g_pre,
                                                                group_bias, group_rows, (__nv_bfloat16*)g_z_planes,
-                                                               (size_t)total, beta);
+                                                               n_planes == 2 ? (size_t)total : 0, beta);
   else
     bn_act_bwd_kernel<1><<<ew_blocks(total), 256, 0, st>>>(z, out, g_out, mean, rstd, g_beta, s2, relu, (uint32_t)total, C,
                                                            1.0f / (float)rows, g_z, g_pre, group_bias, group_rows, nullptr,

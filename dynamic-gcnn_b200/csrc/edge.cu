@@ -15,6 +15,7 @@
 //                 active-edge counts and the incoming gradients), one streaming pass over [P,F]
 //     bwd_apply : recompute z, max, ties, mask from the gathered rows; g_z scattered with 16-byte vector atomics
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -77,6 +78,15 @@ __device__ __forceinline__ float4 ldg4(const __nv_bfloat16* p) {
   const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
   return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
                      __uint_as_float(r.y & 0xffff0000u));
+}
+__device__ __forceinline__ float4 ldg4(const __half* p) {
+  const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float ldg1(const __half* p) {
+  return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(p))));
 }
 __device__ __forceinline__ float ldg1(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float ldg1(const __nv_bfloat16* p) {
@@ -577,7 +587,8 @@ static int ec_check(const void* uv, const int32_t* idx, int B, int N, int F, int
   DG_REQUIRE(k >= 1 && k <= N, DGCNN_ERR_INVALID, "edgeconv: need 1 <= k <= N (k=%d N=%d)", k, N);
   DG_REQUIRE(k <= DGCNN_KNN_MAX_K, DGCNN_ERR_UNSUPPORTED, "edgeconv: k=%d > %d", k, DGCNN_KNN_MAX_K);
   DG_REQUIRE((int64_t)B * N < (1ll << 31) / 2, DGCNN_ERR_UNSUPPORTED, "edgeconv: B*N too large");
-  DG_REQUIRE(dtype == DGCNN_F32 || dtype == DGCNN_BF16, DGCNN_ERR_INVALID, "edgeconv: uv_dtype must be DGCNN_F32 or DGCNN_BF16");
+  DG_REQUIRE(dtype == DGCNN_F32 || dtype == DGCNN_BF16 || dtype == DGCNN_F16, DGCNN_ERR_INVALID,
+             "edgeconv: uv_dtype must be DGCNN_F32, DGCNN_BF16 or DGCNN_F16");
   DG_REQUIRE(((uintptr_t)uv & 15) == 0, DGCNN_ERR_INVALID, "edgeconv: uv must be 16-byte aligned");
   return DGCNN_OK;
 }
@@ -700,8 +711,9 @@ extern "C" int dgcnn_edgeconv_fwd_stats(const void* uv, int uv_dtype, const int3
   DG_REQUIRE(ws_bytes >= dgcnn_edgeconv_workspace_bytes(F), DGCNN_ERR_WORKSPACE, "edgeconv_fwd_stats: workspace");
   DG_REQUIRE(((uintptr_t)ws & 7) == 0, DGCNN_ERR_INVALID, "edgeconv_fwd_stats: workspace must be 8-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  return uv_dtype == DGCNN_BF16 ? fwd_stats_t<__nv_bfloat16>(uv, idx, B, N, F, k, mean, rstd, ws, st)
-                                : fwd_stats_t<float>(uv, idx, B, N, F, k, mean, rstd, ws, st);
+  if (uv_dtype == DGCNN_BF16) return fwd_stats_t<__nv_bfloat16>(uv, idx, B, N, F, k, mean, rstd, ws, st);
+  if (uv_dtype == DGCNN_F16) return fwd_stats_t<__half>(uv, idx, B, N, F, k, mean, rstd, ws, st);
+  return fwd_stats_t<float>(uv, idx, B, N, F, k, mean, rstd, ws, st);
 }
 
 extern "C" int dgcnn_edgeconv_fwd_apply(const void* uv, int uv_dtype, const int32_t* idx, int B, int N, int F, int k,
@@ -719,11 +731,14 @@ extern "C" int dgcnn_edgeconv_fwd_apply(const void* uv, int uv_dtype, const int3
                               (sink_plane_elems & 3) == 0 && ((uintptr_t)sink_planes & 7) == 0),
              DGCNN_ERR_INVALID, "edgeconv_fwd_apply: bad sink geometry (F, pitch, plane distance must be multiples of 4)");
   cudaStream_t st = (cudaStream_t)stream;
-  return uv_dtype == DGCNN_BF16
-             ? fwd_apply_t<__nv_bfloat16>(uv, idx, B, N, F, k, mean, rstd, beta, out_both, zmax, npos, sink_planes, sink_ld,
-                                          sink_plane_elems, st)
-             : fwd_apply_t<float>(uv, idx, B, N, F, k, mean, rstd, beta, out_both, zmax, npos, sink_planes, sink_ld,
-                                  sink_plane_elems, st);
+  if (uv_dtype == DGCNN_BF16)
+    return fwd_apply_t<__nv_bfloat16>(uv, idx, B, N, F, k, mean, rstd, beta, out_both, zmax, npos, sink_planes, sink_ld,
+                                      sink_plane_elems, st);
+  if (uv_dtype == DGCNN_F16)
+    return fwd_apply_t<__half>(uv, idx, B, N, F, k, mean, rstd, beta, out_both, zmax, npos, sink_planes, sink_ld,
+                               sink_plane_elems, st);
+  return fwd_apply_t<float>(uv, idx, B, N, F, k, mean, rstd, beta, out_both, zmax, npos, sink_planes, sink_ld,
+                            sink_plane_elems, st);
 }
 
 extern "C" int dgcnn_edgeconv_bwd_stats(const float* out_both, const uint8_t* npos, const float* beta, const float* g_max,
@@ -769,7 +784,9 @@ extern "C" int dgcnn_edgeconv_bwd_apply(const void* uv, int uv_dtype, const int3
     count_launch();
     DG_CUDA_LAUNCH_CHECK("zero_vhalf_kernel");
   }
-  return uv_dtype == DGCNN_BF16
-             ? bwd_apply_t<__nv_bfloat16>(uv, idx, B, N, F, k, mean, rstd, beta, zmax, g_max, g_mean, g_both, s1, s2, g_uv, st)
-             : bwd_apply_t<float>(uv, idx, B, N, F, k, mean, rstd, beta, zmax, g_max, g_mean, g_both, s1, s2, g_uv, st);
+  if (uv_dtype == DGCNN_BF16)
+    return bwd_apply_t<__nv_bfloat16>(uv, idx, B, N, F, k, mean, rstd, beta, zmax, g_max, g_mean, g_both, s1, s2, g_uv, st);
+  if (uv_dtype == DGCNN_F16)
+    return bwd_apply_t<__half>(uv, idx, B, N, F, k, mean, rstd, beta, zmax, g_max, g_mean, g_both, s1, s2, g_uv, st);
+  return bwd_apply_t<float>(uv, idx, B, N, F, k, mean, rstd, beta, zmax, g_max, g_mean, g_both, s1, s2, g_uv, st);
 }

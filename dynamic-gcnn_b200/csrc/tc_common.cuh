@@ -84,9 +84,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn tensor_map_encoder();
 // bf16 planes [2][rows][cols] row-major -> 3-D map with a {64, box_rows, 1} box, 128B swizzle, zero OOB fill
-int make_plane_map(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, uint32_t box_rows);
+// (n_planes = 1: plain bf16 operand, only the hi plane exists)
+int make_plane_map(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, uint32_t box_rows, int n_planes = 2);
 int make_plane_map_ld(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, int64_t ld, int64_t plane_elems,
-                      uint32_t box_rows);
+                      uint32_t box_rows, int n_planes = 2);
 
 // ---- wide (128x256, persistent) GEMM variant: tc_gemm_wide.cu ----
 struct WideOut {
@@ -101,6 +102,6 @@ struct WideOut {
 bool tc_wide_ok(int M, int N, int K);
 int tc_wide_splits(int M, int N, int K);
 int tc_gemm_wide_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, bool a_k, bool b_k, int M, int N, int K,
-                        int splits, const WideOut& out, cudaStream_t st);
+                        int splits, int planes, const WideOut& out, cudaStream_t st);
 
 }  // namespace dgcnn

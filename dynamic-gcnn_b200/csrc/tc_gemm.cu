@@ -39,7 +39,7 @@ struct OutGroups {
 template <bool A_K, bool B_K, int G_STAGES>
 __global__ void __launch_bounds__(G_THREADS, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   float* __restrict__ C, int M, int N, int K, int kblocks_per_split,
+                   float* __restrict__ C, int M, int N, int K, int kblocks_per_split, int planes,
                    const __grid_constant__ OutGroups og) {
   extern __shared__ unsigned char g_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)g_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -79,11 +79,12 @@ __global__ void __launch_bounds__(G_THREADS, 1)
         const int s = i % G_STAGES;
         const uint32_t ph = (i / G_STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        mbar_expect_tx(&full_bar[s], planes == 2 ? STAGE_BYTES : STAGE_BYTES / 2);
         unsigned char* st = smem + (size_t)s * STAGE_BYTES;
         const int k0 = (kb_begin + i) * GB_K;
 #pragma unroll
         for (int plane = 0; plane < 2; ++plane) {
+          if (plane >= planes) break;                       // single-plane (plain bf16) operands: hi only
           unsigned char* a_dst = st + plane * TILE_BYTES;
           unsigned char* b_dst = st + (2 + plane) * TILE_BYTES;
           if (A_K) {
@@ -123,9 +124,13 @@ __global__ void __launch_bounds__(G_THREADS, 1)
           const uint64_t dal = umma_desc(a_lo + ks * a_step, a_lbo, 1024);
           const uint64_t dbh = umma_desc(b_hi + ks * b_step, b_lbo, 1024);
           const uint64_t dbl = umma_desc(b_lo + ks * b_step, b_lbo, 1024);
-          umma_bf16(tmem_base, dal, dbh, idesc, (i | ks) != 0);   // small terms first
-          umma_bf16(tmem_base, dah, dbl, idesc, 1);
-          umma_bf16(tmem_base, dah, dbh, idesc, 1);
+          if (planes == 2) {
+            umma_bf16(tmem_base, dal, dbh, idesc, (i | ks) != 0);   // small terms first
+            umma_bf16(tmem_base, dah, dbl, idesc, 1);
+            umma_bf16(tmem_base, dah, dbh, idesc, 1);
+          } else {
+            umma_bf16(tmem_base, dah, dbh, idesc, (i | ks) != 0);   // plain bf16: one MMA per k-slice
+          }
         }
         umma_commit(&empty_bar[s]);                       // ring slot free once these MMAs retire
         if (i == nkb - 1) umma_commit(accum_bar);        // accumulator complete
@@ -211,7 +216,7 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int64_t rows, int
     l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
   }
   *reinterpret_cast<uint2*>(planes + r * ldo + c) = *reinterpret_cast<uint2*>(h);
-  *reinterpret_cast<uint2*>(planes + plane_elems + r * ldo + c) = *reinterpret_cast<uint2*>(l);
+  if (plane_elems) *reinterpret_cast<uint2*>(planes + plane_elems + r * ldo + c) = *reinterpret_cast<uint2*>(l);
 }
 
 EncodeTiledFn tensor_map_encoder() {
@@ -226,16 +231,17 @@ EncodeTiledFn tensor_map_encoder() {
   return fn;
 }
 
-int make_plane_map(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, uint32_t box_rows) {
-  return make_plane_map_ld(tm, planes, rows, cols, cols, rows * cols, box_rows);
+int make_plane_map(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, uint32_t box_rows, int n_planes) {
+  return make_plane_map_ld(tm, planes, rows, cols, cols, rows * cols, box_rows, n_planes);
 }
 
 // column slice of a wider operand: row pitch ld elements, second plane plane_elems elements after the first
 int make_plane_map_ld(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, int64_t ld, int64_t plane_elems,
-                      uint32_t box_rows) {
+                      uint32_t box_rows, int n_planes) {
   EncodeTiledFn fn = tensor_map_encoder();
   if (!fn) return set_err(DGCNN_ERR_CUDA, "tensor map: cuTensorMapEncodeTiled unavailable");
-  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(n_planes == 1 ? 1 : 2)};
+  if (plane_elems <= 0) plane_elems = rows * ld;      // unused stride of a single-plane operand (must still be valid)
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_elems * 2};
   cuuint32_t box[3] = {64, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -247,8 +253,8 @@ int make_plane_map_ld(CUtensorMap* tm, const void* planes, int64_t rows, int64_t
 }
 
 // kmajor: box {64 cols(k), 128 rows};  mn-major: box {64 cols(mn), 64 rows(k)}
-static int make_map(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, bool kmajor) {
-  return make_plane_map(tm, planes, rows, cols, kmajor ? 128u : 64u);
+static int make_map(CUtensorMap* tm, const void* planes, int64_t rows, int64_t cols, bool kmajor, int n_planes) {
+  return make_plane_map(tm, planes, rows, cols, kmajor ? 128u : 64u, n_planes);
 }
 
 static int tc_splits(int M, int N, int K) {
@@ -301,7 +307,7 @@ extern "C" int dgcnn_split_bf16(const float* x, int64_t rows, int cols, int64_t 
   DG_REQUIRE(x && planes, DGCNN_ERR_INVALID, "split_bf16: null pointer");
   DG_REQUIRE(rows > 0 && cols > 0 && (cols & 3) == 0, DGCNN_ERR_INVALID,
              "split_bf16: rows=%lld cols=%d (cols must be a positive multiple of 4)", (long long)rows, cols);
-  DG_REQUIRE(ldx >= cols && ldo >= cols && (ldx & 3) == 0 && (ldo & 3) == 0 && (plane_elems & 3) == 0,
+  DG_REQUIRE(ldx >= cols && ldo >= cols && (ldx & 3) == 0 && (ldo & 3) == 0 && (plane_elems & 3) == 0 && plane_elems >= 0,
              DGCNN_ERR_INVALID, "split_bf16: pitches must be multiples of 4 and >= cols");
   DG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)planes & 7) == 0, DGCNN_ERR_INVALID, "split_bf16: alignment");
   return launch_split_bf16(x, rows, cols, ldx, planes, ldo, plane_elems, (cudaStream_t)stream);
@@ -314,27 +320,28 @@ extern "C" size_t dgcnn_tc_gemm_workspace_bytes(int M, int N, int K) {
 }
 
 static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
-                        int transB, void* ws, size_t ws_bytes, const OutGroups& og, float* colstats,
+                        int transB, int planes, void* ws, size_t ws_bytes, const OutGroups& og, float* colstats,
                         dgcnn_stream_t stream, int64_t a_ld = 0, int64_t a_plane_elems = 0);
 
 extern "C" int dgcnn_tc_gemm(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
-                             int transB, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
+                             int transB, int planes, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
   DG_REQUIRE(C, DGCNN_ERR_INVALID, "tc_gemm: null output");
   OutGroups og;
   og.n = 0;
-  return tc_gemm_impl(a_planes, b_planes, C, M, N, K, transA, transB, ws, ws_bytes, og, nullptr, stream);
+  return tc_gemm_impl(a_planes, b_planes, C, M, N, K, transA, transB, planes, ws, ws_bytes, og, nullptr, stream);
 }
 
 extern "C" int dgcnn_tc_gemm_a_slice(const void* a_planes, int64_t a_ld, int64_t a_plane_elems, const void* b_planes,
-                                     float* C, int M, int N, int K, int transA, int transB, void* ws, size_t ws_bytes,
-                                     dgcnn_stream_t stream) {
+                                     float* C, int M, int N, int K, int transA, int transB, int planes, void* ws,
+                                     size_t ws_bytes, dgcnn_stream_t stream) {
   DG_REQUIRE(C, DGCNN_ERR_INVALID, "tc_gemm_a_slice: null output");
   const int64_t a_cols = transA ? M : K;
-  DG_REQUIRE(a_ld >= a_cols && (a_ld & 7) == 0 && a_plane_elems > 0 && (a_plane_elems & 7) == 0, DGCNN_ERR_INVALID,
+  DG_REQUIRE(a_ld >= a_cols && (a_ld & 7) == 0 && a_plane_elems >= 0 && (a_plane_elems & 7) == 0 &&
+                 (a_plane_elems > 0 || planes == 1), DGCNN_ERR_INVALID,
              "tc_gemm_a_slice: bad pitch %lld / plane distance %lld", (long long)a_ld, (long long)a_plane_elems);
   OutGroups og;
   og.n = 0;
-  return tc_gemm_impl(a_planes, b_planes, C, M, N, K, transA, transB, ws, ws_bytes, og, nullptr, stream, a_ld,
+  return tc_gemm_impl(a_planes, b_planes, C, M, N, K, transA, transB, planes, ws, ws_bytes, og, nullptr, stream, a_ld,
                       a_plane_elems);
 }
 
@@ -343,17 +350,17 @@ extern "C" int dgcnn_tc_gemm_stats_supported(int M, int N, int K) {
 }
 
 extern "C" int dgcnn_tc_gemm_stats(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
-                                   int transB, float* colstats, dgcnn_stream_t stream) {
+                                   int transB, int planes, float* colstats, dgcnn_stream_t stream) {
   DG_REQUIRE(C && colstats, DGCNN_ERR_INVALID, "tc_gemm_stats: null output");
   DG_REQUIRE(dgcnn_tc_gemm_stats_supported(M, N, K), DGCNN_ERR_UNSUPPORTED,
              "tc_gemm_stats: needs N %% 256 == 0, M >= 128 and no k-split (M=%d N=%d K=%d)", M, N, K);
   OutGroups og;
   og.n = 0;
-  return tc_gemm_impl(a_planes, b_planes, C, M, N, K, transA, transB, nullptr, 0, og, colstats, stream);
+  return tc_gemm_impl(a_planes, b_planes, C, M, N, K, transA, transB, planes, nullptr, 0, og, colstats, stream);
 }
 
 extern "C" int dgcnn_tc_gemm_grouped(const void* a_planes, const void* b_planes, int M, int N, int K, int transA,
-                                     int transB, int n_groups, const int* starts, const int* widths,
+                                     int transB, int planes, int n_groups, const int* starts, const int* widths,
                                      float* const* outs, dgcnn_stream_t stream) {
   DG_REQUIRE(n_groups >= 1 && n_groups <= 32 && starts && widths && outs, DGCNN_ERR_INVALID,
              "tc_gemm_grouped: need 1..32 output groups");
@@ -372,13 +379,14 @@ extern "C" int dgcnn_tc_gemm_grouped(const void* a_planes, const void* b_planes,
     covered += widths[g];
   }
   DG_REQUIRE(covered <= N, DGCNN_ERR_INVALID, "tc_gemm_grouped: groups overlap");
-  return tc_gemm_impl(a_planes, b_planes, outs[0], M, N, K, transA, transB, nullptr, 0, og, nullptr, stream);
+  return tc_gemm_impl(a_planes, b_planes, outs[0], M, N, K, transA, transB, planes, nullptr, 0, og, nullptr, stream);
 }
 
 static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
-                        int transB, void* ws, size_t ws_bytes, const OutGroups& og, float* colstats,
+                        int transB, int planes, void* ws, size_t ws_bytes, const OutGroups& og, float* colstats,
                         dgcnn_stream_t stream, int64_t a_ld, int64_t a_plane_elems) {
   cudaStream_t st = (cudaStream_t)stream;
+  DG_REQUIRE(planes == 1 || planes == 2, DGCNN_ERR_INVALID, "tc_gemm: planes must be 1 (bf16) or 2 (bf16 hi/lo), got %d", planes);
   DG_REQUIRE(a_planes && b_planes && C, DGCNN_ERR_INVALID, "tc_gemm: null pointer");
   DG_REQUIRE(M > 0 && N > 0 && K > 0, DGCNN_ERR_INVALID, "tc_gemm: bad shape M=%d N=%d K=%d", M, N, K);
   DG_REQUIRE((M & 7) == 0 && (N & 7) == 0 && (K & 7) == 0, DGCNN_ERR_UNSUPPORTED,
@@ -389,10 +397,10 @@ static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, in
   // transB, [N,K] (K-major).
   const bool a_k = !transA, b_k = transB != 0;
   CUtensorMap tmA, tmB;
-  int rc = a_ld > 0 ? make_plane_map_ld(&tmA, a_planes, a_k ? M : K, a_k ? K : M, a_ld, a_plane_elems, a_k ? 128u : 64u)
-                    : make_map(&tmA, a_planes, a_k ? M : K, a_k ? K : M, a_k);
+  int rc = a_ld > 0 ? make_plane_map_ld(&tmA, a_planes, a_k ? M : K, a_k ? K : M, a_ld, a_plane_elems, a_k ? 128u : 64u, planes)
+                    : make_map(&tmA, a_planes, a_k ? M : K, a_k ? K : M, a_k, planes);
   if (rc) return rc;
-  rc = make_map(&tmB, b_planes, b_k ? N : K, b_k ? K : N, b_k);
+  rc = make_map(&tmB, b_planes, b_k ? N : K, b_k ? K : N, b_k, planes);
   if (rc) return rc;
   if (tc_wide_ok(M, N, K)) {
     // 128x256 persistent kernel (tc_gemm_wide.cu)
@@ -412,7 +420,7 @@ static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, in
       DG_REQUIRE(ws && ws_bytes >= need, DGCNN_ERR_WORKSPACE, "tc_gemm: workspace %zu < %zu bytes", ws_bytes, need);
       wo.C = reinterpret_cast<float*>(ws);
     }
-    rc = tc_gemm_wide_launch(tmA, tmB, a_k, b_k, M, N, K, wsplits, wo, st);
+    rc = tc_gemm_wide_launch(tmA, tmB, a_k, b_k, M, N, K, wsplits, planes, wo, st);
     if (rc) return rc;
     if (wsplits > 1) {
       const int64_t MN = (int64_t)M * N;
@@ -451,7 +459,7 @@ static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, in
                            (int)g_smem(ST_));                                                                \
       done_ = true;                                                                                          \
     }                                                                                                        \
-    tc_gemm_kernel<AK_, BK_, ST_><<<grid, G_THREADS, g_smem(ST_), st>>>(tmA, tmB, out, M, N, K, kper, og);    \
+    tc_gemm_kernel<AK_, BK_, ST_><<<grid, G_THREADS, g_smem(ST_), st>>>(tmA, tmB, out, M, N, K, kper, planes, og); \
   } while (0)
 #define DG_TC_LAUNCH_ST(AK_, BK_)          \
   do {                                     \

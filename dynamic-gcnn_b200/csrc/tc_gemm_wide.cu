@@ -32,7 +32,7 @@ constexpr size_t W_SMEM = W_BAR_OFF + 128 + 1024 /*align*/;
 template <bool A_K, bool B_K>
 __global__ void __launch_bounds__(W_THREADS, 1)
     tc_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                        int K, int kblocks_per_split, int splits, const __grid_constant__ WideOut out) {
+                        int K, int kblocks_per_split, int splits, int planes, const __grid_constant__ WideOut out) {
   extern __shared__ unsigned char w_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)w_smem_raw + 1023) & ~(uintptr_t)1023);
   float* tr = reinterpret_cast<float*>(smem + W_TR_OFF);
@@ -80,11 +80,12 @@ __global__ void __launch_bounds__(W_THREADS, 1)
         for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
           const int s = it % W_STAGES;
           mbar_wait(&empty_bar[s], ((it / W_STAGES) & 1) ^ 1);
-          mbar_expect_tx(&full_bar[s], W_STAGE);
+          mbar_expect_tx(&full_bar[s], planes == 2 ? W_STAGE : W_STAGE / 2);
           unsigned char* st = smem + (size_t)s * W_STAGE;
           const int k0 = kb * W_K;
 #pragma unroll
           for (int plane = 0; plane < 2; ++plane) {
+            if (plane >= planes) break;                     // single-plane (plain bf16) operands: hi only
             unsigned char* a_dst = st + plane * W_ATILE;
             unsigned char* b_dst = st + 2 * W_ATILE + plane * W_BTILE;
             if (A_K) {
@@ -131,9 +132,13 @@ __global__ void __launch_bounds__(W_THREADS, 1)
             const uint64_t dal = umma_desc(a_lo + ks * a_step, a_lbo, 1024);
             const uint64_t dbh = umma_desc(b_hi + ks * b_step, b_lbo, 1024);
             const uint64_t dbl = umma_desc(b_lo + ks * b_step, b_lbo, 1024);
-            umma_bf16(acc, dal, dbh, idesc, (kb != kb_begin) || ks != 0);   // small terms first
-            umma_bf16(acc, dah, dbl, idesc, 1);
-            umma_bf16(acc, dah, dbh, idesc, 1);
+            if (planes == 2) {
+              umma_bf16(acc, dal, dbh, idesc, (kb != kb_begin) || ks != 0);   // small terms first
+              umma_bf16(acc, dah, dbl, idesc, 1);
+              umma_bf16(acc, dah, dbh, idesc, 1);
+            } else {
+              umma_bf16(acc, dah, dbh, idesc, (kb != kb_begin) || ks != 0);   // plain bf16: one MMA per k-slice
+            }
           }
           umma_commit(&empty_bar[s]);
           if (kb == kb_end - 1) umma_commit(&acc_full[ab]);
@@ -265,7 +270,7 @@ bool tc_wide_ok(int M, int N, int K) {
 
 // C (or groups / split partials) = op(A).op(B) with the wide kernel.  colstats may be null.
 int tc_gemm_wide_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, bool a_k, bool b_k, int M, int N, int K,
-                        int splits, const WideOut& out, cudaStream_t st) {
+                        int splits, int planes, const WideOut& out, cudaStream_t st) {
   const int kb = cdiv(K, W_K);
   const int kper = cdiv(kb, splits);
   const int total = cdiv(M, W_M) * (N / W_N) * splits;
@@ -278,7 +283,7 @@ int tc_gemm_wide_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, bool a_k
                            (int)W_SMEM);                                                                       \
       done_ = true;                                                                                            \
     }                                                                                                          \
-    tc_gemm_wide_kernel<AK_, BK_><<<grid, W_THREADS, W_SMEM, st>>>(tmA, tmB, M, N, K, kper, splits, out);      \
+    tc_gemm_wide_kernel<AK_, BK_><<<grid, W_THREADS, W_SMEM, st>>>(tmA, tmB, M, N, K, kper, splits, planes, out); \
   } while (0)
   if (a_k && b_k) DG_WIDE(true, true);
   else if (a_k && !b_k) DG_WIDE(true, false);

@@ -35,11 +35,11 @@ SIGNATURES = {
     "dgcnn_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "dgcnn_split_bf16": (_i, [_vp, _i64, _i, _i64, _vp, _i64, _i64, _vp]),
     "dgcnn_tc_gemm_workspace_bytes": (_sz, [_i, _i, _i]),
-    "dgcnn_tc_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
-    "dgcnn_tc_gemm_a_slice": (_i, [_vp, _i64, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "dgcnn_tc_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "dgcnn_tc_gemm_a_slice": (_i, [_vp, _i64, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "dgcnn_tc_gemm_stats_supported": (_i, [_i, _i, _i]),
-    "dgcnn_tc_gemm_stats": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
-    "dgcnn_tc_gemm_grouped": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "dgcnn_tc_gemm_stats": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "dgcnn_tc_gemm_grouped": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dgcnn_edgeconv_workspace_bytes": (_sz, [_i]),
     "dgcnn_edgeconv_fwd_stats": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "dgcnn_edgeconv_fwd_apply": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
@@ -54,7 +54,7 @@ SIGNATURES = {
     "dgcnn_bn_act_bwd_gb": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dgcnn_bn_stats_from_tiles": (_i, [_vp, _i, _i, _i64, _vp, _i, _vp, _vp, _vp]),
     "dgcnn_bn_apply_fwd": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
-    "dgcnn_bn_act_bwd_planes": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dgcnn_bn_act_bwd_planes": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "dgcnn_group_max_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "dgcnn_group_max_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "dgcnn_group_max_bwd_add": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
@@ -64,7 +64,7 @@ SIGNATURES = {
 }
 
 ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = -1, -2, -3, -4
-DT_F32, DT_BF16 = 0, 1   # DGCNN_F32 / DGCNN_BF16
+DT_F32, DT_BF16, DT_F16 = 0, 1, 2   # DGCNN_F32 / DGCNN_BF16 / DGCNN_F16
 
 
 def lib():

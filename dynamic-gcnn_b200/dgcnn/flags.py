@@ -34,6 +34,7 @@ class DGCNN_FLAGS:
     EDGE_CONV_FILTERS = 64
     FC_LAYERS = 2
     FC_FILTERS = "512,256"
+    DTYPE = "f32"     # not in the reference: arithmetic of the 1x1 convolutions, f32 (fp32-faithful) | bf16
     # train / inference (flags.py:20-33)
     SEED = -1
     LEARNING_RATE = 0.001
@@ -84,6 +85,7 @@ class DGCNN_FLAGS:
         ("-dkey", "--data_key", str, "DATA_KEY", "A keyword to fetch data from file"),
         ("-lkey", "--label_key", str, "LABEL_KEY", "A keyword to fetch label from file"),
         ("-sd", "--seed", int, "SEED", "Seed for random number generators"),
+        ("-dt", "--dtype", str, "DTYPE", "Arithmetic of the 1x1 convolutions: f32 (fp32-faithful) or bf16"),
     ]
     _TRAIN_ONLY = [
         ("-wp", "--weight_prefix", str, "WEIGHT_PREFIX", "Prefix (directory + file prefix) for snapshots of weights"),

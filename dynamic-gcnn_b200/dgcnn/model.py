@@ -38,13 +38,18 @@ def build(point_cloud, flags, dropout_mask=None):
     if flags.MODEL_NAME not in ("dgcnn", "residual-dgcnn", "residual-dgcnn-nofc"):
         print("Unsupported MODEL_NAME: %s" % flags.MODEL_NAME)
         raise NotImplementedError
-    old_sinks = ops._sinks
+    dtype = str(getattr(flags, "DTYPE", "f32") or "f32").lower()
+    if dtype not in ("f32", "fp32", "bf16"):
+        print("Unsupported DTYPE: %s (f32 | bf16)" % dtype)
+        raise NotImplementedError
+    old_sinks, old_prec = ops._sinks, ops._precision
+    ops._precision = "bf16" if dtype == "bf16" else "f32"
     ops._sinks = _make_sinks(flags, batch_size * num_point, net.device)
     try:
         return _build_body(net, flags, dropout_mask, num_edge_conv, num_edge_filters, num_fc, num_fc_filters, is_training,
                            k, debug, num_class, batch_size, num_point)
     finally:
-        ops._sinks = old_sinks
+        ops._sinks, ops._precision = old_sinks, old_prec
 
 
 def _make_sinks(flags, P, device):
@@ -66,8 +71,9 @@ def _make_sinks(flags, P, device):
     k_merged = ops.CONV1_WIDTH * L
     k_fc0 = sum(widths) + 1024
     bf = dict(dtype=torch.bfloat16, device=device)
-    sk.planes["MergedEdgeConv"] = torch.empty((2, P, k_merged), **bf)
-    sk.planes["FC0"] = torch.empty((2, P, k_fc0), **bf)
+    npl = ops._npl()
+    sk.planes["MergedEdgeConv"] = torch.empty((npl, P, k_merged), **bf)
+    sk.planes["FC0"] = torch.empty((npl, P, k_fc0), **bf)
     col = 0
     for i, f in enumerate(filt):
         sk.targets[("ec", i, "both")] = [(sk.planes["FC0"], col)]
@@ -75,7 +81,7 @@ def _make_sinks(flags, P, device):
         col += 2 * f + ops.CONV1_WIDTH
     sk.targets[("layer", "MergedEdgeConv")] = [(sk.planes["FC0"], col)]
     if nfc > 1 and ops._tc_ok(P, fcf[0], fcf[1]):
-        sk.planes["FC1"] = torch.empty((2, P, fcf[0]), **bf)
+        sk.planes["FC1"] = torch.empty((npl, P, fcf[0]), **bf)
         sk.targets[("layer", "FC0")] = [(sk.planes["FC1"], 0)]
     return sk
 

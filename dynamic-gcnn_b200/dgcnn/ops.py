@@ -43,7 +43,7 @@ class PlaneSinks:
         n = len(lst)
         ptrs = (ctypes.c_void_p * max(n, 1))(*[pl.data_ptr() + 2 * col for pl, col in lst])
         lds = (ctypes.c_int * max(n, 1))(*[pl.shape[2] for pl, _ in lst])
-        pes = (ctypes.c_int64 * max(n, 1))(*[pl.shape[1] * pl.shape[2] for pl, _ in lst])
+        pes = (ctypes.c_int64 * max(n, 1))(*[_pe(pl) for pl, _ in lst])
         return n, ptrs, lds, pes, lst
 
     def mark(self, t2d_ptr, cols, ld, lst):
@@ -60,6 +60,24 @@ _sinks = None   # set by dgcnn.model.build for the duration of one forward pass
 
 
 relu = "relu"  # stand-in for tf.nn.relu as the `activation` argument (None = linear, ops.py:121)
+
+# Arithmetic mode of the 1x1 convolutions, set by dgcnn.model.build from flags.DTYPE for the duration of a forward pass:
+#   "f32"  : fp32-faithful -- tensor-core operands are two bf16 planes (hi, lo), 3 MMAs per product; uv / conv1 forward
+#            on the exact fp32 SIMT GEMM; fp32 uv table
+#   "bf16" : BASELINE.json configs[2] -- single-plane bf16 operands, 1 MMA per product, every 1x1 conv on the tensor
+#            cores, bf16 uv table (half the gather bytes).  Statistics, activations and k_nn stay fp32.
+_precision = "f32"
+_bf16_table = torch.float16   # bf16 mode: storage type of the gathered uv table (None: fp32)
+_bf16_uv_gemm = True    # bf16 mode: the uv GEMM itself in bf16 (else exact fp32)
+
+
+def _npl() -> int:
+    return 1 if _precision == "bf16" else 2
+
+
+def _pe(planes: torch.Tensor) -> int:
+    """distance of the lo plane in elements (0 = the operand has a hi plane only)"""
+    return planes.shape[1] * planes.shape[2] if planes.shape[0] == 2 else 0
 
 BN_EPS = 1e-3
 CONV1_WIDTH = 64  # ops.py:63
@@ -199,13 +217,23 @@ class _Conv1x1(torch.autograd.Function):
     """slim.conv2d(kernel_size=1, stride=1, VALID) on channels-last data = [P,Cin] x [Cin,Cout]."""
 
     @staticmethod
-    def forward(ctx, a, w):
+    def forward(ctx, a, w, exact=False):
         a = nv.require_cuda(a, "conv input")
         w = nv.require_cuda(w, "conv weights")
         ctx.save_for_backward(a, w)
         # if a producer already wrote this input as bf16 planes into some head operand, the weight gradient reuses them
         ctx.a_planes = _sinks.find(a) if _sinks is not None else None
-        return _gemm_raw(a, w, a.shape[0], w.shape[1], a.shape[1], 0, 0)
+        ctx.npl = _npl()
+        P, Cin = a.shape
+        Cout = w.shape[1]
+        if ctx.npl == 1 and _tc_ok(P, Cin, Cout) and not exact:
+            # reduced-precision variant: the forward takes the tensor cores too (one bf16 MMA per product)
+            pw = _split(w, 1)
+            if ctx.a_planes is not None and ctx.a_planes[0].shape[0] == 1:
+                pl, col = ctx.a_planes
+                return _tc_gemm_a_slice_raw(pl, col, pw, P, Cout, Cin, 0, 0)
+            return _tc_gemm_raw(_split(a, 1), pw, P, Cout, Cin, 0, 0)
+        return _gemm_raw(a, w, P, Cout, Cin, 0, 0)
 
     @staticmethod
     def backward(ctx, g):
@@ -214,31 +242,25 @@ class _Conv1x1(torch.autograd.Function):
         P, Cin = a.shape
         Cout = w.shape[1]
         ga = gw = None
+        npl = ctx.npl
         if _tc_ok(P, Cin, Cout):
-            # the forward stays exact fp32 (the next layer's kNN is built on it); gradients feed no kNN, so they
-            # take the tensor-core path like every other gradient GEMM of the model
-            pg = _split(g)
+            # f32 mode: the forward stays exact fp32 (the next layer's kNN is built on it); gradients feed no kNN, so
+            # they take the tensor-core path like every other gradient GEMM of the model
+            pg = _split(g, npl)
             if ctx.needs_input_grad[0]:
-                ga = _tc_gemm_raw(pg, _split(w), P, Cin, Cout, 0, 1)
+                ga = _tc_gemm_raw(pg, _split(w, npl), P, Cin, Cout, 0, 1)
             if ctx.needs_input_grad[1]:
-                if ctx.a_planes is not None:
+                if ctx.a_planes is not None and ctx.a_planes[0].shape[0] == npl:
                     pl, col = ctx.a_planes
-                    L = nv.lib()
-                    gw = torch.empty((Cin, Cout), dtype=torch.float32, device=pg.device)
-                    need = L.dgcnn_tc_gemm_workspace_bytes(Cin, Cout, P)
-                    ws = nv.workspace(pg.device, need, "gemm") if need else None
-                    nv.check(L.dgcnn_tc_gemm_a_slice(pl.data_ptr() + 2 * col, pl.shape[2], pl.shape[1] * pl.shape[2],
-                                                     pg.data_ptr(), gw.data_ptr(), Cin, Cout, P, 1, 0, nv.ptr(ws),
-                                                     ws.numel() if ws is not None else 0, nv.stream_ptr(pg.device)),
-                             "tc_gemm_a_slice")
+                    gw = _tc_gemm_a_slice_raw(pl, col, pg, Cin, Cout, P, 1, 0)
                 else:
-                    gw = _tc_gemm_raw(_split(a), pg, Cin, Cout, P, 1, 0)
-            return ga, gw
+                    gw = _tc_gemm_raw(_split(a, npl), pg, Cin, Cout, P, 1, 0)
+            return ga, gw, None
         if ctx.needs_input_grad[0]:
             ga = _gemm_raw(g, w, P, Cin, Cout, 0, 1)  # g . W^T
         if ctx.needs_input_grad[1]:
             gw = _gemm_raw(a, g, Cin, Cout, P, 1, 0)  # A^T . g  (split over the P points)
-        return ga, gw
+        return ga, gw, None
 
 
 # ---- tensor-core path: tcgen05 GEMM on pre-split bf16 hi/lo planes (fp32-faithful, csrc/tc_gemm.cu) -------------
@@ -254,13 +276,14 @@ def _split_into(x2d: torch.Tensor, planes: torch.Tensor, col: int) -> None:
     rows, c = x2d.shape
     ld = planes.shape[2]
     dst = planes.data_ptr() + 2 * col
-    nv.check(nv.lib().dgcnn_split_bf16(x2d.data_ptr(), rows, c, x2d.stride(0), dst, ld, planes.shape[1] * ld,
+    nv.check(nv.lib().dgcnn_split_bf16(x2d.data_ptr(), rows, c, x2d.stride(0), dst, ld, _pe(planes),
                                        nv.stream_ptr(x2d.device)), "split_bf16")
 
 
-def _split(x2d: torch.Tensor) -> torch.Tensor:
+def _split(x2d: torch.Tensor, npl: Optional[int] = None) -> torch.Tensor:
+    """fp32 [rows, cols] -> bf16 operand planes [npl, rows, cols] (npl: 2 = hi/lo, 1 = plain bf16; default: the mode)"""
     x2d = nv.require_cuda(x2d, "operand")
-    planes = torch.empty((2,) + tuple(x2d.shape), dtype=torch.bfloat16, device=x2d.device)
+    planes = torch.empty((npl or _npl(),) + tuple(x2d.shape), dtype=torch.bfloat16, device=x2d.device)
     _split_into(x2d, planes, 0)
     return planes
 
@@ -270,8 +293,22 @@ def _tc_gemm_raw(pa, pb, M, N, K, tA, tB):
     out = torch.empty((M, N), dtype=torch.float32, device=pa.device)
     need = L.dgcnn_tc_gemm_workspace_bytes(M, N, K)
     ws = nv.workspace(pa.device, need, "gemm") if need else None
-    nv.check(L.dgcnn_tc_gemm(pa.data_ptr(), pb.data_ptr(), out.data_ptr(), M, N, K, tA, tB, nv.ptr(ws),
+    assert pa.shape[0] == pb.shape[0], "tc_gemm: both operands must be in the same precision mode"
+    nv.check(L.dgcnn_tc_gemm(pa.data_ptr(), pb.data_ptr(), out.data_ptr(), M, N, K, tA, tB, pa.shape[0], nv.ptr(ws),
                              ws.numel() if ws is not None else 0, nv.stream_ptr(pa.device)), "tc_gemm")
+    return out
+
+
+def _tc_gemm_a_slice_raw(pl, col, pb, M, N, K, tA, tB):
+    """op(A) = the column slice starting at `col` of the wider operand `pl` (filled by its producer)"""
+    L = nv.lib()
+    out = torch.empty((M, N), dtype=torch.float32, device=pb.device)
+    need = L.dgcnn_tc_gemm_workspace_bytes(M, N, K)
+    ws = nv.workspace(pb.device, need, "gemm") if need else None
+    assert pl.shape[0] == pb.shape[0], "tc_gemm_a_slice: both operands must be in the same precision mode"
+    nv.check(L.dgcnn_tc_gemm_a_slice(pl.data_ptr() + 2 * col, pl.shape[2], _pe(pl), pb.data_ptr(), out.data_ptr(), M, N, K,
+                                     tA, tB, pb.shape[0], nv.ptr(ws), ws.numel() if ws is not None else 0,
+                                     nv.stream_ptr(pb.device)), "tc_gemm_a_slice")
     return out
 
 
@@ -287,8 +324,8 @@ def _tc_dx_sources(pg, pw, P, K, Cout, widths, needs):
         starts = (ctypes.c_int * n)(*[sum(widths[:i]) for i in range(n)])
         cw = (ctypes.c_int * n)(*widths)
         ptrs = (ctypes.c_void_p * n)(*[b.data_ptr() for b in bufs])
-        nv.check(nv.lib().dgcnn_tc_gemm_grouped(pg.data_ptr(), pw.data_ptr(), P, K, Cout, 0, 1, n, starts, cw, ptrs,
-                                                nv.stream_ptr(pg.device)), "tc_gemm_grouped")
+        nv.check(nv.lib().dgcnn_tc_gemm_grouped(pg.data_ptr(), pw.data_ptr(), P, K, Cout, 0, 1, pg.shape[0], n, starts, cw,
+                                                ptrs, nv.stream_ptr(pg.device)), "tc_gemm_grouped")
         return [b if needs[i] else None for i, b in enumerate(bufs)]
     gcat = _tc_gemm_raw(pg, pw, P, K, Cout, 0, 1)                                     # g . W^T
     outs, off = [], 0
@@ -304,8 +341,8 @@ def _split_sources(srcs, w, planes=None):
     P = srcs[0].shape[0]
     widths = [int(t.shape[1]) for t in srcs]
     K = sum(widths)
-    if planes is None or tuple(planes.shape) != (2, P, K) or _sinks is None:
-        planes = torch.empty((2, P, K), dtype=torch.bfloat16, device=w.device)
+    if planes is None or tuple(planes.shape) != (_npl(), P, K) or _sinks is None:
+        planes = torch.empty((_npl(), P, K), dtype=torch.bfloat16, device=w.device)
         done = {}
     else:
         done = _sinks.done
@@ -338,7 +375,7 @@ class _ConcatConvTC(torch.autograd.Function):
         planes, pw = ctx.saved_tensors
         _, P, K = planes.shape
         Cout = pw.shape[2]
-        pg = _split(nv.require_cuda(g, "grad"))
+        pg = _split(nv.require_cuda(g, "grad"), planes.shape[0])
         gw = _tc_gemm_raw(planes, pg, K, Cout, P, 1, 0) if ctx.needs_input_grad[0] else None   # X^T . g
         return tuple([gw] + _tc_dx_sources(pg, pw, P, K, Cout, ctx.widths, ctx.needs_input_grad[1:]))
 
@@ -376,8 +413,8 @@ class _ConvBnActTC(torch.autograd.Function):
             if _gemm_events is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            nv.check(L.dgcnn_tc_gemm_stats(planes.data_ptr(), pw.data_ptr(), z.data_ptr(), P, Cout, K, 0, 0, cs.data_ptr(),
-                                           st), "tc_gemm_stats")
+            nv.check(L.dgcnn_tc_gemm_stats(planes.data_ptr(), pw.data_ptr(), z.data_ptr(), P, Cout, K, 0, 0, planes.shape[0],
+                                           cs.data_ptr(), st), "tc_gemm_stats")
             if ev is not None:
                 ev[1].record()
                 _gemm_events.append((P, Cout, K, ev[0], ev[1]))
@@ -407,12 +444,12 @@ class _ConvBnActTC(torch.autograd.Function):
         dev = g.device
         L = nv.lib()
         ws = nv.workspace(dev, L.dgcnn_bn_workspace_bytes(Cout), "stats")
-        pg = torch.empty((2, P, Cout), dtype=torch.bfloat16, device=dev)
+        pg = torch.empty((planes.shape[0], P, Cout), dtype=torch.bfloat16, device=dev)
         gz = torch.empty_like(z) if gb is not None else None      # fp32 copy only for the per-cloud bias gradient
         gbeta = torch.empty(Cout, dtype=torch.float32, device=dev)
         nv.check(L.dgcnn_bn_act_bwd_planes(z.data_ptr(), 0, beta.data_ptr(), g.data_ptr(), P, Cout, mean.data_ptr(),
                                            rstd.data_ptr(), nv.ptr(gb), ctx.grows, int(ctx.relu), nv.ptr(gz),
-                                           pg.data_ptr(), gbeta.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           pg.data_ptr(), pg.shape[0], gbeta.data_ptr(), ws.data_ptr(), ws.numel(),
                                            nv.stream_ptr(dev)), "bn_act_bwd_planes")
         gw = _tc_gemm_raw(planes, pg, K, Cout, P, 1, 0) if ctx.needs_input_grad[0] else None   # X^T . g_z
         ggb = gz.view(gb.shape[0], ctx.grows, Cout).sum(dim=1) if gb is not None else None
@@ -437,7 +474,9 @@ class _EdgeConvGather(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, uv, idx, beta, B, N, k, sink_key=None):
-        uv = nv.require_cuda(uv, "uv", uv.dtype if uv.dtype in (torch.float32, torch.bfloat16) else torch.float32)
+        uv = nv.require_cuda(uv, "uv")
+        if _precision == "bf16" and _bf16_table is not None:
+            uv = uv.to(_bf16_table)        # the gathered table in bf16: half the L2 gather bytes (fp32 arithmetic)
         idx = nv.require_cuda(idx, "idx", torch.int32)
         beta = nv.require_cuda(beta, "beta")
         P, F2 = uv.shape
@@ -445,7 +484,7 @@ class _EdgeConvGather(torch.autograd.Function):
         dev = uv.device
         L = nv.lib()
         st = nv.stream_ptr(dev)
-        dt = nv.DT_BF16 if uv.dtype == torch.bfloat16 else nv.DT_F32
+        dt = {torch.bfloat16: nv.DT_BF16, torch.float16: nv.DT_F16}.get(uv.dtype, nv.DT_F32)
         ws = nv.workspace(dev, L.dgcnn_edgeconv_workspace_bytes(F), "stats")
         mean = torch.empty(F, dtype=torch.float32, device=dev)
         rstd = torch.empty(F, dtype=torch.float32, device=dev)
@@ -467,8 +506,7 @@ class _EdgeConvGather(torch.autograd.Function):
         sp, sld, spe = (0, 0, 0)
         if sink is not None:
             pl, col = sink
-            sp, sld = pl.data_ptr() + 2 * col, pl.shape[2]
-            spe = pl.shape[1] * pl.shape[2] if pl.shape[0] == 2 else 0
+            sp, sld, spe = pl.data_ptr() + 2 * col, pl.shape[2], _pe(pl)
         nv.check(L.dgcnn_edgeconv_fwd_apply(uv.data_ptr(), dt, idx.data_ptr(), B, N, F, k, mean.data_ptr(),
                                             rstd.data_ptr(), beta.data_ptr(), both.data_ptr(), nv.ptr(zmax), nv.ptr(npos), sp,
                                             sld, spe, st), "edgeconv_fwd_apply")
@@ -511,8 +549,6 @@ class _EdgeConvGather(torch.autograd.Function):
         if ev is not None:
             ev[1].record()
             _ec_bwd_events.append((B, N, F, k, ev[0], ev[1]))
-        if uv.dtype != torch.float32:
-            guv = guv.to(uv.dtype)
         return guv, None, s1, None, None, None, None
 
 
@@ -538,7 +574,7 @@ class _BnAct(torch.autograd.Function):
         n_s, s_ptr, s_ld, s_pe, s_lst = (0, None, None, None, [])
         if sk is not None and sink_key is not None and C % 4 == 0:
             n_s, s_ptr, s_ld, s_pe, s_lst = sk.sink_args(sink_key)
-            if any(tuple(pl.shape[:2]) != (2, P) for pl, _ in s_lst):
+            if any(pl.shape[1] != P for pl, _ in s_lst):
                 n_s, s_lst = 0, []
         nv.check(L.dgcnn_bn_act_fwd_sinks(z.data_ptr(), P, C, beta.data_ptr(), nv.ptr(res), nv.ptr(gb), grows,
                                           int(bool(relu_flag)), out.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
@@ -723,7 +759,7 @@ def edge_conv(point_cloud, k, num_filters, trainable, activation=relu, debug=Fal
     if debug: _dbg(debug, torch.empty(B, N, k, 2 * C, device="meta"), _cur_scope() + "/edges (never materialised)")
     w0, b0 = _conv_bn_vars("conv0", 2 * C, F, trainable, x.device)              # ops.py:47-54
     wp = torch.cat([w0[:C] - w0[C:], w0[C:]], dim=1)                            # [C, 2F] = [Wa-Wb | Wb]
-    uv = _Conv1x1.apply(x.reshape(B * N, C), wp)   # exact fp32 SIMT: the next layer's kNN is built on these features
+    uv = _Conv1x1.apply(x.reshape(B * N, C), wp, not _bf16_uv_gemm)   # f32 mode: exact fp32 SIMT (the next layer's kNN is built on it)
     li = _sinks.layer if _sinks is not None else -1
     net_max, net_mean, net = _EdgeConvGather.apply(uv, idx, b0, B, N, k, ("ec", li, "both"))   # ops.py:53-58
     if debug: _dbg(debug, torch.empty(B, N, k, F, device="meta"), _cur_scope() + "/conv0 (never materialised)")

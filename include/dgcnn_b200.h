@@ -78,24 +78,28 @@ size_t dgcnn_gemm_workspace_bytes(int M, int N, int K, int transA, int transB);
 int dgcnn_gemm(const float* A, const float* B, float* C, int M, int N, int K, int transA, int transB,
                void* ws, size_t ws_bytes, dgcnn_stream_t stream);
 
-/* ---- the same GEMM on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), fp32-faithful ("bf16x3") -----------
- * Operands are pre-split fp32 -> two bf16 planes, planes[0] = bf16(x), planes[1] = bf16(x - planes[0]), stored
- * back to back ([2][rows][cols], same row-major layout as the fp32 source); the kernel accumulates
- * hi.hi + hi.lo + lo.hi in fp32 (relative error ~2^-17 per product).  M, N, K multiples of 8; all pointers
- * 16-byte aligned.  transA / transB as in dgcnn_gemm; no transposed copies are ever made.                     */
-/* x [rows, cols] fp32 at row pitch ldx -> planes: hi at planes[r*ldo + c], lo at planes[plane_elems + r*ldo + c].
- * With ldo > cols several sources fill column slices of one operand (concat by construction).              */
+/* ---- the same GEMM on the 5th-gen tensor cores (tcgen05 + TMEM + TMA) ---------------------------------------
+ * planes = 2, fp32-faithful ("bf16x3"): operands are pre-split fp32 -> two bf16 planes, planes[0] = bf16(x),
+ *   planes[1] = bf16(x - planes[0]), stored back to back ([2][rows][cols], same row-major layout as the fp32
+ *   source); the kernel accumulates hi.hi + hi.lo + lo.hi in fp32 (relative error ~2^-17 per product).
+ * planes = 1, plain bf16 (the reduced-precision variant, BASELINE.json configs[2]): only planes[0] exists
+ *   ([1][rows][cols]); one MMA per k-slice, fp32 accumulation.  Both operands of a call use the same mode.
+ * M, N, K multiples of 8; all pointers 16-byte aligned.  transA / transB as in dgcnn_gemm; no transposed copies.  */
+/* x [rows, cols] fp32 at row pitch ldx -> planes: hi at planes[r*ldo + c], lo at planes[plane_elems + r*ldo + c]
+ * (plane_elems == 0: hi only, the plain-bf16 operand).  With ldo > cols several sources fill column slices of one
+ * operand (concat by construction).  The same convention (plane distance 0 = hi only) holds for every "sink" below. */
 int dgcnn_split_bf16(const float* x, int64_t rows, int cols, int64_t ldx, void* planes, int64_t ldo,
                      int64_t plane_elems, dgcnn_stream_t stream);
 size_t dgcnn_tc_gemm_workspace_bytes(int M, int N, int K);
 int dgcnn_tc_gemm(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA, int transB,
-                  void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+                  int planes, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
 
 /* Same product with op(A) taken from a column slice of a wider pair of planes: a_planes points at the first element
  * of the slice, rows are a_ld elements apart and the lo plane starts a_plane_elems elements after the hi plane (the
  * operand a producer already filled for another layer is reused, e.g. for a weight gradient X^T.g).              */
 int dgcnn_tc_gemm_a_slice(const void* a_planes, int64_t a_ld, int64_t a_plane_elems, const void* b_planes, float* C,
-                          int M, int N, int K, int transA, int transB, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
+                          int M, int N, int K, int transA, int transB, int planes, void* ws, size_t ws_bytes,
+                          dgcnn_stream_t stream);
 
 /* Same product plus, from the accumulator, the per-column sum and sum of squares of every 128-row tile:
  * colstats [ceil(M/128)][2][N] fp32 (train-mode BatchNorm statistics of the layer output, slim.batch_norm at
@@ -103,20 +107,20 @@ int dgcnn_tc_gemm_a_slice(const void* a_planes, int64_t a_ld, int64_t a_plane_el
  * without a k-split (dgcnn_tc_gemm_stats_supported(M,N,K) == 1: N % 256 == 0, M >= 128).                       */
 int dgcnn_tc_gemm_stats_supported(int M, int N, int K);
 int dgcnn_tc_gemm_stats(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,
-                        int transB, float* colstats, dgcnn_stream_t stream);
+                        int transB, int planes, float* colstats, dgcnn_stream_t stream);
 
 /* Same product, but column ranges [starts[g], starts[g]+widths[g]) of the result go to separate contiguous
  * [M, widths[g]] buffers outs[g] (host arrays of n_groups <= 32 entries; 32-column aligned ranges).  Used for the
  * gradient of a multi-source (concatenated) operand: every source receives its own dense gradient tensor.   */
 int dgcnn_tc_gemm_grouped(const void* a_planes, const void* b_planes, int M, int N, int K, int transA, int transB,
-                          int n_groups, const int* starts, const int* widths, float* const* outs,
+                          int planes, int n_groups, const int* starts, const int* widths, float* const* outs,
                           dgcnn_stream_t stream);
 
 /* ---- fused EdgeConv core: ops.py:45-57 (edges -> conv0 -> BN(train) -> ReLU -> max_k, mean_k) ; ops.py:58 concat
  * Uses [x_i, x_j - x_i].[Wa;Wb] = x_i.(Wa-Wb) + x_j.Wb: the caller first forms
  * uv[P, 2F] = x[P,C] . [Wa-Wb | Wb] (P = B*N), so that z_ij = u_i + v_{idx(i,j)} and the [B,N,k,2C] / [B,N,k,F]
- * tensors are never materialised.  uv is fp32 (uv_dtype DGCNN_F32) or bf16 (DGCNN_BF16, the reduced-precision
- * variant: half the gather bytes; all arithmetic and every other tensor stay fp32); 16-byte aligned.
+ * tensors are never materialised.  uv is fp32 (uv_dtype DGCNN_F32) or, for the reduced-precision variant, fp16 / bf16
+ * (DGCNN_F16 / DGCNN_BF16: half the gather bytes; all arithmetic and every other tensor stay fp32); 16-byte aligned.
  * Three gather passes per layer (two forward, one backward):
  *   fwd_stats : BN batch statistics of z over all B*N*k edges: mean[F], rstd[F] = 1/sqrt(var_biased + 1e-3)
  *   fwd_apply : out_both[P,2F] = ( relu(bn(max_j z_ij)) | mean_j relu(bn(z_ij)) )  -- ops.py:58's concat in place;
@@ -134,6 +138,7 @@ int dgcnn_tc_gemm_grouped(const void* a_planes, const void* b_planes, int M, int
  *               equally among exact ties (tf.reduce_max's gradient).                                             */
 #define DGCNN_F32 0
 #define DGCNN_BF16 1
+#define DGCNN_F16 2
 size_t dgcnn_edgeconv_workspace_bytes(int F);
 int dgcnn_edgeconv_fwd_stats(const void* uv, int uv_dtype, const int32_t* idx, int B, int N, int F, int k, float* mean,
                              float* rstd, void* ws, size_t ws_bytes, dgcnn_stream_t stream);
@@ -177,7 +182,7 @@ int dgcnn_bn_act_bwd_gb(const float* z, const float* out, const float* g_out, in
  *   stats_from_tiles : colstats [tiles][2][C] (per 128-row tile: column sum, column sum of squares of z) -> mean, rstd,
  *                      including the per-group bias analytically (group_rows % 128 == 0)
  *   apply_fwd        : out = act((z [+ bias_g] - mean) * rstd + beta [+ residual]) with given statistics
- *   bwd_planes       : dgcnn_bn_act_bwd_gb whose g_z leaves as bf16 hi/lo planes [2][rows][C] -- the operand format of
+ *   bwd_planes       : dgcnn_bn_act_bwd_gb whose g_z leaves as bf16 planes [n_planes][rows][C] -- the operand format of
  *                      the weight / input gradient GEMMs -- and, only if g_z != NULL, also as fp32.  out may be NULL
  *                      (layers without residual): the ReLU mask is then re-evaluated from z, mean, rstd, beta      */
 int dgcnn_bn_stats_from_tiles(const float* colstats, int tiles, int C, int64_t rows, const float* group_bias,
@@ -198,7 +203,7 @@ int dgcnn_bn_apply_fwd_sinks(const float* z, int64_t rows, int C, const float* b
                              const int64_t* sink_plane_elems, dgcnn_stream_t stream);
 int dgcnn_bn_act_bwd_planes(const float* z, const float* out, const float* beta, const float* g_out, int64_t rows, int C,
                             const float* mean, const float* rstd, const float* group_bias, int group_rows, int relu,
-                            float* g_z, void* g_z_planes, float* g_beta, void* ws, size_t ws_bytes,
+                            float* g_z, void* g_z_planes, int n_planes, float* g_beta, void* ws, size_t ws_bytes,
                             dgcnn_stream_t stream);
 
 /* ---- global max over the points of each cloud: gen_nn_ops.max_pool_v2 ksize [1,N,1,1], model.py:77 ----------

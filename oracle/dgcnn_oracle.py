@@ -168,10 +168,44 @@ def bn_train(t: torch.Tensor, beta: torch.Tensor) -> torch.Tensor:
     return (t - mean) / torch.sqrt(var + BN_EPS) + beta
 
 
+class _BF16MatMul(torch.autograd.Function):
+    """matmul whose operands (forward: input and weights; backward: the incoming gradient too) are rounded to bf16 and
+    whose accumulation is fp32 -- what a bf16 tensor-core execution of the reference's 1x1 convolutions computes."""
+
+    @staticmethod
+    def forward(ctx, a, w):
+        ab, wb = a.bfloat16().to(a.dtype), w.bfloat16().to(w.dtype)
+        ctx.save_for_backward(ab, wb)
+        return ab @ wb
+
+    @staticmethod
+    def backward(ctx, g):
+        ab, wb = ctx.saved_tensors
+        gb = g.bfloat16().to(g.dtype)
+        return gb @ wb.t(), ab.reshape(-1, ab.shape[-1]).t() @ gb.reshape(-1, gb.shape[-1])
+
+
+_bf16_matmul = False
+
+
+class bf16_matmul(object):
+    """with bf16_matmul(): every conv_bn inside runs its matmul on bf16-rounded operands (the yardstick for the
+    reduced-precision variant of BASELINE.json configs[2]: how far a bf16 execution of the reference graph itself is
+    from the fp32 one)."""
+
+    def __enter__(self):
+        global _bf16_matmul
+        self._old, _bf16_matmul = _bf16_matmul, True
+
+    def __exit__(self, *a):
+        global _bf16_matmul
+        _bf16_matmul = self._old
+
+
 def conv_bn(t: torch.Tensor, P: Dict[str, torch.Tensor], scope: str, relu: bool = True) -> torch.Tensor:
     """slim.conv2d(kernel 1, stride 1, VALID, normalizer_fn=batch_norm): 1x1 conv == matmul on the
     channel axis, no bias, BN, then activation_fn (default relu) AFTER BN [TF-default]."""
-    z = torch.matmul(t, P[scope + "/weights"])
+    z = _BF16MatMul.apply(t, P[scope + "/weights"]) if _bf16_matmul else torch.matmul(t, P[scope + "/weights"])
     y = bn_train(z, P[scope + "/BatchNorm/beta"])
     return torch.relu(y) if relu else y
 

@@ -30,7 +30,7 @@ for name, (M, N, K, tA, tB) in {"FC0 fwd": (P, 512, 1792, 0, 0), "FC0 dX": (P, 1
     pa, pb = split(A), split(B)
     out = torch.empty((M, N), device=dev)
     ws = torch.empty(max(L.dgcnn_tc_gemm_workspace_bytes(M, N, K), 16), dtype=torch.uint8, device=dev)
-    f = lambda: nv.check(L.dgcnn_tc_gemm(pa.data_ptr(), pb.data_ptr(), out.data_ptr(), M, N, K, tA, tB, ws.data_ptr(), ws.numel(), nv.stream_ptr(dev)), "g")
+    f = lambda: nv.check(L.dgcnn_tc_gemm(pa.data_ptr(), pb.data_ptr(), out.data_ptr(), M, N, K, tA, tB, 2, ws.data_ptr(), ws.numel(), nv.stream_ptr(dev)), "g")
     t = timeit(f)
     ts = timeit(lambda: split(A))
     opA = A.t() if tA else A

@@ -23,7 +23,7 @@ def test_header_symbols_exported(dg):
     for n in names:
         assert hasattr(lib, n), "missing export %s" % n
     assert sorted(_native.SIGNATURES) == names  # the ctypes table covers the whole header, nothing else
-    assert lib.dgcnn_abi_version() == 1
+    assert lib.dgcnn_abi_version() == 2
 
 
 def test_workspace_queries_are_pure(dg):

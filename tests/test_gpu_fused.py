@@ -38,7 +38,7 @@ def test_wide_gemm_column_statistics(dg, cuda, M, N, K):
     C = torch.empty((M, N), device=cuda)
     cs = torch.empty((tiles, 2, N), device=cuda)
     pa, pb = _split(A), _split(B)
-    nv.check(L.dgcnn_tc_gemm_stats(pa.data_ptr(), pb.data_ptr(), C.data_ptr(), M, N, K, 0, 0, cs.data_ptr(),
+    nv.check(L.dgcnn_tc_gemm_stats(pa.data_ptr(), pb.data_ptr(), C.data_ptr(), M, N, K, 0, 0, 2, cs.data_ptr(),
                                    nv.stream_ptr(cuda)), "tc_gemm_stats")
     ref = A.double() @ B.double()
     scale = float(np.sqrt(K)) * 9.0
@@ -93,7 +93,7 @@ def test_bn_backward_planes_equal_fp32_path(dg, cuda):
     planes = torch.empty((2, P, C), dtype=torch.bfloat16, device=cuda)
     gz, gb = torch.empty_like(z), torch.empty(C, device=cuda)
     nv.check(L.dgcnn_bn_act_bwd_planes(z.data_ptr(), 0, beta.data_ptr(), go.data_ptr(), P, C, mean.data_ptr(),
-                                       rstd.data_ptr(), 0, 0, 1, gz.data_ptr(), planes.data_ptr(), gb.data_ptr(),
+                                       rstd.data_ptr(), 0, 0, 1, gz.data_ptr(), planes.data_ptr(), 2, gb.data_ptr(),
                                        ws.data_ptr(), ws.numel(), st), "bwd planes")
     assert torch.equal(gz, gz_ref) and torch.equal(gb, gb_ref)
     rec = planes[0].float() + planes[1].float()

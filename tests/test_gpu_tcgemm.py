@@ -24,7 +24,7 @@ def _tc(dg, A, B, M, N, K, tA, tB):
     need = L.dgcnn_tc_gemm_workspace_bytes(M, N, K)
     ws = torch.empty(max(need, 16), dtype=torch.uint8, device=A.device)
     pa, pb = _split(dg, A), _split(dg, B)
-    nv.check(L.dgcnn_tc_gemm(pa.data_ptr(), pb.data_ptr(), out.data_ptr(), M, N, K, tA, tB, ws.data_ptr(), ws.numel(),
+    nv.check(L.dgcnn_tc_gemm(pa.data_ptr(), pb.data_ptr(), out.data_ptr(), M, N, K, tA, tB, 2, ws.data_ptr(), ws.numel(),
                              nv.stream_ptr(A.device)), "tc_gemm")
     return out
 
@@ -78,8 +78,8 @@ def test_tc_gemm_weight_gradient_split_k(dg, cuda):
 def test_tc_gemm_rejects_bad_shapes(dg, cuda):
     from dgcnn import _native as nv
     x = torch.zeros(64, device=cuda)
-    assert nv.lib().dgcnn_tc_gemm(x.data_ptr(), x.data_ptr(), x.data_ptr(), 12, 8, 8, 0, 0, None, 0, None) == nv.ERR_UNSUPPORTED
-    assert nv.lib().dgcnn_tc_gemm(None, x.data_ptr(), x.data_ptr(), 8, 8, 8, 0, 0, None, 0, None) == nv.ERR_INVALID
+    assert nv.lib().dgcnn_tc_gemm(x.data_ptr(), x.data_ptr(), x.data_ptr(), 12, 8, 8, 0, 0, 2, None, 0, None) == nv.ERR_UNSUPPORTED
+    assert nv.lib().dgcnn_tc_gemm(None, x.data_ptr(), x.data_ptr(), 8, 8, 8, 0, 0, 2, None, 0, None) == nv.ERR_INVALID
 
 
 @pytest.mark.parametrize("M,N,K", [(130, 70, 33), (256, 128, 64), (49, 8, 1030), (64, 128, 4096), (1000, 64, 128)])
@@ -132,3 +132,33 @@ def test_global_max_pool_matches_amax(dg, cuda):
     (ya * w).sum().backward()
     (yb * w).sum().backward()
     assert torch.allclose(a.grad, b.grad, atol=1e-6)
+
+
+@pytest.mark.parametrize("M,N,K,tA,tB", [(1024, 128, 64, 0, 0), (4096, 512, 320, 0, 0), (2048, 64, 128, 0, 1),
+                                          (128, 64, 8192, 1, 0), (2816, 512, 4096, 1, 0)])
+def test_tc_gemm_single_plane_bf16(dg, cuda, M, N, K, tA, tB):
+    """planes = 1 (BASELINE.json configs[2]'s bf16 arithmetic): one MMA per product on the hi plane only.  Against fp64 on
+    the bf16-ROUNDED operands the result is exact up to fp32 accumulation."""
+    from dgcnn import _native as nv
+    L = nv.lib()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn((K, M) if tA else (M, K), generator=g).to(cuda)
+    B = torch.randn((N, K) if tB else (K, N), generator=g).to(cuda)
+    pa = torch.empty((1,) + tuple(A.shape), dtype=torch.bfloat16, device=cuda)
+    pb = torch.empty((1,) + tuple(B.shape), dtype=torch.bfloat16, device=cuda)
+    for x, p in ((A, pa), (B, pb)):
+        nv.check(L.dgcnn_split_bf16(x.data_ptr(), x.shape[0], x.shape[1], x.shape[1], p.data_ptr(), x.shape[1], 0,
+                                    nv.stream_ptr(cuda)), "split")
+        assert torch.equal(p[0], x.to(torch.bfloat16))
+    out = torch.empty((M, N), device=cuda)
+    need = L.dgcnn_tc_gemm_workspace_bytes(M, N, K)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=cuda)
+    nv.check(L.dgcnn_tc_gemm(pa.data_ptr(), pb.data_ptr(), out.data_ptr(), M, N, K, tA, tB, 1, ws.data_ptr(), ws.numel(),
+                             nv.stream_ptr(cuda)), "tc_gemm")
+    a64 = pa[0].double().t() if tA else pa[0].double()
+    b64 = pb[0].double().t() if tB else pb[0].double()
+    ref = a64 @ b64
+    assert (out.double() - ref).abs().max().item() <= 2e-6 * np.sqrt(K) * 9.0 + 1e-6 * ref.abs().max().item()
+    # mixing modes is refused
+    assert L.dgcnn_tc_gemm(pa.data_ptr(), pb.data_ptr(), out.data_ptr(), M, N, K, tA, tB, 3, ws.data_ptr(), ws.numel(),
+                           nv.stream_ptr(cuda)) == nv.ERR_INVALID
