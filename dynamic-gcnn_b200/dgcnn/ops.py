@@ -14,6 +14,7 @@ Every hot-path op calls hand-written sm_100a CUDA through the C ABI in include/d
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -226,13 +227,15 @@ class _Conv1x1(torch.autograd.Function):
         ctx.npl = _npl()
         P, Cin = a.shape
         Cout = w.shape[1]
-        if ctx.npl == 1 and _tc_ok(P, Cin, Cout) and not exact:
-            # reduced-precision variant: the forward takes the tensor cores too (one bf16 MMA per product)
-            pw = _split(w, 1)
-            if ctx.a_planes is not None and ctx.a_planes[0].shape[0] == 1:
+        have = ctx.a_planes is not None and ctx.a_planes[0].shape[0] == ctx.npl
+        if _tc_ok(P, Cin, Cout) and not exact and (ctx.npl == 1 or (have and _TC_FORWARD)):
+            # bf16 mode: every 1x1 conv takes the tensor cores (one bf16 MMA per product).
+            # f32 mode: exact SIMT kernel, unless the A/B switch _TC_FORWARD is on (see its comment).
+            pw = _split(w, ctx.npl)
+            if have:
                 pl, col = ctx.a_planes
                 return _tc_gemm_a_slice_raw(pl, col, pw, P, Cout, Cin, 0, 0)
-            return _tc_gemm_raw(_split(a, 1), pw, P, Cout, Cin, 0, 0)
+            return _tc_gemm_raw(_split(a, ctx.npl), pw, P, Cout, Cin, 0, 0)
         return _gemm_raw(a, w, P, Cout, Cin, 0, 0)
 
     @staticmethod
@@ -265,6 +268,11 @@ class _Conv1x1(torch.autograd.Function):
 
 # ---- tensor-core path: tcgen05 GEMM on pre-split bf16 hi/lo planes (fp32-faithful, csrc/tc_gemm.cu) -------------
 TC_MIN_ROWS = 1024  # below this the SIMT kernel wins (launch + split overhead)
+# A/B switch (default OFF): conv1 forward on the fp32-faithful tensor-core GEMM, reading the planes its producer left in
+# the FC0 operand.  Measured at configs[1]: 0.03 ms/step faster, but the 2^-16 operand error of `net` is amplified by the
+# next layer's neighbour differences (x_j - x_i): same-graph logits 9e-5 -> 7e-4 from the fp32 oracle, gradients 6x
+# further from fp64 than fp32 arithmetic is.  The EdgeConv stack therefore stays on exact fp32 GEMMs in f32 mode.
+_TC_FORWARD = os.environ.get("DGCNN_TC_FORWARD", "0") == "1"
 
 
 def _tc_ok(P: int, *dims: int) -> bool:
@@ -464,6 +472,28 @@ def conv1x1(srcs, w) -> torch.Tensor:
         return _ConcatConvTC.apply(w, *srcs)
     a = srcs[0] if len(srcs) == 1 else torch.cat(srcs, dim=1)
     return _Conv1x1.apply(a, w)
+
+
+class _EdgeWeights(torch.autograd.Function):
+    """conv0's weights W0 = [Wa ; Wb] ([2C, F], ops.py:47-54) -> the uv operand [Wa - Wb | Wb] ([C, 2F]) of
+    [x_i, x_j - x_i].W0 = x_i.(Wa - Wb) + x_j.Wb.  Two small kernels each way (slicing / cat / neg through autograd
+    took eleven)."""
+
+    @staticmethod
+    def forward(ctx, w0):
+        C, F = w0.shape[0] // 2, w0.shape[1]
+        wp = torch.empty((C, 2 * F), dtype=w0.dtype, device=w0.device)
+        torch.sub(w0[:C], w0[C:], out=wp[:, :F])
+        wp[:, F:].copy_(w0[C:])
+        return wp
+
+    @staticmethod
+    def backward(ctx, g):
+        C, F = g.shape[0], g.shape[1] // 2
+        gw = torch.empty((2 * C, F), dtype=g.dtype, device=g.device)
+        gw[:C].copy_(g[:, :F])                       # d/dWa
+        torch.sub(g[:, F:], g[:, :F], out=gw[C:])    # d/dWb
+        return gw
 
 
 class _EdgeConvGather(torch.autograd.Function):
@@ -758,8 +788,11 @@ def edge_conv(point_cloud, k, num_filters, trainable, activation=relu, debug=Fal
         _knn_out.append(idx)
     if debug: _dbg(debug, torch.empty(B, N, k, 2 * C, device="meta"), _cur_scope() + "/edges (never materialised)")
     w0, b0 = _conv_bn_vars("conv0", 2 * C, F, trainable, x.device)              # ops.py:47-54
-    wp = torch.cat([w0[:C] - w0[C:], w0[C:]], dim=1)                            # [C, 2F] = [Wa-Wb | Wb]
-    uv = _Conv1x1.apply(x.reshape(B * N, C), wp, not _bf16_uv_gemm)   # f32 mode: exact fp32 SIMT (the next layer's kNN is built on it)
+    wp = _EdgeWeights.apply(w0)                                                 # [C, 2F] = [Wa-Wb | Wb]
+    # f32 mode: the uv GEMM stays on the exact fp32 SIMT kernel.  z_ij = u_i + v_j carries its information in the small
+    # differences between neighbours' v rows (the reference subtracts x_j - x_i BEFORE the conv), so an operand error of
+    # 2^-16 (bf16 hi/lo planes) would be amplified by the cancellation.
+    uv = _Conv1x1.apply(x.reshape(B * N, C), wp, (not _bf16_uv_gemm) if _precision == "bf16" else True)
     li = _sinks.layer if _sinks is not None else -1
     net_max, net_mean, net = _EdgeConvGather.apply(uv, idx, b0, B, N, k, ("ec", li, "both"))   # ops.py:53-58
     if debug: _dbg(debug, torch.empty(B, N, k, F, device="meta"), _cur_scope() + "/conv0 (never materialised)")

@@ -164,7 +164,23 @@ class trainval(object):
 
     def _tower_step_eager(self, pts, lab, wgt, G):
         _, acc, loss = self._forward(pts, lab, wgt, want_softmax=False)
-        (loss / G).backward()                                   # grads mean over towers: trainval.py:64-69
+        # Every variable's .grad is a view into the flat gradient buffer.  Left in place, autograd would add into each of
+        # them with its own small kernel (one per variable); instead the views step aside, backward hands over fresh
+        # gradient tensors, and ONE multi-tensor kernel adds them, scaled by 1/len(GPUS) (the tower mean of
+        # trainval.py:64-69), into the flat buffer.
+        st = self._store
+        params = [st.vars[n] for n in st.trainable_names()]
+        views = [p.grad for p in params]
+        for p in params:
+            p.grad = None
+        try:
+            loss.backward()
+            pairs = [(v, p.grad) for v, p in zip(views, params) if p.grad is not None]
+        finally:
+            for p, v in zip(params, views):
+                p.grad = v
+        if pairs:
+            torch._foreach_add_([v for v, _ in pairs], [g for _, g in pairs], alpha=1.0 / G)
         return acc.detach(), loss.detach()
 
     def _tower_step(self, data_i, label_i, weight_i, G):
