@@ -385,7 +385,7 @@ namespace dgcnn {
 // knn_tc.cu: tensor-core filter + exact refinement
 bool knn_tc_eligible(int B, int N, int C, int k);
 size_t knn_tc_bytes(int B, int N, int C, int k_max);
-int knn_tc_run(const float* x, int32_t* idx, int B, int N, int C, int k, void* ws, cudaStream_t st);
+int knn_tc_run(const float* x, int32_t* idx, int B, int N, int C, int k, int filter_mode, void* ws, cudaStream_t st);
 static inline size_t knn_base_bytes(int B, int N, int C) {
   const size_t Npad = npad_of(N);
   return ((((size_t)B * C * Npad + (size_t)B * Npad) * sizeof(float)) + 255) & ~(size_t)255;
@@ -422,7 +422,14 @@ extern "C" int dgcnn_knn(const float* x, int32_t* idx, int B, int N, int C, int 
 
 extern "C" int dgcnn_knn_hinted(const float* x, const int32_t* hint, int32_t* idx, int B, int N, int C, int k,
                                 void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
+  return dgcnn_knn_mode(x, hint, idx, B, N, C, k, DGCNN_KNN_AUTO, ws, ws_bytes, stream);
+}
+
+extern "C" int dgcnn_knn_mode(const float* x, const int32_t* hint, int32_t* idx, int B, int N, int C, int k,
+                              int filter_mode, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  DG_REQUIRE(filter_mode >= DGCNN_KNN_AUTO && filter_mode <= DGCNN_KNN_FINE, DGCNN_ERR_INVALID,
+             "knn: filter_mode must be DGCNN_KNN_AUTO, _COARSE or _FINE");
   DG_REQUIRE(idx, DGCNN_ERR_INVALID, "knn: null output");
   DG_REQUIRE(k >= 1 && k <= N, DGCNN_ERR_INVALID, "knn: need 1 <= k <= N (k=%d, N=%d)", k, N);
   DG_REQUIRE(k <= DGCNN_KNN_MAX_K, DGCNN_ERR_UNSUPPORTED, "knn: k=%d > %d", k, DGCNN_KNN_MAX_K);
@@ -434,7 +441,7 @@ extern "C" int dgcnn_knn_hinted(const float* x, const int32_t* hint, int32_t* id
                "knn: workspace must be 256-byte and x 16-byte aligned");
     DG_REQUIRE(ws_bytes >= dgcnn_knn_workspace_bytes(B, N, C), DGCNN_ERR_WORKSPACE, "knn: workspace %zu < %zu bytes",
                ws_bytes, dgcnn_knn_workspace_bytes(B, N, C));
-    return knn_tc_run(x, idx, B, N, C, k, reinterpret_cast<unsigned char*>(ws) + knn_base_bytes(B, N, C), st);
+    return knn_tc_run(x, idx, B, N, C, k, filter_mode, reinterpret_cast<unsigned char*>(ws) + knn_base_bytes(B, N, C), st);
   }
   float *xT = nullptr, *s = nullptr;
   int Npad = 0;

@@ -792,7 +792,7 @@ size_t knn_tc_bytes(int B, int N, int C, int k_max) {
          al256(P * 4 * k2_cap(k_max) * 2) + al256(P * 4) + al256((4 * P + 1) * 4);
 }
 
-int knn_tc_run(const float* x, int32_t* idx, int B, int N, int C, int k, void* ws, cudaStream_t st) {
+int knn_tc_run(const float* x, int32_t* idx, int B, int N, int C, int k, int filter_mode, void* ws, cudaStream_t st) {
   const int Npad = ((N + 127) / 128) * 128;
   const int Cp = k2_cp(C);
   const int cap = k2_cap(k);
@@ -816,12 +816,8 @@ int knn_tc_run(const float* x, int32_t* idx, int B, int N, int C, int k, void* w
   // Precision mode of the filter.  Coarse (one fp16 product) is enough while the k-th neighbour distance is more than
   // a few percent of the squared norms; dense clouds (many points per cloud) need the hi/lo split or most rows would
   // overflow their candidate lists into the slow exact fallback.  The result is identical either way.
-  static int fine_env = -2;    // DGCNN_KNN_FINE=0|1 overrides the rule (tuning aid)
-  if (fine_env == -2) {
-    const char* e = getenv("DGCNN_KNN_FINE");
-    fine_env = e ? (atoi(e) != 0) : -1;
-  }
-  const int fine = fine_env >= 0 ? fine_env : (N > 4096 ? 1 : 0);
+  // filter_mode (dgcnn_knn_mode's argument): DGCNN_KNN_AUTO applies the rule, COARSE / FINE force a mode (A/B timing).
+  const int fine = filter_mode >= 0 ? (filter_mode != 0) : (N > 4096 ? 1 : 0);
   knn_tc_prep_kernel<<<gp, 128, (size_t)(128 * (C + 1) + C + 2) * 4, st>>>(x, part, N, Npad, C, Cp, s, sig, h, q, Pp * 16,
                                                                           Pp * Cp, fine);
   count_launch();

@@ -441,16 +441,11 @@ static int tc_gemm_impl(const void* a_planes, const void* b_planes, float* C, in
   const int kb = cdiv(K, GB_K);
   const int kper = cdiv(kb, splits);
   dim3 grid(cdiv(M, GB_M), cdiv(N, GB_N), splits);
-  static int forced = -1;  // DGCNN_TC_STAGES=1|3 overrides the heuristic (tuning aid)
-  if (forced < 0) {
-    const char* e = getenv("DGCNN_TC_STAGES");
-    forced = e ? atoi(e) : 0;
-  }
   // deep ring when the k-loop is long, or when the grid leaves SMs idle anyway (split-K weight gradients: one CTA
   // per SM at most, so the single-stage variant's 3-CTAs-per-SM overlap cannot happen and every k-block would
   // expose a full TMA round trip)
   const int64_t ctas = (int64_t)grid.x * grid.y * grid.z;
-  const int stages = forced == 1 || forced == 3 ? forced : ((kper >= 64 || (ctas <= num_sms() && kper >= 3)) ? 3 : 1);
+  const int stages = (kper >= 64 || (ctas <= num_sms() && kper >= 3)) ? 3 : 1;
 #define DG_TC_LAUNCH(AK_, BK_, ST_)                                                                          \
   do {                                                                                                       \
     static bool done_ = false;                                                                               \

@@ -259,14 +259,7 @@ int tc_wide_splits(int M, int N, int K) {
   return s < 1 ? 1 : s;
 }
 
-bool tc_wide_ok(int M, int N, int K) {
-  static int disabled = -1;
-  if (disabled < 0) {
-    const char* e = getenv("DGCNN_TC_WIDE");
-    disabled = (e && atoi(e) == 0) ? 1 : 0;
-  }
-  return !disabled && N >= 256 && (N % W_N) == 0 && M >= 128;
-}
+bool tc_wide_ok(int M, int N, int K) { return N >= 256 && (N % W_N) == 0 && M >= 128; }
 
 // C (or groups / split partials) = op(A).op(B) with the wide kernel.  colstats may be null.
 int tc_gemm_wide_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, bool a_k, bool b_k, int M, int N, int K,

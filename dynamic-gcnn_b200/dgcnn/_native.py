@@ -28,6 +28,7 @@ SIGNATURES = {
     "dgcnn_pairwise_distance": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "dgcnn_knn": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "dgcnn_knn_hinted": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "dgcnn_knn_mode": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "dgcnn_topk_rows": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "dgcnn_edge_feature": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "dgcnn_edge_feature_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -133,8 +133,8 @@ def k_nn(points: torch.Tensor, k: int, hint: Optional[torch.Tensor] = None) -> t
     if hint is not None and hint.shape[-1] >= k and hint.shape[:2] == (B, N):
         hint = nv.require_cuda(hint if hint.shape[-1] == k else hint[:, :, :k], "hint", torch.int32)
         hp = hint.data_ptr()
-    nv.check(L.dgcnn_knn_hinted(x.data_ptr(), hp, idx.data_ptr(), B, N, C, k, ws.data_ptr(), ws.numel(),
-                                nv.stream_ptr(x.device)), "k_nn")
+    nv.check(L.dgcnn_knn_mode(x.data_ptr(), hp, idx.data_ptr(), B, N, C, k, _KNN_FILTER_MODE, ws.data_ptr(), ws.numel(),
+                              nv.stream_ptr(x.device)), "k_nn")
     if ev is not None:
         ev[1].record()
         _knn_events.append((B, N, C, k, ev[0], ev[1]))
@@ -267,6 +267,10 @@ class _Conv1x1(torch.autograd.Function):
 
 
 # ---- tensor-core path: tcgen05 GEMM on pre-split bf16 hi/lo planes (fp32-faithful, csrc/tc_gemm.cu) -------------
+# A/B switch of the k_nn distance filter (host side; the library keeps no state): DGCNN_KNN_FINE=0|1 forces the coarse /
+# fine precision mode, default = the library's rule.  Same result either way.
+_KNN_FILTER_MODE = {"0": 0, "1": 1}.get(os.environ.get("DGCNN_KNN_FINE", ""), -1)
+
 TC_MIN_ROWS = 1024  # below this the SIMT kernel wins (launch + split overhead)
 # A/B switch (default OFF): conv1 forward on the fp32-faithful tensor-core GEMM, reading the planes its producer left in
 # the FC0 operand.  Measured at configs[1]: 0.03 ms/step faster, but the 2^-16 operand error of `net` is amplified by the

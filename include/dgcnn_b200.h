@@ -60,6 +60,15 @@ int dgcnn_knn(const float* x, int32_t* idx, int B, int N, int C, int k, void* ws
  * violates the precondition (the bound would be invalid).                                                      */
 int dgcnn_knn_hinted(const float* x, const int32_t* hint, int32_t* idx, int B, int N, int C, int k, void* ws,
                      size_t ws_bytes, dgcnn_stream_t stream);
+/* Same again with the precision mode of the tensor-core distance filter chosen by the caller instead of by the
+ * library's rule (AUTO: fine for clouds of more than 4096 points).  The result is identical in every mode; COARSE / FINE
+ * exist for A/B timing.  The library itself keeps no such switch: there is no environment variable or other global
+ * mutable state behind any entry point.                                                                         */
+#define DGCNN_KNN_AUTO (-1)
+#define DGCNN_KNN_COARSE 0
+#define DGCNN_KNN_FINE 1
+int dgcnn_knn_mode(const float* x, const int32_t* hint, int32_t* idx, int B, int N, int C, int k, int filter_mode,
+                   void* ws, size_t ws_bytes, dgcnn_stream_t stream);
 /* ops.py:18 on a materialised matrix: D [rows,N] -> idx [rows,k] (k smallest, same tie rule) */
 int dgcnn_topk_rows(const float* D, int32_t* idx, int64_t rows, int N, int k, dgcnn_stream_t stream);
 

@@ -38,6 +38,30 @@ __global__ void __launch_bounds__(256) scatter_regs(const int* __restrict__ idx,
   }
 }
 
+// E: pure gather -- the read-side twin of A: every point sums its k neighbour rows (256 B each) with 16-byte lanes,
+// half a warp per row, all loads of a point in flight at once; one 256-byte store per point.  The L2 gather roof of
+// ec_fwd_stats / ec_fwd_apply.
+__global__ void __launch_bounds__(256) gather_rows(const int* __restrict__ idx, const float* __restrict__ tab,
+                                                   float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, l16 = lane & 15;
+  for (int p = blockIdx.x * 8 + warp; p < P; p += gridDim.x * 8) {
+    const int base = (p / N) * N;
+    const int r = lane < K ? base + idx[p * K + lane] : 0;
+    float4 v[K / 2];
+#pragma unroll
+    for (int t = 0; t < K / 2; ++t) {
+      const int row = __shfl_sync(FULL, r, 2 * t + half);
+      v[t] = __ldg(reinterpret_cast<const float4*>(tab + (size_t)row * (2 * F) + F + 4 * l16));
+    }
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < K / 2; ++t) { s.x += v[t].x; s.y += v[t].y; s.z += v[t].z; s.w += v[t].w; }
+    s.x += __shfl_xor_sync(FULL, s.x, 16); s.y += __shfl_xor_sync(FULL, s.y, 16);
+    s.z += __shfl_xor_sync(FULL, s.z, 16); s.w += __shfl_xor_sync(FULL, s.w, 16);
+    if (half == 0) *reinterpret_cast<float4*>(out + (size_t)p * F + 4 * l16) = s;
+  }
+}
+
 // TMA bulk reduce: each warp stages its k rows (k * 256 B) in shared memory, one lane issues k bulk reductions
 __global__ void __launch_bounds__(256) scatter_bulk(const int* __restrict__ idx, const float* __restrict__ src,
                                                     float* __restrict__ dst) {
@@ -87,7 +111,7 @@ int main() {
   cudaEventCreate(&e1);
   cudaFuncSetAttribute(scatter_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * K * F * 4);
   for (int grid : {148 * 2, 148 * 4, 148 * 8}) {
-    for (int mode = 0; mode < 4; ++mode) {
+    for (int mode = 0; mode < 5; ++mode) {
       float best = 1e9f;
       for (int it = 0; it < 6; ++it) {
         cudaEventRecord(e0);
@@ -95,13 +119,14 @@ int main() {
         if (mode == 1) scatter_regs<1><<<grid, 256>>>(idx, src, dst);
         if (mode == 2) scatter_regs<2><<<grid, 256>>>(idx, src, dst);
         if (mode == 3) scatter_bulk<<<grid, 256, 8 * K * F * 4>>>(idx, src, dst);
+        if (mode == 4) gather_rows<<<grid, 256>>>(idx, dst, src);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms;
         cudaEventElapsedTime(&ms, e0, e1);
         if (it > 0 && ms < best) best = ms;
       }
-      const char* names[] = {"REDG.128 regs", "REDG.64 regs", "REDG.32 regs", "TMA bulk reduce 256B"};
+      const char* names[] = {"REDG.128 regs", "REDG.64 regs", "REDG.32 regs", "TMA bulk reduce 256B", "pure gather LDG.128"};
       printf("grid %4d  %-22s %8.1f us  (%.2f TB/s of row bytes)  err=%s\n", grid, names[mode], best * 1e3,
              (double)P * K * F * 4 / (best * 1e-3) / 1e12, cudaGetErrorString(cudaGetLastError()));
     }

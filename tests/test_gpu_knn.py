@@ -157,3 +157,22 @@ def test_knn_tensor_core_path_ties_fall_back_exactly(dg, oracle, cuda):
                             for _ in range(x.shape[0])]).int().cuda()
         assert torch.equal(dg.ops.k_nn(xc, 20, hint=ref), ref)
         assert torch.equal(dg.ops.k_nn(xc, 20, hint=hint), ref)
+
+
+def test_knn_filter_modes_agree(dg, oracle, cuda):
+    """dgcnn_knn_mode: the coarse and the fine precision mode of the tensor-core filter (and the library's own rule) give
+    the same, oracle-exact result; the switch is an argument, the library holds no state."""
+    from dgcnn import _native as nv
+    L = nv.lib()
+    g = torch.Generator().manual_seed(31)
+    x = torch.rand((2, 640, 64), generator=g)
+    ref = oracle.k_nn(x, 20)
+    xc = x.cuda()
+    ws = torch.empty(L.dgcnn_knn_workspace_bytes(2, 640, 64), dtype=torch.uint8, device=cuda)
+    for mode in (-1, 0, 1):
+        idx = torch.empty((2, 640, 20), dtype=torch.int32, device=cuda)
+        nv.check(L.dgcnn_knn_mode(xc.data_ptr(), 0, idx.data_ptr(), 2, 640, 64, 20, mode, ws.data_ptr(), ws.numel(),
+                                  nv.stream_ptr(cuda)), "knn_mode")
+        assert torch.equal(idx.cpu(), ref), mode
+    assert L.dgcnn_knn_mode(xc.data_ptr(), 0, idx.data_ptr(), 2, 640, 64, 20, 5, ws.data_ptr(), ws.numel(),
+                            nv.stream_ptr(cuda)) == nv.ERR_INVALID
