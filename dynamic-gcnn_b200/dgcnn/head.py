@@ -26,12 +26,13 @@ def conv_bn_act(srcs: List[torch.Tensor], scope: str, cout: int, trainable: bool
     cg = cloud_feature.shape[1] if cloud_feature is not None else 0
     cin = cg + sum(int(t.shape[1]) for t in srcs)
     w, b = _ops._conv_bn_vars(scope, cin, cout, trainable, srcs[0].device)
-    gb = _ops._Conv1x1.apply(cloud_feature, w[:cg]) if cg else None      # [B, cout]: tiny, SIMT; added inside BN
+    w_g, w_rest = _ops._SplitWeightRows.apply(w, cg) if cg else (None, w)
+    gb = _ops._Conv1x1.apply(cloud_feature, w_g, True) if cg else None   # [B, cout]: tiny, exact SIMT; added inside BN
     P = srcs[0].shape[0]
     if _ops._tc_ok(P, cout, *[t.shape[1] for t in srcs]):
         # the whole layer around one tcgen05 GEMM: BN statistics from its epilogue, gradients as bf16 planes
-        return _ops._ConvBnActTC.apply(w[cg:] if cg else w, b, gb, activation is not None, points_per_cloud, scope, *srcs)
-    z = _ops.conv1x1(srcs, w[cg:] if cg else w)
+        return _ops._ConvBnActTC.apply(w_rest, b, gb, activation is not None, points_per_cloud, scope, *srcs)
+    z = _ops.conv1x1(srcs, w_rest)
     return _ops._BnAct.apply(z, b, None, activation is not None, gb, None)
 
 

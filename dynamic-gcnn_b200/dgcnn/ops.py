@@ -108,6 +108,56 @@ def _layer_knn(x, k, hint=None):
     return idx
 
 
+# =============================================================================== weight gradients on a side stream
+# A weight gradient (X^T . g) has no consumer inside the backward pass: only the optimizer reads it.  When the trainer
+# enables _async_dw it is launched on a second stream, forked after the kernel that produced g: the tensor-bound dW
+# GEMMs of the head then overlap the HBM-bound BatchNorm-backward / EdgeConv-gather kernels of the layers below instead
+# of extending the critical path (in a captured CUDA graph the fork / join become graph edges).  The caller of backward
+# joins with join_side_stream() before it reads any gradient; generic autograd users leave the switch off.
+_async_dw = False
+_side_streams = {}
+_side_keep = []       # tensors the side stream still reads: kept alive until the join (no allocator reuse under it)
+
+
+class _SideStream(object):
+    """with _SideStream(dev, keep...): the body's launches go to the side stream, ordered after everything already
+    queued on the current stream.  No-op unless _async_dw."""
+
+    def __init__(self, dev, *keep):
+        self.dev, self.keep, self.ctx = dev, keep, None
+
+    def __enter__(self):
+        if _async_dw:
+            key = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
+            side = _side_streams.get(key)
+            if side is None:
+                side = _side_streams[key] = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            _side_keep.extend(t for t in self.keep if t is not None)
+            self.ctx = torch.cuda.stream(side)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def ws_tag(base: str) -> str:
+    """scratch buffers are per stream: the side stream must not share the main stream's split-K workspace"""
+    return base + "_side" if (_async_dw and torch.cuda.current_stream() in _side_streams.values()) else base
+
+
+def join_side_stream(dev) -> None:
+    """current stream waits for every weight gradient launched on the side stream"""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    side = _side_streams.get(key)
+    if side is not None:
+        torch.cuda.current_stream(dev).wait_stream(side)
+    del _side_keep[:]
+
+
 # =============================================================================== raw kernels
 def k_nn(points: torch.Tensor, k: int, hint: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ops.py:8-19.  Fused distance + top-k; the [B,N,N] matrix is never written.  Not differentiable
@@ -208,7 +258,7 @@ def _gemm_raw(A, Bm, M, N, K, tA, tB):
     L = nv.lib()
     out = torch.empty((M, N), dtype=torch.float32, device=A.device)
     need = L.dgcnn_gemm_workspace_bytes(M, N, K, tA, tB)
-    ws = nv.workspace(A.device, need, "gemm") if need else None
+    ws = nv.workspace(A.device, need, ws_tag("gemm")) if need else None
     nv.check(L.dgcnn_gemm(A.data_ptr(), Bm.data_ptr(), out.data_ptr(), M, N, K, tA, tB, nv.ptr(ws),
                           ws.numel() if ws is not None else 0, nv.stream_ptr(A.device)), "gemm")
     return out
@@ -253,16 +303,19 @@ class _Conv1x1(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 ga = _tc_gemm_raw(pg, _split(w, npl), P, Cin, Cout, 0, 1)
             if ctx.needs_input_grad[1]:
-                if ctx.a_planes is not None and ctx.a_planes[0].shape[0] == npl:
-                    pl, col = ctx.a_planes
-                    gw = _tc_gemm_a_slice_raw(pl, col, pg, Cin, Cout, P, 1, 0)
-                else:
-                    gw = _tc_gemm_raw(_split(a, npl), pg, Cin, Cout, P, 1, 0)
+                have = ctx.a_planes is not None and ctx.a_planes[0].shape[0] == npl
+                with _SideStream(g.device, pg, a, ctx.a_planes[0] if have else None):
+                    if have:
+                        pl, col = ctx.a_planes
+                        gw = _tc_gemm_a_slice_raw(pl, col, pg, Cin, Cout, P, 1, 0)
+                    else:
+                        gw = _tc_gemm_raw(_split(a, npl), pg, Cin, Cout, P, 1, 0)
             return ga, gw, None
+        if ctx.needs_input_grad[1]:
+            with _SideStream(g.device, a, g):
+                gw = _gemm_raw(a, g, Cin, Cout, P, 1, 0)  # A^T . g  (split over the P points)
         if ctx.needs_input_grad[0]:
             ga = _gemm_raw(g, w, P, Cin, Cout, 0, 1)  # g . W^T
-        if ctx.needs_input_grad[1]:
-            gw = _gemm_raw(a, g, Cin, Cout, P, 1, 0)  # A^T . g  (split over the P points)
         return ga, gw, None
 
 
@@ -304,7 +357,7 @@ def _tc_gemm_raw(pa, pb, M, N, K, tA, tB):
     L = nv.lib()
     out = torch.empty((M, N), dtype=torch.float32, device=pa.device)
     need = L.dgcnn_tc_gemm_workspace_bytes(M, N, K)
-    ws = nv.workspace(pa.device, need, "gemm") if need else None
+    ws = nv.workspace(pa.device, need, ws_tag("gemm")) if need else None
     assert pa.shape[0] == pb.shape[0], "tc_gemm: both operands must be in the same precision mode"
     nv.check(L.dgcnn_tc_gemm(pa.data_ptr(), pb.data_ptr(), out.data_ptr(), M, N, K, tA, tB, pa.shape[0], nv.ptr(ws),
                              ws.numel() if ws is not None else 0, nv.stream_ptr(pa.device)), "tc_gemm")
@@ -316,7 +369,7 @@ def _tc_gemm_a_slice_raw(pl, col, pb, M, N, K, tA, tB):
     L = nv.lib()
     out = torch.empty((M, N), dtype=torch.float32, device=pb.device)
     need = L.dgcnn_tc_gemm_workspace_bytes(M, N, K)
-    ws = nv.workspace(pb.device, need, "gemm") if need else None
+    ws = nv.workspace(pb.device, need, ws_tag("gemm")) if need else None
     assert pl.shape[0] == pb.shape[0], "tc_gemm_a_slice: both operands must be in the same precision mode"
     nv.check(L.dgcnn_tc_gemm_a_slice(pl.data_ptr() + 2 * col, pl.shape[2], _pe(pl), pb.data_ptr(), out.data_ptr(), M, N, K,
                                      tA, tB, pb.shape[0], nv.ptr(ws), ws.numel() if ws is not None else 0,
@@ -463,8 +516,12 @@ class _ConvBnActTC(torch.autograd.Function):
                                            rstd.data_ptr(), nv.ptr(gb), ctx.grows, int(ctx.relu), nv.ptr(gz),
                                            pg.data_ptr(), pg.shape[0], gbeta.data_ptr(), ws.data_ptr(), ws.numel(),
                                            nv.stream_ptr(dev)), "bn_act_bwd_planes")
-        gw = _tc_gemm_raw(planes, pg, K, Cout, P, 1, 0) if ctx.needs_input_grad[0] else None   # X^T . g_z
-        ggb = gz.view(gb.shape[0], ctx.grows, Cout).sum(dim=1) if gb is not None else None
+        gw = ggb = None
+        with _SideStream(dev, planes, pg, gz):
+            if ctx.needs_input_grad[0]:
+                gw = _tc_gemm_raw(planes, pg, K, Cout, P, 1, 0)                                # X^T . g_z
+        if gb is not None:
+            ggb = gz.view(gb.shape[0], ctx.grows, Cout).sum(dim=1)
         return tuple([gw, gbeta, ggb, None, None, None] +
                      _tc_dx_sources(pg, pw, P, K, Cout, ctx.widths, ctx.needs_input_grad[6:]))
 
@@ -494,10 +551,37 @@ class _EdgeWeights(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         C, F = g.shape[0], g.shape[1] // 2
-        gw = torch.empty((2 * C, F), dtype=g.dtype, device=g.device)
-        gw[:C].copy_(g[:, :F])                       # d/dWa
-        torch.sub(g[:, F:], g[:, :F], out=gw[C:])    # d/dWb
+        with _SideStream(g.device, g):               # g is a weight gradient: it may still be in flight on the side stream
+            gw = torch.empty((2 * C, F), dtype=g.dtype, device=g.device)
+            gw[:C].copy_(g[:, :F])                       # d/dWa
+            torch.sub(g[:, F:], g[:, :F], out=gw[C:])    # d/dWb
         return gw
+
+
+class _SplitWeightRows(torch.autograd.Function):
+    """w [cin, cout] -> (w[:r], w[r:]) for a layer whose input is a concat handled in two parts (model.py:83-88: the tiled
+    global feature and the per-point sources of FC0).  Exists for its backward: the two weight gradients are joined on the
+    side stream they were produced on (plain slicing would route them through autograd kernels on the main stream)."""
+
+    @staticmethod
+    def forward(ctx, w, r):
+        ctx.r, ctx.shape = int(r), tuple(w.shape)
+        return w[:ctx.r], w[ctx.r:]
+
+    @staticmethod
+    def backward(ctx, g_top, g_rest):
+        ref = g_top if g_top is not None else g_rest
+        with _SideStream(ref.device, g_top, g_rest):
+            gw = torch.empty(ctx.shape, dtype=ref.dtype, device=ref.device)
+            if g_top is not None:
+                gw[:ctx.r].copy_(g_top)
+            else:
+                gw[:ctx.r].zero_()
+            if g_rest is not None:
+                gw[ctx.r:].copy_(g_rest)
+            else:
+                gw[ctx.r:].zero_()
+        return gw, None
 
 
 class _EdgeConvGather(torch.autograd.Function):

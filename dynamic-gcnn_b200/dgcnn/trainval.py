@@ -173,10 +173,15 @@ class trainval(object):
         views = [p.grad for p in params]
         for p in params:
             p.grad = None
+        from . import ops as _ops
+        old_async = _ops._async_dw
+        _ops._async_dw = os.environ.get("DGCNN_ASYNC_DW", "1") != "0"    # weight-gradient GEMMs on a side stream
         try:
             loss.backward()
             pairs = [(v, p.grad) for v, p in zip(views, params) if p.grad is not None]
         finally:
+            _ops.join_side_stream(self._device)
+            _ops._async_dw = old_async
             for p, v in zip(params, views):
                 p.grad = v
         if pairs:
