@@ -346,7 +346,7 @@ extern "C" int dgcnn_tc_gemm_a_slice(const void* a_planes, int64_t a_ld, int64_t
 }
 
 extern "C" int dgcnn_tc_gemm_stats_supported(int M, int N, int K) {
-  return (tc_wide_ok(M, N, K) && tc_wide_splits(M, N, K) == 1) ? 1 : 0;
+  return (tc_wide_ok(M, N, K) && (N % 256) == 0 && tc_wide_splits(M, N, K) == 1) ? 1 : 0;
 }
 
 extern "C" int dgcnn_tc_gemm_stats(const void* a_planes, const void* b_planes, float* C, int M, int N, int K, int transA,

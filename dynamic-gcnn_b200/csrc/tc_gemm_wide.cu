@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(W_THREADS, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt_n = (M + W_M - 1) / W_M, nt_n = N / W_N;
+  const int mt_n = (M + W_M - 1) / W_M, nt_n = (N + W_N - 1) / W_N;   // the last n-tile may be partial (N % 32 == 0)
   const int kb_total = (K + W_K - 1) / W_K;
   const int total = mt_n * nt_n * splits;
 
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(W_THREADS, 1)
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
         const int c0 = n0 + ch * 32;
-        // where this 32-column chunk goes
+        // where this 32-column chunk goes (chunks beyond N: the partial last tile; TMA zero-filled their operands)
         float* obase = Cout + c0;
         int opitch = N;
         if (out.n_groups > 0) {
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(W_THREADS, 1)
               opitch = out.width[g];
             }
         }
-        if (out.dbg_nostore) obase = nullptr;
+        if (out.dbg_nostore || c0 >= N) obase = nullptr;
         // Transpose through shared memory in two 16-column halves: lane (c, rh) then owns column c of the rows
         // rh, rh+2, ...  Every store instruction writes two 64-byte row segments (whole 32-byte sectors; a lane
         // storing 16 bytes of its own row would fill half a sector per transaction), and the column statistics
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(W_THREADS, 1)
 
 // number of k-splits for the wide kernel: fill the machine when there are fewer tiles than SMs (weight gradients)
 int tc_wide_splits(int M, int N, int K) {
-  const int64_t tiles = (int64_t)cdiv(M, W_M) * (N / W_N);
+  const int64_t tiles = (int64_t)cdiv(M, W_M) * cdiv(N, W_N);
   const int kb = cdiv(K, W_K);
   const int sms = num_sms();
   if (tiles >= sms || kb < 16) return 1;
@@ -259,14 +259,15 @@ int tc_wide_splits(int M, int N, int K) {
   return s < 1 ? 1 : s;
 }
 
-bool tc_wide_ok(int M, int N, int K) { return N >= 256 && (N % W_N) == 0 && M >= 128; }
+// N need not be a multiple of the 256-column tile: the last tile's missing columns are zero-filled by TMA and never stored
+bool tc_wide_ok(int M, int N, int K) { return N >= 256 && (N % 32) == 0 && M >= 128; }
 
 // C (or groups / split partials) = op(A).op(B) with the wide kernel.  colstats may be null.
 int tc_gemm_wide_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, bool a_k, bool b_k, int M, int N, int K,
                         int splits, int planes, const WideOut& out, cudaStream_t st) {
   const int kb = cdiv(K, W_K);
   const int kper = cdiv(kb, splits);
-  const int total = cdiv(M, W_M) * (N / W_N) * splits;
+  const int total = cdiv(M, W_M) * cdiv(N, W_N) * splits;
   const int grid = total < num_sms() ? total : num_sms();
 #define DG_WIDE(AK_, BK_)                                                                                     \
   do {                                                                                                         \

@@ -162,3 +162,26 @@ def test_tc_gemm_single_plane_bf16(dg, cuda, M, N, K, tA, tB):
     # mixing modes is refused
     assert L.dgcnn_tc_gemm(pa.data_ptr(), pb.data_ptr(), out.data_ptr(), M, N, K, tA, tB, 3, ws.data_ptr(), ws.numel(),
                            nv.stream_ptr(cuda)) == nv.ERR_INVALID
+
+
+@pytest.mark.parametrize("M,N,K,tA,tB", [(4096, 384, 256, 0, 1), (2048 + 40, 2176, 512, 0, 1), (1024, 288, 64, 0, 0),
+                                          (2176, 512, 4096, 1, 0), (384, 1024, 8192, 1, 0)])
+def test_wide_gemm_partial_last_column_tile(dg, cuda, M, N, K, tA, tB):
+    """Widths that are not multiples of the 256-column tile (FC0 / MergedEdgeConv gradients with 6 EdgeConv layers:
+    2176 and 384 columns) take the persistent wide kernel too: the missing columns of the last tile are zero-filled by
+    TMA and never stored.  Guard columns after the output must stay untouched."""
+    from dgcnn import _native as nv
+    L = nv.lib()
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn((K, M) if tA else (M, K), generator=g).to(cuda)
+    B = torch.randn((N, K) if tB else (K, N), generator=g).to(cuda)
+    buf = torch.full((M * N + 4096,), 7.0, device=cuda)            # output + guard
+    need = L.dgcnn_tc_gemm_workspace_bytes(M, N, K)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=cuda)
+    pa, pb = _split(dg, A), _split(dg, B)
+    nv.check(L.dgcnn_tc_gemm(pa.data_ptr(), pb.data_ptr(), buf.data_ptr(), M, N, K, tA, tB, 2, ws.data_ptr(), ws.numel(),
+                             nv.stream_ptr(cuda)), "tc_gemm")
+    out = buf[:M * N].view(M, N)
+    ref = (A.double().t() if tA else A.double()) @ (B.double().t() if tB else B.double())
+    assert (out.double() - ref).abs().max().item() <= 4e-5 * float(np.sqrt(K)) * 9.0
+    assert bool((buf[M * N:] == 7.0).all())
