@@ -19,6 +19,15 @@ struct BnSinks {
   int ld[2];
   size_t plane[2];
 };
+// Max-pool over the rows of each group fused around a layer (model.py:76-77: the global max over the N points of a cloud
+// of the MergedEdgeConv output).  Forward: the apply pass leaves max / #argmax per (group, channel).  Backward: the pool's
+// gradient  [y == max] g_pool / cnt  is added to the layer's incoming gradient on the fly, y re-evaluated from z.
+struct BnPool {
+  const float* pmax;    // [groups][C] or null (no pool)
+  const float* pcnt;    // [groups][C]
+  const float* pgrad;   // [groups][C]
+  int rows;             // rows per group
+};
 constexpr int BN_BLOCKS_PER_SM = 8;
 
 static inline int bn_max_blocks() { return num_sms() * BN_BLOCKS_PER_SM; }
@@ -85,7 +94,7 @@ __global__ void __launch_bounds__(BN_THREADS)
     bn_colsum_vec_kernel(const float* __restrict__ z, const float* __restrict__ out, const float* __restrict__ gout,
                          const float* __restrict__ mean, const float* __restrict__ rstd, int relu, int64_t rows, int C,
                          int cb, double* __restrict__ acc, const float* __restrict__ gbias, int grows,
-                         const float* __restrict__ beta) {
+                         const float* __restrict__ beta, const BnPool pool) {
   __shared__ float red[2][BN_THREADS][4];
   const int tpr = cb >> 2;                        // threads per row
   const int cv = threadIdx.x % tpr, rl = threadIdx.x / tpr, lanes = BN_THREADS / tpr;
@@ -110,6 +119,12 @@ __global__ void __launch_bounds__(BN_THREADS)
       if (relu && out) *reinterpret_cast<float4*>(ov) = *reinterpret_cast<const float4*>(out + o);
     }
     if (gbias) *reinterpret_cast<float4*>(gb) = *reinterpret_cast<const float4*>(gbias + (r / grows) * C + c);
+    float pm[4];
+    int64_t po = 0;
+    if (MODE == 1 && pool.pmax) {
+      po = (r / pool.rows) * C + c;
+      *reinterpret_cast<float4*>(pm) = __ldg(reinterpret_cast<const float4*>(pool.pmax + po));
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float v = zv[i] + gb[i];
@@ -118,7 +133,11 @@ __global__ void __launch_bounds__(BN_THREADS)
         q[i] = fmaf(v, v, q[i]);
       } else {
         float g = gp[i];
-        if (relu && !((out ? ov[i] : fmaf(v - mu[i], rs[i], be[i])) > 0.f)) g = 0.f;
+        const float t = out ? ov[i] : fmaf(v - mu[i], rs[i], be[i]);   // the forward output before the ReLU clamp
+        // the pooled copy of this output: its gradient goes to the arg-max rows (ties share); a hit is rare, so the
+        // count and the pooled gradient are fetched only then
+        if (pool.pmax && fmaxf(t, 0.f) == pm[i]) g += __ldg(pool.pgrad + po + i) / __ldg(pool.pcnt + po + i);
+        if (relu && !(t > 0.f)) g = 0.f;
         a[i] += g;
         q[i] = fmaf(g, (v - mu[i]) * rs[i], q[i]);
       }
@@ -152,7 +171,7 @@ __global__ void __launch_bounds__(BN_THREADS)
 template <int MODE>
 static void launch_colsum(const float* z, const float* out, const float* gout, const float* mean, const float* rstd,
                           int relu, int64_t rows, int C, double* acc, const float* gbias, int grows, const float* beta,
-                          cudaStream_t st) {
+                          cudaStream_t st, const BnPool pool = BnPool{nullptr, nullptr, nullptr, 1}) {
   const bool vec = (C & 3) == 0 && C >= 16 &&
                    (((uintptr_t)z | (uintptr_t)out | (uintptr_t)gout | (uintptr_t)gbias | (uintptr_t)mean |
                      (uintptr_t)rstd | (uintptr_t)beta) & 15) == 0;
@@ -165,7 +184,7 @@ static void launch_colsum(const float* z, const float* out, const float* gout, c
     while (cb > C) cb >>= 1;                        // 16 .. 256, a power of two <= C
     dim3 grid(nb, cdiv(C, cb));
     bn_colsum_vec_kernel<MODE><<<grid, BN_THREADS, 0, st>>>(z, out, gout, mean, rstd, relu, rows, C, cb, acc, gbias,
-                                                            grows, beta);
+                                                            grows, beta, pool);
   } else {
     dim3 grid(nb, cdiv(C, 64));
     bn_colsum_kernel<MODE><<<grid, BN_THREADS, 0, st>>>(z, out, gout, mean, rstd, relu, rows, C, acc, gbias, grows, beta);
@@ -236,13 +255,101 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Apply pass of a layer whose output is also max-pooled over the rows of each group (MergedEdgeConv, model.py:65-81):
+// y = relu((z - mean) rstd + beta) goes to the plane sinks (and to `out` if given) while every thread keeps the running
+// (max, #argmax) of its 4 channels over the rows of its slice of one group; slices are combined with a 64-bit CAS on
+// packed (value bits : count) words -- y >= 0, so the unsigned order of the bits is the order of the values.
+// grid = (row slices per group, groups); a thread owns channel quad c4 = threadIdx.x, + 256, ...
+__global__ void __launch_bounds__(256)
+    bn_apply_pool_kernel(const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ rstd,
+                         const float* __restrict__ beta, int C, int pool_rows, int slice_rows, float* __restrict__ out,
+                         const BnSinks sinks, unsigned long long* __restrict__ packed) {
+  const int g = blockIdx.y;
+  const int r_lo = blockIdx.x * slice_rows, r_hi = min(pool_rows, r_lo + slice_rows);
+  for (int c4 = threadIdx.x; c4 < (C >> 2); c4 += blockDim.x) {
+    const int c = c4 * 4;
+    float mu[4], rs[4], be[4];
+    *reinterpret_cast<float4*>(mu) = __ldg(reinterpret_cast<const float4*>(mean + c));
+    *reinterpret_cast<float4*>(rs) = __ldg(reinterpret_cast<const float4*>(rstd + c));
+    *reinterpret_cast<float4*>(be) = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float m[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned n[4] = {0u, 0u, 0u, 0u};
+    constexpr int U = 4;                                   // rows in flight per thread
+    for (int rb = r_lo; rb < r_hi; rb += U) {
+      float zz[U][4];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int rl = rb + u < r_hi ? rb + u : r_hi - 1;     // clamp: the duplicate row is skipped below
+        *reinterpret_cast<float4*>(zz[u]) =
+            *reinterpret_cast<const float4*>(z + ((size_t)g * pool_rows + rl) * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (rb + u >= r_hi) break;
+        const size_t r = (size_t)g * pool_rows + rb + u;
+        const size_t e = r * C + c;
+        float y[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          y[i] = fmaxf(fmaf(zz[u][i] - mu[i], rs[i], be[i]), 0.f);
+          if (y[i] > m[i]) { m[i] = y[i]; n[i] = 1u; } else if (y[i] == m[i]) ++n[i];
+        }
+        if (out) *reinterpret_cast<float4*>(out + e) = *reinterpret_cast<float4*>(y);
+        if (sinks.n > 0) {
+          __nv_bfloat16 h[4], l[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            h[i] = __float2bfloat16_rn(y[i]);
+            l[i] = __float2bfloat16_rn(y[i] - __bfloat162float(h[i]));
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (q < sinks.n) {
+              const size_t se = r * sinks.ld[q] + c;
+              *reinterpret_cast<uint2*>(sinks.p[q] + se) = *reinterpret_cast<uint2*>(h);
+              if (sinks.plane[q]) *reinterpret_cast<uint2*>(sinks.p[q] + sinks.plane[q] + se) = *reinterpret_cast<uint2*>(l);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (n[i] == 0u) continue;
+      unsigned long long* w = packed + (size_t)g * C + c + i;
+      const unsigned long long mine_bits = (unsigned long long)__float_as_uint(m[i]) << 32;
+      unsigned long long old = *w;
+      while (true) {
+        const unsigned long long ov = old & 0xffffffff00000000ull;
+        unsigned long long nw;
+        if (ov > mine_bits) break;                                      // a larger maximum is already there
+        if (ov == mine_bits) nw = old + n[i];                            // same maximum: counts add
+        else nw = mine_bits | n[i];                                      // ours is larger
+        const unsigned long long seen = atomicCAS(w, old, nw);
+        if (seen == old) break;
+        old = seen;
+      }
+    }
+  }
+}
+
+__global__ void bn_pool_unpack_kernel(const unsigned long long* __restrict__ packed, int n, float* __restrict__ pmax,
+                                      float* __restrict__ pcnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long w = packed[i];
+  pmax[i] = __uint_as_float((unsigned)(w >> 32));
+  pcnt[i] = (float)(unsigned)(w & 0xffffffffull);
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256)
     bn_act_bwd_kernel(const float* __restrict__ z, const float* __restrict__ out, const float* __restrict__ gout,
                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ s1,
                       const float* __restrict__ s2, int relu, uint32_t nvec, int C, float inv_rows,
                       float* __restrict__ gz, float* __restrict__ gpre, const float* __restrict__ gbias, int grows,
-                      __nv_bfloat16* __restrict__ gz_planes, size_t plane_elems, const float* __restrict__ beta) {
+                      __nv_bfloat16* __restrict__ gz_planes, size_t plane_elems, const float* __restrict__ beta,
+                      const BnPool pool) {
   const uint32_t cv = (uint32_t)C / VEC;
   for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
     const uint32_t r = v / cv;
@@ -274,13 +381,21 @@ __global__ void __launch_bounds__(256)
       a2[0] = s2[c];
       if (beta) be[0] = beta[c];
     }
+    float pm[VEC];
+    size_t po = 0;
+    if (VEC == 4 && pool.pmax) {
+      po = (size_t)(r / pool.rows) * C + c;
+      *reinterpret_cast<float4*>(pm) = __ldg(reinterpret_cast<const float4*>(pool.pmax + po));
+    }
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       float gp = gg[i];
       const float rs = rsv[i];
       float zv = zz[i];
       if (gbias) zv += gb[i];
-      if (relu && !((out ? oo[i] : fmaf(zv - mu[i], rs, be[i])) > 0.f)) gp = 0.f;
+      const float t = (relu || pool.pmax) ? (out ? oo[i] : fmaf(zv - mu[i], rs, be[i])) : 1.f;
+      if (VEC == 4 && pool.pmax && fmaxf(t, 0.f) == pm[i]) gp += __ldg(pool.pgrad + po + i) / __ldg(pool.pcnt + po + i);
+      if (relu && !(t > 0.f)) gp = 0.f;
       const float zh = (zv - mu[i]) * rs;
       gzv[i] = rs * (gp - a1[i] * inv_rows - zh * (a2[i] * inv_rows));
       gpv[i] = gp;
@@ -617,21 +732,67 @@ extern "C" int dgcnn_bn_apply_fwd_sinks(const float* z, int64_t rows, int C, con
   return DGCNN_OK;
 }
 
+extern "C" size_t dgcnn_bn_pool_workspace_bytes(int groups, int C) {
+  return groups > 0 && C > 0 ? (size_t)groups * C * sizeof(unsigned long long) : 0;
+}
+
+extern "C" int dgcnn_bn_apply_fwd_pool(const float* z, int64_t rows, int C, const float* beta, const float* mean,
+                                       const float* rstd, float* out, int pool_rows, float* pool_max, float* pool_cnt,
+                                       void* ws, size_t ws_bytes, int n_sinks, void* const* sink_planes,
+                                       const int* sink_lds, const int64_t* sink_plane_elems, dgcnn_stream_t stream) {
+  BnSinks sinks;
+  {
+    int rcs = bn_make_sinks(&sinks, n_sinks, sink_planes, sink_lds, sink_plane_elems, C);
+    if (rcs) return rcs;
+  }
+  DG_REQUIRE(z && beta && mean && rstd && pool_max && pool_cnt && ws, DGCNN_ERR_INVALID, "bn_apply_fwd_pool: null pointer");
+  DG_REQUIRE(out || sinks.n > 0, DGCNN_ERR_INVALID, "bn_apply_fwd_pool: the output needs at least one destination");
+  DG_REQUIRE(rows > 0 && C >= 4 && (C & 3) == 0 && pool_rows > 0 && rows % pool_rows == 0, DGCNN_ERR_INVALID,
+             "bn_apply_fwd_pool: bad shape rows=%lld C=%d pool_rows=%d", (long long)rows, C, pool_rows);
+  DG_REQUIRE((((uintptr_t)z | (uintptr_t)out | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta | (uintptr_t)pool_max |
+               (uintptr_t)pool_cnt) & 15) == 0 && ((uintptr_t)ws & 7) == 0, DGCNN_ERR_INVALID, "bn_apply_fwd_pool: alignment");
+  const int groups = (int)(rows / pool_rows);
+  DG_REQUIRE(groups <= 65535, DGCNN_ERR_UNSUPPORTED, "bn_apply_fwd_pool: more than 65535 groups");
+  const size_t need = dgcnn_bn_pool_workspace_bytes(groups, C);
+  DG_REQUIRE(ws_bytes >= need, DGCNN_ERR_WORKSPACE, "bn_apply_fwd_pool: workspace %zu < %zu bytes", ws_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(ws, 0, need, st) != cudaSuccess) return set_err(DGCNN_ERR_CUDA, "bn_apply_fwd_pool: memset failed");
+  // enough slices per group to fill the machine several times over, at least 16 rows each
+  int slices = cdiv((int64_t)num_sms() * 8, groups);
+  if (slices > cdiv(pool_rows, 16)) slices = cdiv(pool_rows, 16);
+  if (slices < 1) slices = 1;
+  const int slice_rows = cdiv(pool_rows, slices);
+  dim3 grid(cdiv(pool_rows, slice_rows), groups);
+  bn_apply_pool_kernel<<<grid, 256, 0, st>>>(z, mean, rstd, beta, C, pool_rows, slice_rows, out, sinks,
+                                             (unsigned long long*)ws);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("bn_apply_pool_kernel");
+  bn_pool_unpack_kernel<<<cdiv((int64_t)groups * C, 256), 256, 0, st>>>((const unsigned long long*)ws, groups * C,
+                                                                          pool_max, pool_cnt);
+  count_launch();
+  DG_CUDA_LAUNCH_CHECK("bn_pool_unpack_kernel");
+  return DGCNN_OK;
+}
+
 static int bn_act_bwd_impl(const float* z, const float* out, const float* g_out, int64_t rows, int C, const float* mean,
                            const float* rstd, const float* group_bias, int group_rows, int relu, float* g_z,
                            void* g_z_planes, float* g_beta, float* g_pre, const float* beta, void* ws, size_t ws_bytes,
-                           dgcnn_stream_t stream, int n_planes = 2);
+                           dgcnn_stream_t stream, int n_planes = 2, const BnPool pool = BnPool{nullptr, nullptr, nullptr, 1});
 
 extern "C" int dgcnn_bn_act_bwd_planes(const float* z, const float* out, const float* beta, const float* g_out,
                                        int64_t rows, int C, const float* mean, const float* rstd,
                                        const float* group_bias, int group_rows, int relu, float* g_z, void* g_z_planes,
-                                       int n_planes, float* g_beta, void* ws, size_t ws_bytes, dgcnn_stream_t stream) {
+                                       int n_planes, float* g_beta, const float* pool_max, const float* pool_cnt,
+                                       const float* pool_grad, int pool_rows, void* ws, size_t ws_bytes,
+                                       dgcnn_stream_t stream) {
   DG_REQUIRE(!relu || out || beta, DGCNN_ERR_INVALID, "bn_act_bwd_planes: relu backward needs out or beta");
+  DG_REQUIRE(!pool_max || (pool_cnt && pool_grad), DGCNN_ERR_INVALID, "bn_act_bwd_planes: pool_max needs pool_cnt and pool_grad");
   DG_REQUIRE(n_planes == 1 || n_planes == 2, DGCNN_ERR_INVALID, "bn_act_bwd_planes: n_planes must be 1 or 2");
   DG_REQUIRE(g_z_planes && (C & 3) == 0 && ((uintptr_t)g_z_planes & 7) == 0, DGCNN_ERR_INVALID,
              "bn_act_bwd_planes: needs a plane buffer and C %% 4 == 0");
   return bn_act_bwd_impl(z, out, g_out, rows, C, mean, rstd, group_bias, group_rows, relu, g_z, g_z_planes, g_beta,
-                         nullptr, out ? nullptr : beta, ws, ws_bytes, stream, n_planes);
+                         nullptr, out ? nullptr : beta, ws, ws_bytes, stream, n_planes,
+                         BnPool{pool_max, pool_cnt, pool_grad, pool_rows > 0 ? pool_rows : 1});
 }
 
 extern "C" int dgcnn_bn_act_bwd(const float* z, const float* out, const float* g_out, int64_t rows, int C,
@@ -653,7 +814,7 @@ extern "C" int dgcnn_bn_act_bwd_gb(const float* z, const float* out, const float
 static int bn_act_bwd_impl(const float* z, const float* out, const float* g_out, int64_t rows, int C, const float* mean,
                            const float* rstd, const float* group_bias, int group_rows, int relu, float* g_z,
                            void* g_z_planes, float* g_beta, float* g_pre, const float* beta, void* ws, size_t ws_bytes,
-                           dgcnn_stream_t stream, int n_planes) {
+                           dgcnn_stream_t stream, int n_planes, const BnPool pool) {
   DG_REQUIRE(!group_bias || (group_rows > 0 && rows % group_rows == 0), DGCNN_ERR_INVALID,
              "bn_act_bwd: rows=%lld is not a multiple of group_rows=%d", (long long)rows, group_rows);
   DG_REQUIRE(z && g_out && mean && rstd && (g_z || g_z_planes) && g_beta && ws, DGCNN_ERR_INVALID,
@@ -667,7 +828,7 @@ static int bn_act_bwd_impl(const float* z, const float* out, const float* g_out,
   float* s2 = reinterpret_cast<float*>(acc + (size_t)2 * C);
   int rc = stats_acc_reset(ws, C, st);
   if (rc) return rc;
-  launch_colsum<1>(z, out, g_out, mean, rstd, relu, rows, C, acc, group_bias, group_rows, beta, st);
+  launch_colsum<1>(z, out, g_out, mean, rstd, relu, rows, C, acc, group_bias, group_rows, beta, st, pool);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_colsum_kernel<1>");
   rc = launch_finalize_sums(acc, C, g_beta, s2, st);
@@ -678,15 +839,18 @@ static int bn_act_bwd_impl(const float* z, const float* out, const float* g_out,
                                      (uintptr_t)group_bias | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta |
                                      (uintptr_t)g_beta | (uintptr_t)s2) & 15) == 0;
   DG_REQUIRE(vec || !g_z_planes, DGCNN_ERR_INVALID, "bn_act_bwd: plane output needs 16-byte aligned buffers, C %% 4 == 0");
+  DG_REQUIRE(!pool.pmax || (vec && C >= 16 && beta && !out && relu && pool.rows > 0 && rows % pool.rows == 0 &&
+                            (((uintptr_t)pool.pmax | (uintptr_t)pool.pcnt | (uintptr_t)pool.pgrad) & 15) == 0),
+             DGCNN_ERR_INVALID, "bn_act_bwd: a fused pool needs C %% 4 == 0, relu, beta (mask from z) and rows %% pool_rows == 0");
   if (vec)
     bn_act_bwd_kernel<4><<<ew_blocks(total / 4), 256, 0, st>>>(z, out, g_out, mean, rstd, g_beta, s2, relu,
                                                                (uint32_t)(total / 4), C, 1.0f / (float)rows, g_z, g_pre,
                                                                group_bias, group_rows, (__nv_bfloat16*)g_z_planes,
-                                                               n_planes == 2 ? (size_t)total : 0, beta);
+                                                               n_planes == 2 ? (size_t)total : 0, beta, pool);
   else
     bn_act_bwd_kernel<1><<<ew_blocks(total), 256, 0, st>>>(z, out, g_out, mean, rstd, g_beta, s2, relu, (uint32_t)total, C,
                                                            1.0f / (float)rows, g_z, g_pre, group_bias, group_rows, nullptr,
-                                                           0, beta);
+                                                           0, beta, pool);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_act_bwd_kernel");
   return DGCNN_OK;

@@ -20,9 +20,10 @@ from . import ops as _ops
 
 
 def conv_bn_act(srcs: List[torch.Tensor], scope: str, cout: int, trainable: bool, activation=_ops.relu,
-                cloud_feature: Optional[torch.Tensor] = None, points_per_cloud: int = 0) -> torch.Tensor:
+                cloud_feature: Optional[torch.Tensor] = None, points_per_cloud: int = 0, pool_rows: int = 0):
     """srcs: [P, c_i] tensors whose channel concat is the layer input (after the optional per-cloud feature
-    [B, cg] that the reference tiles in front of it).  -> [P, cout]."""
+    [B, cg] that the reference tiles in front of it).  -> [P, cout]; with pool_rows > 0 -> ([P, cout], [P/pool_rows, cout]):
+    the layer output and its maximum over every pool_rows consecutive rows (model.py:76-77, fused when possible)."""
     cg = cloud_feature.shape[1] if cloud_feature is not None else 0
     cin = cg + sum(int(t.shape[1]) for t in srcs)
     w, b = _ops._conv_bn_vars(scope, cin, cout, trainable, srcs[0].device)
@@ -31,9 +32,22 @@ def conv_bn_act(srcs: List[torch.Tensor], scope: str, cout: int, trainable: bool
     P = srcs[0].shape[0]
     if _ops._tc_ok(P, cout, *[t.shape[1] for t in srcs]):
         # the whole layer around one tcgen05 GEMM: BN statistics from its epilogue, gradients as bf16 planes
-        return _ops._ConvBnActTC.apply(w_rest, b, gb, activation is not None, points_per_cloud, scope, *srcs)
-    z = _ops.conv1x1(srcs, w_rest)
-    return _ops._BnAct.apply(z, b, None, activation is not None, gb, None)
+        kin = sum(int(t.shape[1]) for t in srcs)
+        fuse_pool = bool(pool_rows) and gb is None and activation is not None and P % pool_rows == 0 and \
+            _ops.nv.lib().dgcnn_tc_gemm_stats_supported(P, cout, kin) and _ops._FUSE_POOL
+        out, pooled = _ops._ConvBnActTC.apply(w_rest, b, gb, activation is not None, points_per_cloud, scope,
+                                              pool_rows if fuse_pool else 0, *srcs)
+        if not pool_rows:
+            return out
+        if fuse_pool:
+            return out, pooled
+    else:
+        z = _ops.conv1x1(srcs, w_rest)
+        out = _ops._BnAct.apply(z, b, None, activation is not None, gb, None)
+        if not pool_rows:
+            return out
+    out3, pooled = _ops.pool_and_pass(out.view(P // pool_rows, pool_rows, cout))      # separate pooling kernels
+    return out3.view(P, cout), pooled
 
 
 def conv_bn_relu_dense(net: torch.Tensor, scope: str, cout: int, trainable: bool, activation=_ops.relu) -> torch.Tensor:

@@ -103,10 +103,10 @@ def _build_body(net, flags, dropout_mask, num_edge_conv, num_edge_filters, num_f
     P = batch_size * num_point
     flat = [x.reshape(P, x.shape[-1]) for x in tensors]
     # model.py:60-72: concat of every layer's `net` -> MergedEdgeConv (1024) ; the concat is never built
-    merged = conv_bn_act([flat[3 * i + 2] for i in range(num_edge_conv)], "MergedEdgeConv", 1024, True)
+    # ... and model.py:77's global max pool of it, produced by the same BN apply pass
+    merged, g = conv_bn_act([flat[3 * i + 2] for i in range(num_edge_conv)], "MergedEdgeConv", 1024, True,
+                            pool_rows=num_point)
     if debug: print("Shape %s ... Name %s" % ((batch_size, num_point, 1, 1024), "MergedEdgeConv"))
-    merged3, g = ops.pool_and_pass(merged.view(batch_size, num_point, 1024))           # model.py:77 global max pool
-    merged = merged3.view(P, 1024)
     if debug: print("Shape %s ... Name %s" % ((batch_size, 1, 1, 1024), "maxpool0"))
     # model.py:80-88: tile(g) ++ tensors ++ merged -> FC stack.  First FC layer: the tiled global feature is a
     # per-cloud term, the rest a multi-source GEMM; later FC layers are plain.

@@ -330,6 +330,7 @@ TC_MIN_ROWS = 1024  # below this the SIMT kernel wins (launch + split overhead)
 # next layer's neighbour differences (x_j - x_i): same-graph logits 9e-5 -> 7e-4 from the fp32 oracle, gradients 6x
 # further from fp64 than fp32 arithmetic is.  The EdgeConv stack therefore stays on exact fp32 GEMMs in f32 mode.
 _TC_FORWARD = os.environ.get("DGCNN_TC_FORWARD", "0") == "1"
+_FUSE_POOL = os.environ.get("DGCNN_FUSE_POOL", "1") != "0"     # A/B switch: global max pool fused into MergedEdgeConv's BN
 
 
 def _tc_ok(P: int, *dims: int) -> bool:
@@ -450,10 +451,13 @@ class _ConvBnActTC(torch.autograd.Function):
     BatchNorm [+ per-cloud bias] [+ ReLU], fused around the tcgen05 GEMM:
       forward : sources -> bf16 planes -> GEMM whose epilogue also leaves the BN column statistics of every 128-row
                 tile -> tiny finalisation -> one apply pass.  (No separate statistics pass over z.)
-      backward: BN backward writes g_z directly as bf16 planes (the operand format of the dW / dX GEMMs)."""
+      backward: BN backward writes g_z directly as bf16 planes (the operand format of the dW / dX GEMMs).
+    pool_rows > 0 (MergedEdgeConv, model.py:76-77): the layer also returns the max over every pool_rows consecutive rows
+    (one cloud); the apply pass produces it on the way, the fp32 output is not even written when every consumer reads
+    the operand planes, and the pool's gradient is added inside the BN-backward kernels.  -> (out, pooled or None)"""
 
     @staticmethod
-    def forward(ctx, w, beta, gb, relu_flag, grows, scope, *srcs):
+    def forward(ctx, w, beta, gb, relu_flag, grows, scope, pool_rows, *srcs):
         w = nv.require_cuda(w, "conv weights")
         beta = nv.require_cuda(beta, "beta")
         gb = nv.require_cuda(gb, "group_bias") if gb is not None else None
@@ -462,15 +466,20 @@ class _ConvBnActTC(torch.autograd.Function):
         planes, widths, P, K = _split_sources(srcs, w, sk.planes.get(scope) if sk is not None else None)
         n_s, s_ptr, s_ld, s_pe, s_lst = sk.sink_args(("layer", scope)) if sk is not None else (0, None, None, None, [])
         Cout = w.shape[1]
-        pw = _split(w)
+        pw = _split(w, planes.shape[0])
         dev = w.device
         L = nv.lib()
         st = nv.stream_ptr(dev)
         grows = int(grows) if gb is not None else 0
+        pool_rows = int(pool_rows)
         mean = torch.empty(Cout, dtype=torch.float32, device=dev)
         rstd = torch.empty(Cout, dtype=torch.float32, device=dev)
         out = torch.empty((P, Cout), dtype=torch.float32, device=dev)
-        if L.dgcnn_tc_gemm_stats_supported(P, Cout, K) and (gb is None or grows % 128 == 0):
+        pmax = pcnt = None
+        fused = L.dgcnn_tc_gemm_stats_supported(P, Cout, K) and (gb is None or grows % 128 == 0)
+        if pool_rows and not (fused and gb is None and relu_flag and P % pool_rows == 0):
+            raise ValueError("_ConvBnActTC: a fused pool needs the statistics GEMM path, ReLU and no per-cloud bias")
+        if fused:
             z = torch.empty((P, Cout), dtype=torch.float32, device=dev)
             tiles = (P + 127) // 128
             cs = torch.empty((tiles, 2, Cout), dtype=torch.float32, device=dev)
@@ -485,9 +494,20 @@ class _ConvBnActTC(torch.autograd.Function):
                 _gemm_events.append((P, Cout, K, ev[0], ev[1]))
             nv.check(L.dgcnn_bn_stats_from_tiles(cs.data_ptr(), tiles, Cout, P, nv.ptr(gb), grows, mean.data_ptr(),
                                                  rstd.data_ptr(), st), "bn_stats_from_tiles")
-            nv.check(L.dgcnn_bn_apply_fwd_sinks(z.data_ptr(), P, Cout, beta.data_ptr(), 0, nv.ptr(gb), grows,
-                                                int(bool(relu_flag)), mean.data_ptr(), rstd.data_ptr(), out.data_ptr(),
-                                                n_s, s_ptr, s_ld, s_pe, st), "bn_apply_fwd")
+            if pool_rows:
+                G = P // pool_rows
+                pmax = torch.empty((G, Cout), dtype=torch.float32, device=dev)
+                pcnt = torch.empty((G, Cout), dtype=torch.float32, device=dev)
+                pws = nv.workspace(dev, L.dgcnn_bn_pool_workspace_bytes(G, Cout), "pool")
+                # when the planes take the output (n_s > 0) nobody reads the fp32 copy: `out` stays an unwritten handle
+                nv.check(L.dgcnn_bn_apply_fwd_pool(z.data_ptr(), P, Cout, beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                   0 if n_s else out.data_ptr(), pool_rows, pmax.data_ptr(), pcnt.data_ptr(),
+                                                   pws.data_ptr(), pws.numel(), n_s, s_ptr, s_ld, s_pe, st),
+                         "bn_apply_fwd_pool")
+            else:
+                nv.check(L.dgcnn_bn_apply_fwd_sinks(z.data_ptr(), P, Cout, beta.data_ptr(), 0, nv.ptr(gb), grows,
+                                                    int(bool(relu_flag)), mean.data_ptr(), rstd.data_ptr(), out.data_ptr(),
+                                                    n_s, s_ptr, s_ld, s_pe, st), "bn_apply_fwd")
         else:
             z = _tc_gemm_raw(planes, pw, P, Cout, K, 0, 0)
             ws = nv.workspace(dev, L.dgcnn_bn_workspace_bytes(Cout), "stats")
@@ -496,17 +516,19 @@ class _ConvBnActTC(torch.autograd.Function):
                                               ws.data_ptr(), ws.numel(), n_s, s_ptr, s_ld, s_pe, st), "bn_act_fwd")
         if n_s:
             sk.mark(out.data_ptr(), Cout, Cout, s_lst)
-        ctx.save_for_backward(planes, pw, z, beta, mean, rstd, gb)   # the ReLU mask is re-evaluated from z in backward
-        ctx.widths, ctx.relu, ctx.grows = widths, bool(relu_flag), grows
-        return out
+        ctx.save_for_backward(planes, pw, z, beta, mean, rstd, gb, pmax, pcnt)   # the ReLU mask is re-evaluated from z
+        ctx.widths, ctx.relu, ctx.grows, ctx.pool_rows = widths, bool(relu_flag), grows, pool_rows
+        return out, pmax
 
     @staticmethod
-    def backward(ctx, g):
-        planes, pw, z, beta, mean, rstd, gb = ctx.saved_tensors
+    def backward(ctx, g, gpool):
+        planes, pw, z, beta, mean, rstd, gb, pmax, pcnt = ctx.saved_tensors
         _, P, K = planes.shape
         Cout = pw.shape[2]
-        g = nv.require_cuda(g, "grad")
-        dev = g.device
+        dev = z.device
+        g = nv.require_cuda(g, "grad") if g is not None else torch.zeros_like(z)
+        if pmax is not None:
+            gpool = nv.require_cuda(gpool, "grad pooled") if gpool is not None else torch.zeros_like(pmax)
         L = nv.lib()
         ws = nv.workspace(dev, L.dgcnn_bn_workspace_bytes(Cout), "stats")
         pg = torch.empty((planes.shape[0], P, Cout), dtype=torch.bfloat16, device=dev)
@@ -514,16 +536,17 @@ class _ConvBnActTC(torch.autograd.Function):
         gbeta = torch.empty(Cout, dtype=torch.float32, device=dev)
         nv.check(L.dgcnn_bn_act_bwd_planes(z.data_ptr(), 0, beta.data_ptr(), g.data_ptr(), P, Cout, mean.data_ptr(),
                                            rstd.data_ptr(), nv.ptr(gb), ctx.grows, int(ctx.relu), nv.ptr(gz),
-                                           pg.data_ptr(), pg.shape[0], gbeta.data_ptr(), ws.data_ptr(), ws.numel(),
-                                           nv.stream_ptr(dev)), "bn_act_bwd_planes")
+                                           pg.data_ptr(), pg.shape[0], gbeta.data_ptr(), nv.ptr(pmax), nv.ptr(pcnt),
+                                           nv.ptr(gpool) if pmax is not None else 0, ctx.pool_rows, ws.data_ptr(),
+                                           ws.numel(), nv.stream_ptr(dev)), "bn_act_bwd_planes")
         gw = ggb = None
         with _SideStream(dev, planes, pg, gz):
             if ctx.needs_input_grad[0]:
                 gw = _tc_gemm_raw(planes, pg, K, Cout, P, 1, 0)                                # X^T . g_z
         if gb is not None:
             ggb = gz.view(gb.shape[0], ctx.grows, Cout).sum(dim=1)
-        return tuple([gw, gbeta, ggb, None, None, None] +
-                     _tc_dx_sources(pg, pw, P, K, Cout, ctx.widths, ctx.needs_input_grad[6:]))
+        return tuple([gw, gbeta, ggb, None, None, None, None] +
+                     _tc_dx_sources(pg, pw, P, K, Cout, ctx.widths, ctx.needs_input_grad[7:]))
 
 
 def conv1x1(srcs, w) -> torch.Tensor:

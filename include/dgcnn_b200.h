@@ -212,7 +212,22 @@ int dgcnn_bn_apply_fwd_sinks(const float* z, int64_t rows, int C, const float* b
                              const int64_t* sink_plane_elems, dgcnn_stream_t stream);
 int dgcnn_bn_act_bwd_planes(const float* z, const float* out, const float* beta, const float* g_out, int64_t rows, int C,
                             const float* mean, const float* rstd, const float* group_bias, int group_rows, int relu,
-                            float* g_z, void* g_z_planes, int n_planes, float* g_beta, void* ws, size_t ws_bytes,
+                            float* g_z, void* g_z_planes, int n_planes, float* g_beta, const float* pool_max,
+                            const float* pool_cnt, const float* pool_grad, int pool_rows, void* ws, size_t ws_bytes,
+                            dgcnn_stream_t stream);
+
+/* A layer whose output is ALSO max-pooled over the rows of each group (MergedEdgeConv followed by max_pool_v2 over the
+ * N points of a cloud, model.py:65-81), without a pass of its own for the pool:
+ *   apply_fwd_pool : out = relu((z - mean) * rstd + beta) to the plane sinks and, if out != NULL, as fp32 (when every
+ *                    consumer reads the planes the fp32 copy is never written); pool_max / pool_cnt [rows/pool_rows, C]
+ *                    = maximum of each group and the number of rows attaining it.  ws: dgcnn_bn_pool_workspace_bytes.
+ *   bwd_planes     : with pool_max / pool_cnt / pool_grad given (NULL = no pool), the pool's gradient
+ *                    [out == pool_max] * pool_grad / pool_cnt (ties share, like tf.reduce_max / MaxPoolGrad) is added to
+ *                    g_out on the fly; out is re-evaluated from z (pass out = NULL and beta).                          */
+size_t dgcnn_bn_pool_workspace_bytes(int groups, int C);
+int dgcnn_bn_apply_fwd_pool(const float* z, int64_t rows, int C, const float* beta, const float* mean, const float* rstd,
+                            float* out, int pool_rows, float* pool_max, float* pool_cnt, void* ws, size_t ws_bytes,
+                            int n_sinks, void* const* sink_planes, const int* sink_lds, const int64_t* sink_plane_elems,
                             dgcnn_stream_t stream);
 
 /* ---- global max over the points of each cloud: gen_nn_ops.max_pool_v2 ksize [1,N,1,1], model.py:77 ----------

@@ -93,7 +93,7 @@ def test_bn_backward_planes_equal_fp32_path(dg, cuda):
     planes = torch.empty((2, P, C), dtype=torch.bfloat16, device=cuda)
     gz, gb = torch.empty_like(z), torch.empty(C, device=cuda)
     nv.check(L.dgcnn_bn_act_bwd_planes(z.data_ptr(), 0, beta.data_ptr(), go.data_ptr(), P, C, mean.data_ptr(),
-                                       rstd.data_ptr(), 0, 0, 1, gz.data_ptr(), planes.data_ptr(), 2, gb.data_ptr(),
+                                       rstd.data_ptr(), 0, 0, 1, gz.data_ptr(), planes.data_ptr(), 2, gb.data_ptr(), 0, 0, 0, 0,
                                        ws.data_ptr(), ws.numel(), st), "bwd planes")
     assert torch.equal(gz, gz_ref) and torch.equal(gb, gb_ref)
     rec = planes[0].float() + planes[1].float()
