@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(256)
       y[i] = relu ? fmaxf(t, 0.f) : t;
     }
     if (VEC == 4) {
-      *reinterpret_cast<float4*>(out + e) = *reinterpret_cast<float4*>(y);
+      if (out) *reinterpret_cast<float4*>(out + e) = *reinterpret_cast<float4*>(y);   // null: only the planes are wanted
       if (sinks.n > 0) {
         __nv_bfloat16 h[4], l[4];
 #pragma unroll
@@ -711,7 +711,7 @@ extern "C" int dgcnn_bn_apply_fwd_sinks(const float* z, int64_t rows, int C, con
     int rcs = bn_make_sinks(&sinks, n_sinks, sink_planes, sink_lds, sink_plane_elems, C);
     if (rcs) return rcs;
   }
-  DG_REQUIRE(z && beta && out && mean && rstd, DGCNN_ERR_INVALID, "bn_apply_fwd: null pointer");
+  DG_REQUIRE(z && beta && mean && rstd && (out || sinks.n > 0), DGCNN_ERR_INVALID, "bn_apply_fwd: null pointer");
   DG_REQUIRE(rows > 0 && C > 0, DGCNN_ERR_INVALID, "bn_apply_fwd: bad shape rows=%lld C=%d", (long long)rows, C);
   DG_REQUIRE(!group_bias || (group_rows > 0 && rows % group_rows == 0), DGCNN_ERR_INVALID,
              "bn_apply_fwd: rows=%lld is not a multiple of group_rows=%d", (long long)rows, group_rows);
@@ -720,7 +720,8 @@ extern "C" int dgcnn_bn_apply_fwd_sinks(const float* z, int64_t rows, int C, con
   DG_REQUIRE(total < (1ll << 32), DGCNN_ERR_UNSUPPORTED, "bn_apply_fwd: more than 2^32 elements");
   const bool vec = (C & 3) == 0 && (((uintptr_t)z | (uintptr_t)out | (uintptr_t)residual | (uintptr_t)group_bias |
                                      (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)beta) & 15) == 0;
-  DG_REQUIRE(vec || sinks.n == 0, DGCNN_ERR_INVALID, "bn_apply_fwd: plane sinks need C %% 4 == 0 and 16-byte aligned buffers");
+  DG_REQUIRE(vec || (sinks.n == 0 && out), DGCNN_ERR_INVALID,
+             "bn_apply_fwd: plane sinks need C %% 4 == 0 and 16-byte aligned buffers");
   if (vec)
     bn_act_fwd_kernel<4><<<ew_blocks(total / 4), 256, 0, st>>>(z, mean, rstd, beta, residual, relu, (uint32_t)(total / 4), C,
                                                                out, group_bias, group_rows, sinks);

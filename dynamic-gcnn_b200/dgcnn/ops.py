@@ -505,9 +505,12 @@ class _ConvBnActTC(torch.autograd.Function):
                                                    pws.data_ptr(), pws.numel(), n_s, s_ptr, s_ld, s_pe, st),
                          "bn_apply_fwd_pool")
             else:
+                # a layer whose output goes to plane sinks has only tensor-core consumers (model._make_sinks): like the
+                # pooled layer above, its fp32 copy is then never read and `out` stays an unwritten handle
                 nv.check(L.dgcnn_bn_apply_fwd_sinks(z.data_ptr(), P, Cout, beta.data_ptr(), 0, nv.ptr(gb), grows,
-                                                    int(bool(relu_flag)), mean.data_ptr(), rstd.data_ptr(), out.data_ptr(),
-                                                    n_s, s_ptr, s_ld, s_pe, st), "bn_apply_fwd")
+                                                    int(bool(relu_flag)), mean.data_ptr(), rstd.data_ptr(),
+                                                    0 if (n_s and _FUSE_POOL) else out.data_ptr(), n_s, s_ptr, s_ld, s_pe,
+                                                    st), "bn_apply_fwd")
         else:
             z = _tc_gemm_raw(planes, pw, P, Cout, K, 0, 0)
             ws = nv.workspace(dev, L.dgcnn_bn_workspace_bytes(Cout), "stats")

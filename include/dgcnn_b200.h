@@ -201,7 +201,8 @@ int dgcnn_bn_apply_fwd(const float* z, int64_t rows, int C, const float* beta, c
                        float* out, dgcnn_stream_t stream);
 /* ..._sinks: the same forward passes with up to two plane sinks (host arrays of n_sinks entries: device pointer of the
  * first element of the column slice, row pitch, distance of the lo plane in elements): the output is also written as
- * bf16 hi / lo planes into the operands of the layers that consume it.                                             */
+ * bf16 hi / lo planes into the operands of the layers that consume it.  apply_fwd_sinks: out may be NULL when there is
+ * at least one sink (every consumer reads the planes: the fp32 copy is not written at all).                          */
 int dgcnn_bn_act_fwd_sinks(const float* z, int64_t rows, int C, const float* beta, const float* residual,
                            const float* group_bias, int group_rows, int relu, float* out, float* mean, float* rstd,
                            void* ws, size_t ws_bytes, int n_sinks, void* const* sink_planes, const int* sink_lds,
