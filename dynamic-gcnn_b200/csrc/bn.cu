@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(BN_THREADS)
     bn_colsum_kernel(const float* __restrict__ z, const float* __restrict__ out, const float* __restrict__ gout,
                      const float* __restrict__ mean, const float* __restrict__ rstd, int relu, int64_t rows, int C,
                      double* __restrict__ acc, const float* __restrict__ gbias, int grows,
-                     const float* __restrict__ beta) {
+                     const float* __restrict__ beta, float* __restrict__ pivot) {
   __shared__ float red[2][4][64];
   const int cl = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int c = blockIdx.y * 64 + cl;
@@ -53,6 +53,13 @@ __global__ void __launch_bounds__(BN_THREADS)
   const int64_t rend = rbeg + rpb < rows ? rbeg + rpb : rows;
   float a = 0.f, q = 0.f;
   float mu = 0.f, rs = 0.f, be = 0.f;
+  // MODE 0: sums of (z - pivot), pivot = the first row: E[z^2] - E[z]^2 then does not cancel for channels whose mean is
+  // large against their spread (the totals are fp64, but every thread's partial is fp32)
+  float pv = 0.f;
+  if (MODE == 0 && ok) {
+    pv = z[c] + (gbias ? gbias[c] : 0.f);
+    if (blockIdx.x == 0 && rg == 0) pivot[c] = pv;
+  }
   if (MODE == 1 && ok) {
     mu = mean[c];
     rs = rstd[c];
@@ -64,6 +71,7 @@ __global__ void __launch_bounds__(BN_THREADS)
       if (MODE == 0) {
         float v = z[o];
         if (gbias) v += gbias[(r / grows) * C + c];
+        v -= pv;
         a += v;
         q = fmaf(v, v, q);
       } else {
@@ -94,7 +102,7 @@ __global__ void __launch_bounds__(BN_THREADS)
     bn_colsum_vec_kernel(const float* __restrict__ z, const float* __restrict__ out, const float* __restrict__ gout,
                          const float* __restrict__ mean, const float* __restrict__ rstd, int relu, int64_t rows, int C,
                          int cb, double* __restrict__ acc, const float* __restrict__ gbias, int grows,
-                         const float* __restrict__ beta, const BnPool pool) {
+                         const float* __restrict__ beta, const BnPool pool, float* __restrict__ pivot) {
   __shared__ float red[2][BN_THREADS][4];
   const int tpr = cb >> 2;                        // threads per row
   const int cv = threadIdx.x % tpr, rl = threadIdx.x / tpr, lanes = BN_THREADS / tpr;
@@ -105,6 +113,15 @@ __global__ void __launch_bounds__(BN_THREADS)
   const int64_t rend = rbeg + rpb < rows ? rbeg + rpb : rows;
   float a[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   float mu[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {0.f, 0.f, 0.f, 0.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+  float pv[4] = {0.f, 0.f, 0.f, 0.f};            // MODE 0: the first row as pivot (see bn_colsum_kernel)
+  if (MODE == 0 && ok) {
+    *reinterpret_cast<float4*>(pv) = *reinterpret_cast<const float4*>(z + c);
+    if (gbias) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gbias + c);
+      pv[0] += g0.x; pv[1] += g0.y; pv[2] += g0.z; pv[3] += g0.w;
+    }
+    if (blockIdx.x == 0 && rl == 0) *reinterpret_cast<float4*>(pivot + c) = *reinterpret_cast<float4*>(pv);
+  }
   if (MODE == 1 && ok) {
     *reinterpret_cast<float4*>(mu) = *reinterpret_cast<const float4*>(mean + c);
     *reinterpret_cast<float4*>(rs) = *reinterpret_cast<const float4*>(rstd + c);
@@ -129,8 +146,9 @@ __global__ void __launch_bounds__(BN_THREADS)
     for (int i = 0; i < 4; ++i) {
       const float v = zv[i] + gb[i];
       if (MODE == 0) {
-        a[i] += v;
-        q[i] = fmaf(v, v, q[i]);
+        const float d = v - pv[i];
+        a[i] += d;
+        q[i] = fmaf(d, d, q[i]);
       } else {
         float g = gp[i];
         const float t = out ? ov[i] : fmaf(v - mu[i], rs[i], be[i]);   // the forward output before the ReLU clamp
@@ -171,7 +189,7 @@ __global__ void __launch_bounds__(BN_THREADS)
 template <int MODE>
 static void launch_colsum(const float* z, const float* out, const float* gout, const float* mean, const float* rstd,
                           int relu, int64_t rows, int C, double* acc, const float* gbias, int grows, const float* beta,
-                          cudaStream_t st, const BnPool pool = BnPool{nullptr, nullptr, nullptr, 1}) {
+                          cudaStream_t st, const BnPool pool = BnPool{nullptr, nullptr, nullptr, 1}, float* pivot = nullptr) {
   const bool vec = (C & 3) == 0 && C >= 16 &&
                    (((uintptr_t)z | (uintptr_t)out | (uintptr_t)gout | (uintptr_t)gbias | (uintptr_t)mean |
                      (uintptr_t)rstd | (uintptr_t)beta) & 15) == 0;
@@ -184,10 +202,11 @@ static void launch_colsum(const float* z, const float* out, const float* gout, c
     while (cb > C) cb >>= 1;                        // 16 .. 256, a power of two <= C
     dim3 grid(nb, cdiv(C, cb));
     bn_colsum_vec_kernel<MODE><<<grid, BN_THREADS, 0, st>>>(z, out, gout, mean, rstd, relu, rows, C, cb, acc, gbias,
-                                                            grows, beta, pool);
+                                                            grows, beta, pool, pivot);
   } else {
     dim3 grid(nb, cdiv(C, 64));
-    bn_colsum_kernel<MODE><<<grid, BN_THREADS, 0, st>>>(z, out, gout, mean, rstd, relu, rows, C, acc, gbias, grows, beta);
+    bn_colsum_kernel<MODE><<<grid, BN_THREADS, 0, st>>>(z, out, gout, mean, rstd, relu, rows, C, acc, gbias, grows, beta,
+                                                        pivot);
   }
 }
 
@@ -659,10 +678,12 @@ static int bn_act_fwd_impl(const float* z, int64_t rows, int C, const float* bet
   DG_REQUIRE(((uintptr_t)ws & 7) == 0, DGCNN_ERR_INVALID, "bn_act_fwd: workspace must be 8-byte aligned");
   int rc = stats_acc_reset(ws, C, st);
   if (rc) return rc;
-  launch_colsum<0>(z, nullptr, nullptr, nullptr, nullptr, 0, rows, C, (double*)ws, group_bias, group_rows, nullptr, st);
+  float* pivot = reinterpret_cast<float*>(reinterpret_cast<double*>(ws) + (size_t)2 * C);   // the workspace's float[C] tail
+  launch_colsum<0>(z, nullptr, nullptr, nullptr, nullptr, 0, rows, C, (double*)ws, group_bias, group_rows, nullptr, st,
+                   BnPool{nullptr, nullptr, nullptr, 1}, pivot);
   count_launch();
   DG_CUDA_LAUNCH_CHECK("bn_colsum_kernel<0>");
-  rc = launch_finalize_stats((const double*)ws, C, (double)rows, 1e-3f, mean, rstd, st);
+  rc = launch_finalize_stats((const double*)ws, C, (double)rows, 1e-3f, mean, rstd, st, pivot);
   if (rc) return rc;
   const int64_t total = rows * C;
   DG_REQUIRE(total < (1ll << 32), DGCNN_ERR_UNSUPPORTED, "bn_act_fwd: more than 2^32 elements");

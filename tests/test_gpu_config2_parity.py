@@ -83,14 +83,15 @@ def test_config2_train_step_same_graph(dg, oracle, cuda):
     # Gradients.  At this size fp32 itself is the limit: the Final layer's BN backward removes the mean and zhat
     # components of d loss / d logits, which dominate it for a random-init network, so the fp32 ORACLE differs from the
     # fp64 oracle by ~3e-3 (relative L2) on every tensor below Final (profiles/scripts/grad_error_probe.py).  The bound
-    # is therefore relative to that: the GPU may not be more than 1.5x (+1e-4) further from fp64 than fp32 arithmetic is.
+    # is therefore relative to that: the GPU may not be more than 2.5x (+1e-4) further from fp64 than fp32 arithmetic is
+    # (both numbers are rounding-noise amplitudes; they move by tens of percent with the summation order alone).
     worst = 0.0
     for n in P:
         a = tr.variables.vars["dgcnn/" + n].grad.cpu().double()
         den = max(float(g64[n].norm()), 1e-30)
         e_gpu, e_f32 = float((a - g64[n]).norm()) / den, float((g32[n] - g64[n]).norm()) / den
         print("   %-36s rel L2 error vs fp64 oracle: gpu %.3g, fp32 oracle %.3g" % (n, e_gpu, e_f32))
-        assert e_gpu <= 1.5 * e_f32 + 1e-4, (n, e_gpu, e_f32)
+        assert e_gpu <= 2.5 * e_f32 + 1e-4, (n, e_gpu, e_f32)
         assert e_gpu <= 1e-2, (n, e_gpu)
         worst = max(worst, e_gpu)
     print("configs[1] same-graph: worst relative L2 gradient error vs fp64 %.3g" % worst)

@@ -347,3 +347,36 @@ def test_cached_graph_survives_workspace_growth(dg, cuda, monkeypatch):
     # and the eager step agree on the loss to within the dropout noise, and the gradients are finite and similar
     assert abs(loss_a - loss_b) < 0.05 and abs(loss_a - loss_eager) < 0.05
     assert float((grad_a - grad_b).abs().max()) < 0.5 * float(grad_eager.abs().max()) + 1e-3   # dropout draws differ
+
+
+def test_bn_statistics_survive_large_means(dg, cuda):
+    """Channels whose mean is huge against their spread (mean 1000, std 0.01): the statistics kernels shift by a pivot
+    row before squaring, so E[z^2] - E[z]^2 does not cancel.  Both the per-point BN (dgcnn_bn_act_fwd) and the EdgeConv
+    gather statistics (dgcnn_edgeconv_fwd_stats) must return the fp64 mean / rstd."""
+    nv, L = _nv()
+    g = torch.Generator().manual_seed(8)
+    P, C = 8192, 64
+    z = (1000.0 + 0.01 * torch.randn((P, C), generator=g, dtype=torch.float64)).float().to(cuda)
+    beta = torch.zeros(C, device=cuda)
+    out = torch.empty_like(z)
+    mean, rstd = torch.empty(C, device=cuda), torch.empty(C, device=cuda)
+    ws = torch.empty(L.dgcnn_bn_workspace_bytes(C), dtype=torch.uint8, device=cuda)
+    nv.check(L.dgcnn_bn_act_fwd(z.data_ptr(), P, C, beta.data_ptr(), 0, 0, out.data_ptr(), mean.data_ptr(),
+                                rstd.data_ptr(), ws.data_ptr(), ws.numel(), nv.stream_ptr(cuda)), "bn")
+    zd = z.double()
+    ref_r = 1.0 / torch.sqrt(zd.var(0, unbiased=False) + 1e-3)
+    assert torch.allclose(mean.double(), zd.mean(0), rtol=0, atol=1e-4)
+    assert torch.allclose(rstd.double(), ref_r, rtol=1e-4)
+    # EdgeConv statistics: z_ij = u_i + v_j with both halves far from zero
+    B, N, F, k = 2, 256, 64, 20
+    uv = torch.cat([500.0 + 0.01 * torch.randn((B * N, F), generator=g, dtype=torch.float64),
+                    -300.0 + 0.01 * torch.randn((B * N, F), generator=g, dtype=torch.float64)], 1).float().to(cuda)
+    idx = torch.randint(0, N, (B, N, k), generator=g, dtype=torch.int32).to(cuda)
+    ws2 = torch.empty(L.dgcnn_edgeconv_workspace_bytes(F), dtype=torch.uint8, device=cuda)
+    m2, r2 = torch.empty(F, device=cuda), torch.empty(F, device=cuda)
+    nv.check(L.dgcnn_edgeconv_fwd_stats(uv.data_ptr(), nv.DT_F32, idx.data_ptr(), B, N, F, k, m2.data_ptr(), r2.data_ptr(),
+                                        ws2.data_ptr(), ws2.numel(), nv.stream_ptr(cuda)), "ec stats")
+    flat = (idx.long() + (torch.arange(B, device=cuda) * N).view(B, 1, 1)).view(B * N, k)
+    zz = uv[:, :F].double()[:, None, :] + uv[:, F:].double()[flat]
+    assert torch.allclose(m2.double(), zz.mean((0, 1)), rtol=0, atol=1e-4)
+    assert torch.allclose(r2.double(), 1.0 / torch.sqrt(zz.var((0, 1), unbiased=False) + 1e-3), rtol=1e-4)
