@@ -298,9 +298,11 @@ def run_ours(args, cfg):
 
     def step(i, host):
         tr.zero_gradients(None)
-        res = tr.accum_gradient(None, feed(h_pts if host else d_pts, i), feed(h_lab if host else d_lab, i), sync=host)
+        res = tr.accum_gradient(None, feed(h_pts if host else d_pts, i), feed(h_lab if host else d_lab, i), sync=False)
         tr.apply_gradient(None)
-        return res[2]
+        # e2e: the loss is read back to the host every step -- after the optimizer step has been enqueued, so that the
+        # read waits for the device once instead of stalling the launch of the Adam kernel behind it
+        return float(res[2]) if host else res[2]
 
     def barrier():
         if world > 1:

@@ -160,10 +160,13 @@ def train_loop(flags, handlers):
             label_v, _ = _slices(flags, label, current_idx)
             weight_v, _ = _slices(flags, weight, current_idx)
             current_idx = nxt
-            res = trainer.accum_gradient(handlers.sess, data_v, label_v, weight_v)
+            res = trainer.accum_gradient(handlers.sess, data_v, label_v, weight_v, sync=False)
             accuracy_v.append(res[1])
             loss_v.append(res[2])
         trainer.apply_gradient(handlers.sess)
+        # loss / accuracy come back to the host once per iteration, after the optimizer step has been enqueued
+        accuracy_v = [float(a) for a in accuracy_v]
+        loss_v = [float(l) for l in loss_v]
         torch.cuda.synchronize()
         tspent_train = time.time() - t0
         tsum_train += tspent_train
