@@ -176,3 +176,32 @@ def test_cli_train_config1_plumbing(dg, cuda, tmp_path):
     csv = open(str(tmp_path / "log" / "train_log-0000000.csv")).read().splitlines()
     assert csv[0].startswith("iter,epoch,titer,ttrain,tio,tsave,tsummary") and len(csv) == 4
     assert os.path.exists(str(tmp_path / "w" / "snapshot-1"))
+
+
+def test_cli_inference_from_checkpoint(dg, cuda, tmp_path):
+    """bin/dgcnn.py train (2 iterations, checkpoint every step) then bin/dgcnn.py inference -mp <checkpoint> -of out.npz:
+    the reference's second sub-command (main_funcs.py:47-51,212-305) through the same files: softmax rows are stored per
+    entry in request order, sum to one, and the CSV carries the reference's inference columns."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = [sys.executable, os.path.join(root, "dynamic-gcnn_b200", "bin", "dgcnn.py")]
+    common = ["-io", "synthetic", "-bs", "2", "-mbs", "2", "-ecl", "2", "-kv", "16", "-np", "384", "-db", "0", "-sd", "3",
+              "-rs", "1"]
+    tr = subprocess.run(exe + ["train"] + common + ["-it", "2", "-wp", str(tmp_path / "w" / "snap"), "-chks", "1"],
+                        capture_output=True, text=True, timeout=600)
+    assert tr.returncode == 0, tr.stderr[-2000:]
+    ckpt = str(tmp_path / "w" / "snap-1")
+    assert os.path.exists(ckpt)
+    out = str(tmp_path / "pred.npz")
+    inf = subprocess.run(exe + ["inference"] + common + ["-it", "3", "-sh", "0", "-mp", ckpt, "-of", out,
+                                                         "-ld", str(tmp_path / "ilog")],
+                         capture_output=True, text=True, timeout=600)
+    assert inf.returncode == 0, inf.stderr[-2000:]
+    z = np.load(out)
+    # 3 iterations x 2 entries, in sequential order; the first batch (entries 0, 1) is consumed by prepare()'s throw-away
+    # next() exactly like the reference (main_funcs.py:66)
+    assert z["softmax"].shape == (6, 384, 2) and list(z["index"]) == [2, 3, 4, 5, 6, 7]
+    assert np.allclose(z["softmax"].sum(-1), 1.0, atol=1e-5)
+    csv = open(str(tmp_path / "ilog" / "inference_log-0000001.csv")).read().splitlines()
+    assert csv[0] == "iter,epoch,titer,tinference,tio,tsumiter,tsuminference,tsumio,loss,accuracy" and len(csv) == 4

@@ -207,3 +207,31 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["metric"].startswith("points/sec")
+
+
+def test_checkpoint_pruning_ignores_foreign_files(dg, tmp_path):
+    """_prune_checkpoints keeps the newest CHECKPOINT_NUM files named PREFIX-<iteration> and never touches (or trips over)
+    neighbours such as PREFIX-100.bak or PREFIX-final (main_funcs.py:82-83: Saver(max_to_keep))."""
+    from dgcnn.main_funcs import _prune_checkpoints
+    prefix = str(tmp_path / "snapshot")
+    for name in ("-3", "-10", "-200", "-100.bak", "-final"):
+        open(prefix + name, "w").close()
+    _prune_checkpoints(prefix, 2)
+    left = sorted(p.name for p in tmp_path.iterdir())
+    assert left == ["snapshot-10", "snapshot-100.bak", "snapshot-200", "snapshot-final"]
+
+
+def test_oracle_bf16_matmul_mode_is_scoped_and_close(oracle):
+    """oracle.bf16_matmul(): the yardstick of the reduced-precision variant rounds matmul operands to bf16 inside the
+    context only; outside it the fp32 path is untouched."""
+    import torch
+    fl = oracle.make_flags(EDGE_CONV_LAYERS=1, KVALUE=4, FC_FILTERS=[16, 8], TRAIN=False)
+    P = oracle.init_params(fl, 3, seed=1)
+    x = torch.rand((1, 32, 3), generator=torch.Generator().manual_seed(0))
+    ref = oracle.build(x, fl, P)
+    with oracle.bf16_matmul():
+        low = oracle.build(x, fl, P)
+    again = oracle.build(x, fl, P)
+    assert torch.equal(ref, again)
+    d = (low - ref).abs().max().item()
+    assert 0.0 < d < 0.2
