@@ -298,7 +298,7 @@ def run_ours(args, cfg):
 
     def step(i, host):
         tr.zero_gradients(None)
-        res = tr.accum_gradient(None, feed(h_pts if host else d_pts, i), feed(h_lab if host else d_lab, i), sync=False)
+        res = tr.accum_gradient(None, feed(h_pts if host else d_pts, i), feed(h_lab if host else d_lab, i), sync=False, last=True)
         tr.apply_gradient(None)
         # e2e: the loss is read back to the host every step -- after the optimizer step has been enqueued, so that the
         # read waits for the device once instead of stalling the launch of the Adam kernel behind it
@@ -379,8 +379,17 @@ def run_ours(args, cfg):
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Teardown must never hold the result hostage: the line above is out.  Captured graphs with NCCL nodes keep the
+        # communicator referenced (destroy_process_group would wait for them), so they go first; a watchdog ends the
+        # process if the teardown stalls all the same.
+        import threading
+        wd = threading.Timer(30.0, lambda: os._exit(0))
+        wd.daemon = True
+        wd.start()
+        tr.release_graphs()
         dist.barrier()
         dist.destroy_process_group()
+        wd.cancel()
 
 
 def main():

@@ -160,7 +160,8 @@ def train_loop(flags, handlers):
             label_v, _ = _slices(flags, label, current_idx)
             weight_v, _ = _slices(flags, weight, current_idx)
             current_idx = nxt
-            res = trainer.accum_gradient(handlers.sess, data_v, label_v, weight_v, sync=False)
+            res = trainer.accum_gradient(handlers.sess, data_v, label_v, weight_v, sync=False,
+                                         last=current_idx >= flags.BATCH_SIZE)
             accuracy_v.append(res[1])
             loss_v.append(res[2])
         trainer.apply_gradient(handlers.sess)

@@ -7,6 +7,11 @@ What changes underneath:
   * every trainable variable and its gradient live in ONE flat fp32 buffer.  Each tower's backward adds
     grad/len(GPUS) into it (accumulation over micro-steps is a SUM, trainval.py:79); apply_gradient() issues
     a single NCCL all-reduce(sum) of that buffer -- the only collective -- and one fused TF-form Adam kernel.
+  * with more than one rank, the LAST micro-step before apply_gradient() (accum_gradient(..., last=True)) reduces the
+    buffer itself, as two buckets: the head's gradients (MergedEdgeConv / FC / Final: 96 % of the bytes, finished first)
+    are all-reduced on NCCL's stream while the EdgeConv backward is still running, the rest when backward ends
+    (parallel.GradBuckets; both collectives are nodes of the captured CUDA graph).  DGCNN_OVERLAP_AR=0 keeps the single
+    all-reduce inside apply_gradient().
   * BatchNorm statistics stay per tower micro-batch (the reference's BN is per tower), so no SyncBN.
   * `sess` is accepted and ignored.
 """
@@ -21,7 +26,7 @@ import torch.distributed as dist
 
 from . import _native as nv
 from . import model as _model
-from .parallel import allreduce_flat_, tower_assignment
+from .parallel import GradBuckets, allreduce_flat_, head_split_offset, tower_assignment
 from .variables import VariableStore, set_default_store, default_store
 
 
@@ -68,9 +73,62 @@ class trainval(object):
             self._adam_m = torch.zeros(n, dtype=torch.float32, device=self._device)
             self._adam_v = torch.zeros(n, dtype=torch.float32, device=self._device)
             self._adam_t = 0
+        self._setup_overlap()
         self._sync_replicas()
         self.last_loss = None
         self.last_accuracy = None
+
+    def _setup_overlap(self):
+        """Gradient all-reduce overlapped with backward (module docstring).  Active with > 1 rank (DGCNN_OVERLAP_AR=force:
+        also on a 1-rank group, for tests); needs the head's variables to be the tail of the flat buffer."""
+        self._buckets, self._ovl, self._reduced, self._head = None, None, False, []
+        mode = os.environ.get("DGCNN_OVERLAP_AR", "1")
+        if not self._flags.TRAIN or mode == "0" or not (dist.is_available() and dist.is_initialized()):
+            return
+        if self._world <= 1 and mode != "force":
+            return
+        st = self._store
+        names = st.trainable_names()
+        split = head_split_offset(names, [st.vars[n].numel() for n in names])
+        if not split:
+            return
+        self._buckets = GradBuckets(st.flat_grad, split)
+        import atexit
+        import weakref
+        me = weakref.ref(self)
+        atexit.register(lambda: me() is not None and me().release_graphs())   # before the process group goes away
+        off = 0
+        for n in names:
+            if off >= split:
+                self._head.append(st.vars[n])
+                st.vars[n].register_post_accumulate_grad_hook(self._on_head_grad)
+            off += st.vars[n].numel()
+
+    def _on_head_grad(self, param):
+        """post-accumulate hook of every head variable.  When the last of them has its gradient (MergedEdgeConv's: the
+        head's backward is over, the EdgeConv stack's has not started) the head gradients are folded into the flat buffer
+        and their all-reduce starts; the autograd engine goes on with the EdgeConv backward meanwhile."""
+        ov = self._ovl
+        if ov is None or ov["fired"]:
+            return
+        ov["seen"] += 1
+        if ov["seen"] < len(self._head):
+            return
+        ov["fired"] = True
+        from . import ops as _ops
+        # On the SIDE stream (the one the head's weight-gradient GEMMs run on, ordered after everything queued on the main
+        # stream so far): the main stream is not held up -- it goes straight on to the EdgeConv backward, which keeps
+        # overlapping the dW GEMMs, the fold and the collective.  NCCL's stream forks from the side stream here and is
+        # joined by GradBuckets.wait() at the end of the micro-step.
+        with torch.cuda.stream(ov["stream"]):
+            with _ops._SideStream(self._device):
+                pairs = [(ov["views"][id(p)], p.grad) for p in self._head if p.grad is not None]
+                if pairs:
+                    torch._foreach_add_([v for v, _ in pairs], [g for _, g in pairs], alpha=1.0 / ov["G"])
+                    _ops._side_keep.extend(g for _, g in pairs)    # read on the side stream: alive until the join
+                for p in self._head:
+                    p.grad = None                               # folded: the end-of-backward accumulation skips them
+                self._buckets.reduce_head_async()
 
     def _sync_replicas(self):
         """Every rank starts from rank 0's variables (and optimizer state): replicas that differ would apply the averaged
@@ -162,8 +220,10 @@ class trainval(object):
     def _as_tensor(self, a):
         return a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))
 
-    def _tower_step_eager(self, pts, lab, wgt, G):
+    def _tower_step_eager(self, pts, lab, wgt, G, reduce_now=False):
         _, acc, loss = self._forward(pts, lab, wgt, want_softmax=False)
+        # loss / accuracy ride in the two trailing slots of the flat gradient buffer (tower mean: 1/len(GPUS) each)
+        self._store.flat_grad[-2:].add_(torch.stack([loss.detach(), acc.detach().to(loss.dtype)]), alpha=1.0 / G)
         # Every variable's .grad is a view into the flat gradient buffer.  Left in place, autograd would add into each of
         # them with its own small kernel (one per variable); instead the views step aside, backward hands over fresh
         # gradient tensors, and ONE multi-tensor kernel adds them, scaled by 1/len(GPUS) (the tower mean of
@@ -176,23 +236,35 @@ class trainval(object):
         from . import ops as _ops
         old_async = _ops._async_dw
         _ops._async_dw = os.environ.get("DGCNN_ASYNC_DW", "1") != "0"    # weight-gradient GEMMs on a side stream
+        if reduce_now:
+            self._ovl = {"seen": 0, "fired": False, "G": G, "stream": torch.cuda.current_stream(self._device),
+                         "views": {id(p): v for p, v in zip(params, views)}}
+        fired = False
         try:
             loss.backward()
             pairs = [(v, p.grad) for v, p in zip(views, params) if p.grad is not None]
         finally:
+            fired = bool(self._ovl and self._ovl["fired"])
+            self._ovl = None
             _ops.join_side_stream(self._device)
             _ops._async_dw = old_async
             for p, v in zip(params, views):
                 p.grad = v
         if pairs:
             torch._foreach_add_([v for v, _ in pairs], [g for _, g in pairs], alpha=1.0 / G)
+        if reduce_now:
+            if not fired:                                      # (a model whose head saw no gradient: nothing overlapped)
+                self._buckets.reduce_head_async()
+            self._buckets.reduce_tail()
+            self._buckets.wait()
         return acc.detach(), loss.detach()
 
-    def _tower_step(self, data_i, label_i, weight_i, G):
-        """forward + backward of one tower's micro-batch -> (accuracy, loss) 0-d device tensors."""
+    def _tower_step(self, data_i, label_i, weight_i, G, reduce_now=False):
+        """forward + backward of one tower's micro-batch -> (accuracy, loss) 0-d device tensors.  reduce_now: this is the
+        last micro-step before apply_gradient() and the two-bucket gradient all-reduce runs inside it."""
         use_graph = os.environ.get("DGCNN_CUDA_GRAPH", "1") != "0" and label_i is not None
         src_p = self._as_tensor(data_i)
-        key = (tuple(src_p.shape), weight_i is not None)
+        key = (tuple(src_p.shape), weight_i is not None, bool(reduce_now))
         if not hasattr(self, "_graphs"):
             from collections import OrderedDict
             self._graphs, self._graph_seen = OrderedDict(), {}
@@ -206,14 +278,15 @@ class trainval(object):
             seen = self._graph_seen.get(key, 0)
             if not use_graph or seen < self.GRAPH_WARMUP:
                 self._graph_seen[key] = seen + 1
-                return self._tower_step_eager(pts, lab, wgt, G)
+                return self._tower_step_eager(pts, lab, wgt, G, reduce_now)
             # capture: static inputs, private memory pool, side stream (torch.cuda.graph does the stream dance)
             ent = {"pts": pts.clone(), "lab": lab.clone(), "wgt": wgt.clone() if wgt is not None else None}
             torch.cuda.synchronize(self._device)
             n0 = nv.launch_count()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                acc, loss = self._tower_step_eager(ent["pts"], ent["lab"], ent["wgt"], G)
+            # (with collectives inside, other threads -- NCCL's watchdog -- may query events while this one captures)
+            with torch.cuda.graph(graph, capture_error_mode="thread_local" if reduce_now else "global"):
+                acc, loss = self._tower_step_eager(ent["pts"], ent["lab"], ent["wgt"], G, reduce_now)
             # the captured kernels have the current scratch buffers' addresses baked in: the entry keeps them alive, so
             # that a later, larger request (another N, an eager inference call) that replaces a buffer in the cache
             # cannot hand this graph's scratch to the allocator while the graph can still be replayed
@@ -237,25 +310,33 @@ class trainval(object):
         nv.add_replayed_launches(ent["launches"])
         return ent["acc"], ent["loss"]
 
-    def accum_gradient(self, sess, data, label, weight=None, summary=False, sync=True):
+    def accum_gradient(self, sess, data, label, weight=None, summary=False, sync=True, last=False):
         """trainval.py:110-119 -> [None, accuracy, loss(, summary)].  Adds this micro-batch's tower-averaged
-        gradient into the flat accumulator.  sync=False returns 0-d device tensors instead of floats."""
+        gradient into the flat accumulator.  sync=False returns 0-d device tensors instead of floats.
+        last=True: the caller promises that apply_gradient() comes next; with more than one rank the gradient
+        all-reduce then runs inside this call, overlapped with the backward pass (no effect on the result)."""
         if not self._flags.TRAIN:
             raise NotImplementedError
+        if self._reduced:
+            raise RuntimeError("accum_gradient(last=True) must be followed by apply_gradient()")
         G = float(len(self._flags.GPUS))
         accs, losses = [], []
+        reduce_here = bool(last) and self._buckets is not None
         for i in self._towers:
             acc, loss = self._tower_step(data[i], label[i] if label is not None else None,
-                                         weight[i] if weight is not None else None, G)
+                                         weight[i] if weight is not None else None, G,
+                                         reduce_now=reduce_here and i == self._towers[-1])
             accs.append(acc)
             losses.append(loss)
+        if reduce_here:
+            if not self._towers:                   # a rank without a tower still takes part in the collectives
+                self._buckets.reduce_head_async()
+                self._buckets.reduce_tail()
+                self._buckets.wait()
+            self._reduced = True
         if losses:
             acc = torch.stack(accs).mean()
             loss = torch.stack(losses).mean()
-            fg = self._store.flat_grad
-            scale = len(self._towers) / G
-            fg[-2] += loss * scale
-            fg[-1] += acc * scale
         else:
             acc = loss = torch.zeros((), device=self._device)
         res = [None, acc, loss] if not sync else [None, float(acc), float(loss)]
@@ -263,10 +344,19 @@ class trainval(object):
             res.append({"accuracy": float(acc), "loss": float(loss)})
         return res
 
+    def release_graphs(self):
+        """Drop every captured micro-step (and the memory pools they own).  Captured graphs that contain NCCL nodes keep
+        their communicator referenced: dist.destroy_process_group() waits for them, so call this first."""
+        if getattr(self, "_graphs", None):
+            torch.cuda.synchronize(self._device)
+            self._graphs.clear()
+            torch.cuda.synchronize(self._device)
+
     def zero_gradients(self, sess=None):
         if not self._flags.TRAIN:
             raise NotImplementedError
         self._store.flat_grad.zero_()
+        self._reduced = False
         return [None]
 
     def apply_gradient(self, sess=None):
@@ -275,7 +365,10 @@ class trainval(object):
             raise NotImplementedError
         st = self._store
         fg = st.flat_grad
-        allreduce_flat_(fg)                                      # towers were pre-divided by len(GPUS)
+        if self._reduced:
+            self._reduced = False                                # the last micro-step reduced both buckets already
+        else:
+            allreduce_flat_(fg)                                  # towers were pre-divided by len(GPUS)
         n = st.num_trainable
         self.last_loss, self.last_accuracy = fg[-2], fg[-1]      # summed over micro-steps, mean over towers
         self._adam_t += 1

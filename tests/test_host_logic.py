@@ -158,6 +158,77 @@ def test_two_rank_allreduce_equals_tower_mean_summed_over_microsteps():
     assert torch.equal(got[0], got[1])
 
 
+def _bucket_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dynamic-gcnn_b200"))
+    from dgcnn.parallel import GradBuckets, allreduce_flat_, head_split_offset
+    from dgcnn.variables import VariableStore
+    st = VariableStore(device="cpu", seed=0)
+    with st.variable_scope("dgcnn"):
+        with st.variable_scope("EdgeConv0"):
+            with st.variable_scope("conv0"):
+                w0 = st.get_variable("weights", (3, 4), "xavier")
+        with st.variable_scope("FC0"):
+            w1 = st.get_variable("weights", (4, 2), "xavier")
+    st.flatten(extra=2)
+    names = st.trainable_names()
+    split = head_split_offset(names, [st.vars[n].numel() for n in names])
+    g = torch.Generator().manual_seed(11 + rank)            # every rank its own micro-batch
+    x = torch.randn(6, 3, generator=g)
+    loss = (torch.relu(x @ w0) @ w1).pow(2).mean()
+    # the trainer's sequence: loss slot, head gradient folded -> head bucket starts, tail folded -> tail bucket, wait
+    views = [w0.grad, w1.grad]
+    w0.grad = w1.grad = None
+    loss.backward()
+    st.flat_grad[-2:].add_(torch.stack([loss.detach(), torch.tensor(float(rank))]), alpha=0.5)
+    bk = GradBuckets(st.flat_grad, split)
+    views[1].add_(w1.grad, alpha=0.5)
+    bk.reduce_head_async()
+    views[0].add_(w0.grad, alpha=0.5)
+    bk.reduce_tail()
+    bk.wait()
+    two = st.flat_grad.clone()
+    # the single all-reduce of the same local sums
+    st.flat_grad.zero_()
+    views[0].add_(w0.grad, alpha=0.5)
+    views[1].add_(w1.grad, alpha=0.5)
+    st.flat_grad[-2:].add_(torch.stack([loss.detach(), torch.tensor(float(rank))]), alpha=0.5)
+    allreduce_flat_(st.flat_grad)
+    q.put((rank, split, two, st.flat_grad.clone()))
+    dist.destroy_process_group()
+
+
+def test_two_bucket_overlapped_allreduce_equals_single_allreduce():
+    """parallel.GradBuckets (head bucket reduced while the rest of backward runs, tail bucket after) gives exactly the
+    flat buffer a single all-reduce gives; head_split_offset finds the head as the tail of the declaration order."""
+    from dgcnn.parallel import GradBuckets, head_split_offset
+    names = ["dgcnn/EdgeConv0/conv0/weights", "dgcnn/EdgeConv0/conv0/BatchNorm/beta", "dgcnn/MergedEdgeConv/weights",
+             "dgcnn/FC0/weights", "dgcnn/FC1/BatchNorm/beta", "dgcnn/Final/weights"]
+    assert head_split_offset(names, [384, 64, 1000, 10, 5, 2]) == 448
+    assert head_split_offset(names[:2], [384, 64]) is None                       # no head at all
+    assert head_split_offset(names[2:], [1000, 10, 5, 2]) is None                # nothing below the head
+    assert head_split_offset([names[2], names[0]], [1000, 384]) is None           # head is not a suffix
+    assert head_split_offset(["dgcnn/EdgeConv1/conv1/weights", "dgcnn/Final/weights"], [8192, 128]) == 8192   # -nofc
+    with pytest.raises(ValueError):
+        GradBuckets(torch.zeros(8), 8)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, split, two, one in got:
+        assert split == 12
+        assert torch.equal(two, one)
+    assert torch.equal(got[0][2], got[1][2])
+    assert got[0][2][-1].item() == 0.5                                            # (0 + 1) / 2: the accuracy slot
+
+
 def test_plane_sink_layout_matches_the_concat_order():
     """model._make_sinks: the column each producer is told to fill equals the position of its tensor in the
     reference's concats (model.py:60-63 MergedEdgeConv input; model.py:83-85 FC0 input = tensors ++ merged)."""
