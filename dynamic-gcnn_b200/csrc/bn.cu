@@ -96,11 +96,13 @@ __global__ void __launch_bounds__(BN_THREADS)
 }
 
 // The same reduction with 16-byte loads (C % 4 == 0, 16-byte aligned buffers): a thread owns 4 consecutive channels,
-// a block covers CB = min(C, 256) channels x (256 / (CB/4)) row lanes, two rows in flight per thread.
-template <int MODE>
-__global__ void __launch_bounds__(BN_THREADS)
+// a block covers CB = min(C, 256) channels x (256 / (CB/4)) row lanes, U rows in flight per thread (all of a batch's
+// loads are issued before the first is consumed).  Row indices are 32-bit (rows < 2^31 is checked by the callers'
+// 2^32-element limit): the per-row group / pool divisions are 32-bit ones.
+template <int MODE, int U>
+__global__ void __launch_bounds__(BN_THREADS, U == 2 ? 3 : 2)
     bn_colsum_vec_kernel(const float* __restrict__ z, const float* __restrict__ out, const float* __restrict__ gout,
-                         const float* __restrict__ mean, const float* __restrict__ rstd, int relu, int64_t rows, int C,
+                         const float* __restrict__ mean, const float* __restrict__ rstd, int relu, int rows, int C,
                          int cb, double* __restrict__ acc, const float* __restrict__ gbias, int grows,
                          const float* __restrict__ beta, const BnPool pool, float* __restrict__ pivot) {
   __shared__ float red[2][BN_THREADS][4];
@@ -108,9 +110,9 @@ __global__ void __launch_bounds__(BN_THREADS)
   const int cv = threadIdx.x % tpr, rl = threadIdx.x / tpr, lanes = BN_THREADS / tpr;
   const int c = blockIdx.y * cb + cv * 4;
   const bool ok = c < C;
-  const int64_t rpb = (rows + gridDim.x - 1) / gridDim.x;
-  const int64_t rbeg = (int64_t)blockIdx.x * rpb;
-  const int64_t rend = rbeg + rpb < rows ? rbeg + rpb : rows;
+  const int rpb = (rows + gridDim.x - 1) / gridDim.x;
+  const int rbeg = blockIdx.x * rpb;
+  const int rend = rbeg + rpb < rows ? rbeg + rpb : rows;
   float a[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   float mu[4] = {0.f, 0.f, 0.f, 0.f}, rs[4] = {0.f, 0.f, 0.f, 0.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
   float pv[4] = {0.f, 0.f, 0.f, 0.f};            // MODE 0: the first row as pivot (see bn_colsum_kernel)
@@ -127,47 +129,52 @@ __global__ void __launch_bounds__(BN_THREADS)
     *reinterpret_cast<float4*>(rs) = *reinterpret_cast<const float4*>(rstd + c);
     if (beta) *reinterpret_cast<float4*>(be) = *reinterpret_cast<const float4*>(beta + c);
   }
-  auto step = [&](int64_t r) {
-    const int64_t o = r * C + c;
-    float zv[4], gp[4], ov[4], gb[4] = {0.f, 0.f, 0.f, 0.f};
-    *reinterpret_cast<float4*>(zv) = *reinterpret_cast<const float4*>(z + o);
-    if (MODE == 1) {
-      *reinterpret_cast<float4*>(gp) = *reinterpret_cast<const float4*>(gout + o);
-      if (relu && out) *reinterpret_cast<float4*>(ov) = *reinterpret_cast<const float4*>(out + o);
-    }
-    if (gbias) *reinterpret_cast<float4*>(gb) = *reinterpret_cast<const float4*>(gbias + (r / grows) * C + c);
-    float pm[4];
-    int64_t po = 0;
-    if (MODE == 1 && pool.pmax) {
-      po = (r / pool.rows) * C + c;
-      *reinterpret_cast<float4*>(pm) = __ldg(reinterpret_cast<const float4*>(pool.pmax + po));
-    }
+  const bool use_out = MODE == 1 && relu && out;
+  if (ok) {
+    for (int rb = rbeg + rl; rb < rend; rb += U * lanes) {
+      float zv[U][4], gp[U][4], ov[U][4], gb[U][4], pm[U][4];
+      bool live[U];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float v = zv[i] + gb[i];
-      if (MODE == 0) {
-        const float d = v - pv[i];
-        a[i] += d;
-        q[i] = fmaf(d, d, q[i]);
-      } else {
-        float g = gp[i];
-        const float t = out ? ov[i] : fmaf(v - mu[i], rs[i], be[i]);   // the forward output before the ReLU clamp
-        // the pooled copy of this output: its gradient goes to the arg-max rows (ties share); a hit is rare, so the
-        // count and the pooled gradient are fetched only then
-        if (pool.pmax && fmaxf(t, 0.f) == pm[i]) g += __ldg(pool.pgrad + po + i) / __ldg(pool.pcnt + po + i);
-        if (relu && !(t > 0.f)) g = 0.f;
-        a[i] += g;
-        q[i] = fmaf(g, (v - mu[i]) * rs[i], q[i]);
+      for (int u = 0; u < U; ++u) {                  // every load of the batch first
+        const int r = rb + u * lanes;
+        live[u] = r < rend;
+        const int rr = live[u] ? r : rend - 1;       // clamped duplicate, skipped below
+        const size_t o = (size_t)rr * C + c;
+        *reinterpret_cast<float4*>(zv[u]) = *reinterpret_cast<const float4*>(z + o);
+        if (MODE == 1) {
+          *reinterpret_cast<float4*>(gp[u]) = *reinterpret_cast<const float4*>(gout + o);
+          if (use_out) *reinterpret_cast<float4*>(ov[u]) = *reinterpret_cast<const float4*>(out + o);
+        }
+        if (gbias) *reinterpret_cast<float4*>(gb[u]) = __ldg(reinterpret_cast<const float4*>(gbias + (size_t)(rr / grows) * C + c));
+        if (MODE == 1 && pool.pmax)
+          *reinterpret_cast<float4*>(pm[u]) = __ldg(reinterpret_cast<const float4*>(pool.pmax + (size_t)(rr / pool.rows) * C + c));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!live[u]) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float v = gbias ? zv[u][i] + gb[u][i] : zv[u][i];
+          if (MODE == 0) {
+            const float d = v - pv[i];
+            a[i] += d;
+            q[i] = fmaf(d, d, q[i]);
+          } else {
+            float g = gp[u][i];
+            const float t = use_out ? ov[u][i] : fmaf(v - mu[i], rs[i], be[i]);   // the forward output before the ReLU clamp
+            // the pooled copy of this output: its gradient goes to the arg-max rows (ties share); a hit is rare, so the
+            // count and the pooled gradient are fetched only then
+            if (pool.pmax && fmaxf(t, 0.f) == pm[u][i]) {
+              const size_t po = (size_t)((rb + u * lanes) / pool.rows) * C + c + i;
+              g += __ldg(pool.pgrad + po) / __ldg(pool.pcnt + po);
+            }
+            if (relu && !(t > 0.f)) g = 0.f;
+            a[i] += g;
+            q[i] = fmaf(g, (v - mu[i]) * rs[i], q[i]);
+          }
+        }
       }
     }
-  };
-  if (ok) {
-    int64_t r = rbeg + rl;
-    for (; r + lanes < rend; r += 2 * lanes) {
-      step(r);
-      step(r + lanes);
-    }
-    if (r < rend) step(r);
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -197,12 +204,23 @@ static void launch_colsum(const float* z, const float* out, const float* gout, c
   // every block ends with 2*cb fp64 atomics onto the same 2*C addresses: with narrow tensors (C <= 128) that tail, not
   // the streaming, sets the time -- fewer, longer blocks there
   if (C <= 128 && nb > 2 * num_sms()) nb = 2 * num_sms();
-  if (vec) {
+  if (vec && rows < (1ll << 31)) {
     int cb = 256;
     while (cb > C) cb >>= 1;                        // 16 .. 256, a power of two <= C
-    dim3 grid(nb, cdiv(C, cb));
-    bn_colsum_vec_kernel<MODE><<<grid, BN_THREADS, 0, st>>>(z, out, gout, mean, rstd, relu, rows, C, cb, acc, gbias,
-                                                            grows, beta, pool, pivot);
+    const int slabs = cdiv(C, cb);
+    if (MODE == 1) {
+      // backward statistics (two streams in, z and g): ONE wave of 2 blocks per SM with four rows in flight per thread
+      // beats many short blocks with two (profiles/r02_bn_bwd_sweep.txt: -17 us at C = 1024 / 512, -9 us at 256, -5 us
+      // at 64 on P = 49152 rows): the per-block reduction + fp64 atomics tail is paid 296 times instead of 3072
+      const int one_wave = max(1, 2 * num_sms() / slabs);
+      dim3 grid(nb < one_wave ? nb : one_wave, slabs);
+      bn_colsum_vec_kernel<MODE, 4><<<grid, BN_THREADS, 0, st>>>(z, out, gout, mean, rstd, relu, (int)rows, C, cb, acc,
+                                                                 gbias, grows, beta, pool, pivot);
+    } else {
+      dim3 grid(nb, slabs);
+      bn_colsum_vec_kernel<MODE, 2><<<grid, BN_THREADS, 0, st>>>(z, out, gout, mean, rstd, relu, (int)rows, C, cb, acc,
+                                                                 gbias, grows, beta, pool, pivot);
+    }
   } else {
     dim3 grid(nb, cdiv(C, 64));
     bn_colsum_kernel<MODE><<<grid, BN_THREADS, 0, st>>>(z, out, gout, mean, rstd, relu, rows, C, acc, gbias, grows, beta,
@@ -361,80 +379,97 @@ __global__ void bn_pool_unpack_kernel(const unsigned long long* __restrict__ pac
   pcnt[i] = (float)(unsigned)(w & 0xffffffffull);
 }
 
+// UN elements (of VEC channels each) in flight per thread: every load of a batch is issued before the first is consumed.
 template <int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
     bn_act_bwd_kernel(const float* __restrict__ z, const float* __restrict__ out, const float* __restrict__ gout,
                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ s1,
                       const float* __restrict__ s2, int relu, uint32_t nvec, int C, float inv_rows,
                       float* __restrict__ gz, float* __restrict__ gpre, const float* __restrict__ gbias, int grows,
                       __nv_bfloat16* __restrict__ gz_planes, size_t plane_elems, const float* __restrict__ beta,
                       const BnPool pool) {
+  constexpr int UN = VEC == 4 ? 2 : 1;
   const uint32_t cv = (uint32_t)C / VEC;
-  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
-    const uint32_t r = v / cv;
-    const uint32_t c = (v - r * cv) * VEC;
-    const size_t e = (size_t)r * C + c;
-    float zz[VEC], oo[VEC], gg[VEC], gb[VEC], gzv[VEC], gpv[VEC];
-    if (VEC == 4) {
-      *reinterpret_cast<float4*>(zz) = *reinterpret_cast<const float4*>(z + e);
-      *reinterpret_cast<float4*>(gg) = *reinterpret_cast<const float4*>(gout + e);
-      if (relu && out) *reinterpret_cast<float4*>(oo) = *reinterpret_cast<const float4*>(out + e);
-      if (gbias) *reinterpret_cast<float4*>(gb) = *reinterpret_cast<const float4*>(gbias + (size_t)(r / grows) * C + c);
-    } else {
-      zz[0] = z[e];
-      gg[0] = gout[e];
-      if (relu && out) oo[0] = out[e];
-      if (gbias) gb[0] = gbias[(size_t)(r / grows) * C + c];
-    }
-    float mu[VEC], rsv[VEC], be[VEC], a1[VEC], a2[VEC];
-    if (VEC == 4) {   // per-channel constants as 16-byte loads too (they are L1-resident)
-      *reinterpret_cast<float4*>(mu) = __ldg(reinterpret_cast<const float4*>(mean + c));
-      *reinterpret_cast<float4*>(rsv) = __ldg(reinterpret_cast<const float4*>(rstd + c));
-      *reinterpret_cast<float4*>(a1) = __ldg(reinterpret_cast<const float4*>(s1 + c));
-      *reinterpret_cast<float4*>(a2) = __ldg(reinterpret_cast<const float4*>(s2 + c));
-      if (beta) *reinterpret_cast<float4*>(be) = __ldg(reinterpret_cast<const float4*>(beta + c));
-    } else {
-      mu[0] = mean[c];
-      rsv[0] = rstd[c];
-      a1[0] = s1[c];
-      a2[0] = s2[c];
-      if (beta) be[0] = beta[c];
-    }
-    float pm[VEC];
-    size_t po = 0;
-    if (VEC == 4 && pool.pmax) {
-      po = (size_t)(r / pool.rows) * C + c;
-      *reinterpret_cast<float4*>(pm) = __ldg(reinterpret_cast<const float4*>(pool.pmax + po));
-    }
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const bool use_out = relu && out;
+  for (uint32_t v0 = blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += UN * stride) {
+    float zz[UN][VEC], oo[UN][VEC], gg[UN][VEC], gb[UN][VEC], pm[UN][VEC];
+    uint32_t rr[UN], cc[UN];
+    bool live[UN];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      float gp = gg[i];
-      const float rs = rsv[i];
-      float zv = zz[i];
-      if (gbias) zv += gb[i];
-      const float t = (relu || pool.pmax) ? (out ? oo[i] : fmaf(zv - mu[i], rs, be[i])) : 1.f;
-      if (VEC == 4 && pool.pmax && fmaxf(t, 0.f) == pm[i]) gp += __ldg(pool.pgrad + po + i) / __ldg(pool.pcnt + po + i);
-      if (relu && !(t > 0.f)) gp = 0.f;
-      const float zh = (zv - mu[i]) * rs;
-      gzv[i] = rs * (gp - a1[i] * inv_rows - zh * (a2[i] * inv_rows));
-      gpv[i] = gp;
-    }
-    if (VEC == 4) {
-      if (gz) *reinterpret_cast<float4*>(gz + e) = *reinterpret_cast<float4*>(gzv);
-      if (gpre) *reinterpret_cast<float4*>(gpre + e) = *reinterpret_cast<float4*>(gpv);
-      if (gz_planes) {   // the gradient as a tcgen05 operand: bf16 hi / lo planes (tc_gemm.cu), no fp32 round trip
-        __nv_bfloat16 h[4], l[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          h[i] = __float2bfloat16_rn(gzv[i]);
-          l[i] = __float2bfloat16_rn(gzv[i] - __bfloat162float(h[i]));
-        }
-        *reinterpret_cast<uint2*>(gz_planes + e) = *reinterpret_cast<uint2*>(h);
-        if (plane_elems) *reinterpret_cast<uint2*>(gz_planes + plane_elems + e) = *reinterpret_cast<uint2*>(l);
+    for (int u = 0; u < UN; ++u) {
+      const uint32_t v = v0 + u * stride;
+      live[u] = v < nvec;
+      const uint32_t vv = live[u] ? v : v0;                 // clamped duplicate, skipped below
+      rr[u] = vv / cv;
+      cc[u] = (vv - rr[u] * cv) * VEC;
+      const size_t e = (size_t)rr[u] * C + cc[u];
+      if (VEC == 4) {
+        *reinterpret_cast<float4*>(zz[u]) = *reinterpret_cast<const float4*>(z + e);
+        *reinterpret_cast<float4*>(gg[u]) = *reinterpret_cast<const float4*>(gout + e);
+        if (use_out) *reinterpret_cast<float4*>(oo[u]) = *reinterpret_cast<const float4*>(out + e);
+        if (gbias) *reinterpret_cast<float4*>(gb[u]) = __ldg(reinterpret_cast<const float4*>(gbias + (size_t)(rr[u] / grows) * C + cc[u]));
+        if (pool.pmax)
+          *reinterpret_cast<float4*>(pm[u]) = __ldg(reinterpret_cast<const float4*>(pool.pmax + (size_t)(rr[u] / pool.rows) * C + cc[u]));
+      } else {
+        zz[u][0] = z[e];
+        gg[u][0] = gout[e];
+        if (use_out) oo[u][0] = out[e];
+        if (gbias) gb[u][0] = gbias[(size_t)(rr[u] / grows) * C + cc[u]];
       }
-    } else {
-      if (gz) gz[e] = gzv[0];
-      if (gpre) gpre[e] = gpv[0];
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (!live[u]) continue;
+      const uint32_t c = cc[u];
+      const size_t e = (size_t)rr[u] * C + c;
+      float mu[VEC], rsv[VEC], be[VEC], a1[VEC], a2[VEC], gzv[VEC], gpv[VEC];
+      if (VEC == 4) {   // per-channel constants as 16-byte loads too (they are L1-resident)
+        *reinterpret_cast<float4*>(mu) = __ldg(reinterpret_cast<const float4*>(mean + c));
+        *reinterpret_cast<float4*>(rsv) = __ldg(reinterpret_cast<const float4*>(rstd + c));
+        *reinterpret_cast<float4*>(a1) = __ldg(reinterpret_cast<const float4*>(s1 + c));
+        *reinterpret_cast<float4*>(a2) = __ldg(reinterpret_cast<const float4*>(s2 + c));
+        if (beta) *reinterpret_cast<float4*>(be) = __ldg(reinterpret_cast<const float4*>(beta + c));
+      } else {
+        mu[0] = mean[c];
+        rsv[0] = rstd[c];
+        a1[0] = s1[c];
+        a2[0] = s2[c];
+        if (beta) be[0] = beta[c];
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float gp = gg[u][i];
+        const float rs = rsv[i];
+        float zv = zz[u][i];
+        if (gbias) zv += gb[u][i];
+        const float t = (relu || pool.pmax) ? (out ? oo[u][i] : fmaf(zv - mu[i], rs, be[i])) : 1.f;
+        if (VEC == 4 && pool.pmax && fmaxf(t, 0.f) == pm[u][i]) {
+          const size_t po = (size_t)(rr[u] / pool.rows) * C + c + i;
+          gp += __ldg(pool.pgrad + po) / __ldg(pool.pcnt + po);
+        }
+        if (relu && !(t > 0.f)) gp = 0.f;
+        const float zh = (zv - mu[i]) * rs;
+        gzv[i] = rs * (gp - a1[i] * inv_rows - zh * (a2[i] * inv_rows));
+        gpv[i] = gp;
+      }
+      if (VEC == 4) {
+        if (gz) *reinterpret_cast<float4*>(gz + e) = *reinterpret_cast<float4*>(gzv);
+        if (gpre) *reinterpret_cast<float4*>(gpre + e) = *reinterpret_cast<float4*>(gpv);
+        if (gz_planes) {   // the gradient as a tcgen05 operand: bf16 hi / lo planes (tc_gemm.cu), no fp32 round trip
+          __nv_bfloat16 h[4], l[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            h[i] = __float2bfloat16_rn(gzv[i]);
+            l[i] = __float2bfloat16_rn(gzv[i] - __bfloat162float(h[i]));
+          }
+          *reinterpret_cast<uint2*>(gz_planes + e) = *reinterpret_cast<uint2*>(h);
+          if (plane_elems) *reinterpret_cast<uint2*>(gz_planes + plane_elems + e) = *reinterpret_cast<uint2*>(l);
+        }
+      } else {
+        if (gz) gz[e] = gzv[0];
+        if (gpre) gpre[e] = gpv[0];
+      }
     }
   }
 }

@@ -5,7 +5,10 @@ finalize() / num_entries() / num_channels() / batch_size().
 Out of scope for performance.  What exists here:
   io_array  : the dense fixed-N layout of io_h5 (data [n,N,C], label [n,N], optional weight [n,N], whole
               dataset in RAM, shuffle / sequential-wraparound batching: iotool.py:220-231,258-278) read from
-              .npz / .npy-dict files, or from .h5/.hdf5 when h5py happens to be importable.  -io h5
+              HDF5 files (.h5 / .hdf5: h5py when it is importable, else the built-in reader dgcnn.h5lite) or .npz
+              files with the same keys; the inference output goes to an HDF5 file with the reference's layout
+              (iotool.py:226-250: extendable zlib-5 EArrays DATA_KEY / softmax / LABEL_KEY, the label stored as
+              float32 like the reference's Float32Atom) when OUTPUT_FILE ends in .h5 / .hdf5, else to .npz.  -io h5
   io_synth  : seeded in-memory clouds of the benchmark shape (uniform [0,1)^C points, labels in {0..NUM_CLASS-1})
               -io synthetic
   io_larcv  : needs larcv2 + ROOT (external HEP stack, not in this image) -> NotImplementedError on use.
@@ -58,12 +61,14 @@ class io_array(io_base):
 
     def _read(self, path):
         f = self._flags
-        if path.endswith((".h5", ".hdf5")):
+        if path.endswith((".h5", ".hdf5", ".hdf")):
             try:
                 import h5py
+                opener = lambda: h5py.File(path, "r")  # noqa: E731
             except ImportError:
-                raise NotImplementedError("h5py is not installed; convert %s to .npz (same keys)" % path)
-            with h5py.File(path, "r") as h:
+                from . import h5lite
+                opener = lambda: h5lite.File(path)  # noqa: E731
+            with opener() as h:
                 get = lambda key: np.array(h[key])  # noqa: E731
                 return (get(f.DATA_KEY), get(f.LABEL_KEY) if f.LABEL_KEY else None,
                         get(f.WEIGHT_KEY) if f.WEIGHT_KEY else None)
@@ -110,7 +115,13 @@ class io_array(io_base):
             out = {self._flags.DATA_KEY: self._data[order], "softmax": np.stack(self._out["softmax"]), "index": order}
             if self._label is not None:
                 out[self._flags.LABEL_KEY] = self._label[order]
-            np.savez_compressed(self._flags.OUTPUT_FILE, **out)
+            if str(self._flags.OUTPUT_FILE).endswith((".h5", ".hdf5", ".hdf")):
+                from . import h5lite
+                if self._label is not None:                       # iotool.py:235: create_earray(..., Float32Atom())
+                    out[self._flags.LABEL_KEY] = out[self._flags.LABEL_KEY].astype(np.float32)
+                h5lite.write(self._flags.OUTPUT_FILE, out, compress=5)
+            else:
+                np.savez_compressed(self._flags.OUTPUT_FILE, **out)
 
 
 io_h5 = io_array  # the reference's name

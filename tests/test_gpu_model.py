@@ -205,3 +205,37 @@ def test_cli_inference_from_checkpoint(dg, cuda, tmp_path):
     assert np.allclose(z["softmax"].sum(-1), 1.0, atol=1e-5)
     csv = open(str(tmp_path / "ilog" / "inference_log-0000001.csv")).read().splitlines()
     assert csv[0] == "iter,epoch,titer,tinference,tio,tsumiter,tsuminference,tsumio,loss,accuracy" and len(csv) == 4
+
+
+def test_cli_config0_hdf5_in_hdf5_out(dg, cuda, tmp_path):
+    """BASELINE configs[0] through the reference's own file formats: bin/dgcnn.py train -io h5 on an HDF5 file (keys data /
+    label, iotool.py:213-224), then inference writing the PyTables-style output file (iotool.py:226-250); both files go
+    through dgcnn.h5lite (no h5py / PyTables in the image)."""
+    import subprocess
+    import sys
+    from dgcnn import h5lite
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = [sys.executable, os.path.join(root, "dynamic-gcnn_b200", "bin", "dgcnn.py")]
+    rng = np.random.RandomState(5)
+    src = str(tmp_path / "clouds.h5")
+    data = rng.rand(8, 512, 3).astype(np.float32)
+    label = (data[..., 0] > 0.5).astype(np.int32)
+    h5lite.write(src, {"data": data, "label": label}, compress=5)
+    common = ["-io", "h5", "-if", src, "-bs", "2", "-mbs", "2", "-ecl", "1", "-kv", "20", "-np", "512", "-db", "0",
+              "-sd", "3", "-rs", "1"]
+    tr = subprocess.run(exe + ["train"] + common + ["-it", "2", "-wp", str(tmp_path / "w" / "snap"), "-chks", "1",
+                                                    "-ld", str(tmp_path / "log")],
+                        capture_output=True, text=True, timeout=600)
+    assert tr.returncode == 0, tr.stderr[-2000:]
+    assert "Iteration 2" in tr.stdout
+    out = str(tmp_path / "pred.h5")
+    inf = subprocess.run(exe + ["inference"] + common + ["-it", "2", "-sh", "0", "-mp", str(tmp_path / "w" / "snap-1"),
+                                                         "-of", out, "-ld", str(tmp_path / "ilog")],
+                         capture_output=True, text=True, timeout=600)
+    assert inf.returncode == 0, inf.stderr[-2000:]
+    with h5lite.File(out) as f:
+        sm, idx = f["softmax"], f["index"]
+        assert sm.shape == (4, 512, 2) and idx.tolist() == [2, 3, 4, 5]      # entries 0, 1 go to prepare()'s throw-away next()
+        assert np.allclose(sm.sum(-1), 1.0, atol=1e-5)
+        assert np.array_equal(f["data"], data[idx]) and np.array_equal(f["label"], label[idx].astype(np.float32))
+        assert f.attrs("softmax")["CLASS"] == "EARRAY"

@@ -1,0 +1,162 @@
+"""dgcnn.h5lite: the built-in HDF5 reader / writer behind `-io h5` (/root/reference/dgcnn/iotool.py:199-280 uses h5py for the
+input and PyTables EArrays for the output; neither exists in this image).  Round trips, the on-disk structures the
+specification fixes (so that other HDF5 libraries read the files), and the io_h5 handler on .h5 files."""
+import struct
+import zlib
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture()
+def h5(dg):
+    from dgcnn import h5lite
+    return h5lite
+
+
+def _arrays():
+    rng = np.random.RandomState(0)
+    return {"data": rng.rand(5, 16, 4).astype(np.float32), "label": rng.randint(0, 3, (5, 16)).astype(np.int32),
+            "weight": rng.rand(5, 16), "u8": np.arange(7, dtype=np.uint8), "i64": np.arange(-3, 3, dtype=np.int64),
+            "f16": rng.rand(3, 2).astype(np.float16)}
+
+
+@pytest.mark.parametrize("compress", [0, 5])
+def test_round_trip_all_dtypes(h5, tmp_path, compress):
+    d = _arrays()
+    path = str(tmp_path / "t.h5")
+    h5.write(path, d, compress=compress)
+    with h5.File(path) as f:
+        assert f.keys() == sorted(d) and "data" in f and "nope" not in f
+        for k, v in d.items():
+            a = f[k]
+            assert a.dtype == v.dtype and a.shape == v.shape and np.array_equal(a, v), k
+            assert f.shape(k) == v.shape
+        with pytest.raises(KeyError):
+            f["nope"]
+        if compress:      # what PyTables puts on an EArray / the root group (iotool.py:226-236 writes through PyTables)
+            assert f.attrs("data") == {"CLASS": "EARRAY", "EXTDIM": 0, "TITLE": "", "VERSION": "1.1"}
+            assert f.attrs("/")["PYTABLES_FORMAT_VERSION"] == "2.1"
+    assert h5.read(path, ["label"])["label"].tolist() == d["label"].tolist()
+
+
+def test_on_disk_structures_follow_the_specification(h5, tmp_path):
+    """Byte-level known answers for the fixed parts of the format (HDF5 File Format Specification, II.A superblock v0,
+    III.A v1 B-trees, III.C symbol table nodes, III.D local heaps, IV.A v1 object headers)."""
+    path = str(tmp_path / "s.h5")
+    x = np.arange(12, dtype=np.float32).reshape(3, 4)
+    h5.write(path, {"x": x})
+    b = open(path, "rb").read()
+    assert b[:8] == b"\x89HDF\r\n\x1a\n"
+    assert b[8:16] == bytes([0, 0, 0, 0, 0, 8, 8, 0])                       # versions 0, 8-byte offsets and lengths
+    leaf_k, int_k, flags = struct.unpack_from("<HHI", b, 16)
+    assert (leaf_k, int_k, flags) == (4, 16, 0)
+    base, free, eof, drv = struct.unpack_from("<QQQQ", b, 24)
+    assert base == 0 and free == drv == 0xFFFFFFFFFFFFFFFF and eof == len(b)
+    name_off, root_hdr, cache, _, btree, heap = struct.unpack_from("<QQIIQQ", b, 56)
+    assert name_off == 0 and cache == 1
+    assert b[btree:btree + 4] == b"TREE" and b[btree + 4] == 0 and b[btree + 5] == 0      # group node, leaf level
+    assert b[heap:heap + 4] == b"HEAP"
+    seg_size, free_head, seg = struct.unpack_from("<QQQ", b, heap + 8)
+    assert b[seg:seg + 8] == b"\0" * 8 and b[seg + 8:seg + 10] == b"x\0"                  # offset 0: the empty name
+    assert struct.unpack_from("<QQ", b, seg + free_head) == (1, seg_size - free_head)      # one free block closes it
+    n_sym, = struct.unpack_from("<H", b, btree + 6)
+    snod, = struct.unpack_from("<Q", b, btree + 24 + 8)
+    assert n_sym == 1 and b[snod:snod + 4] == b"SNOD" and b[snod + 4] == 1
+    ent_name, ent_hdr = struct.unpack_from("<QQ", b, snod + 8)
+    assert ent_name == 8
+    # the dataset's object header: version 1, 4 messages: dataspace, datatype, fill value, layout
+    ver, _, nmsg, refs, hsize = struct.unpack_from("<BBHII", b, ent_hdr)
+    assert (ver, nmsg, refs) == (1, 4, 1) and hsize % 8 == 0
+    p, seen = ent_hdr + 16, {}
+    for _ in range(nmsg):
+        t, sz = struct.unpack_from("<HH", b, p)
+        seen[t] = b[p + 8:p + 8 + sz]
+        p += 8 + sz
+    assert p == ent_hdr + 16 + hsize
+    assert seen[1][:8] == bytes([1, 2, 0, 0, 0, 0, 0, 0]) and struct.unpack_from("<QQ", seen[1], 8) == (3, 4)
+    assert seen[3][:8] == bytes([0x11, 0x20, 31, 0, 4, 0, 0, 0])                           # IEEE float, LE, sign bit 31
+    assert struct.unpack_from("<HHBBBBI", seen[3], 8) == (0, 32, 23, 8, 0, 23, 127)
+    lay_ver, lay_cls, addr, size = struct.unpack_from("<BBQQ", seen[8], 0)
+    assert (lay_ver, lay_cls, size) == (3, 1, 48)
+    assert np.array_equal(np.frombuffer(b, np.float32, 12, addr).reshape(3, 4), x)
+
+
+def test_chunked_deflate_layout_and_multi_level_btree(h5, tmp_path):
+    rng = np.random.RandomState(1)
+    big = rng.rand(5000, 3).astype(np.float32)            # 5000 chunks: 79 leaf nodes of <= 64 entries, 2 levels above
+    path = str(tmp_path / "c.h5")
+    h5.write(path, {"x": big}, compress=1)
+    with h5.File(path) as f:
+        assert np.array_equal(f["x"], big)
+        obj = f._resolve("x")
+        lay = obj.first(8)
+        assert lay[0] == 3 and lay[1] == 2 and lay[2] == 3            # v3, chunked, rank + 1
+        root, = struct.unpack_from("<Q", lay, 3)
+        assert struct.unpack_from("<III", lay, 11) == (1, 3, 4)       # one entry per chunk, 3 columns, 4-byte elements
+        b = f._b
+        assert b[root:root + 4] == b"TREE" and b[root + 4] == 1 and b[root + 5] == 2      # chunk tree, two levels up
+        filt = obj.first(0xB)
+        assert filt[:2] == bytes([1, 1]) and struct.unpack_from("<HHHHI", filt, 8) == (1, 0, 1, 1, 1)
+        sp = obj.first(1)
+        assert sp[2] == 1 and struct.unpack_from("<QQ", sp, 8 + 16) == (0xFFFFFFFFFFFFFFFF, 3)   # unlimited along axis 0
+        # first leaf: key 0 = (size of the deflated chunk, mask 0, offsets 0,0,0), child = the chunk itself
+        node = root
+        while b[node + 5] > 0:
+            node, = struct.unpack_from("<Q", b, node + 24 + 32)
+        nbytes, mask, o0, o1, o2, child = struct.unpack_from("<IIQQQQ", b, node + 24)
+        assert (mask, o0, o1, o2) == (0, 0, 0, 0)
+        assert np.array_equal(np.frombuffer(zlib.decompress(b[child:child + nbytes]), np.float32), big[0])
+
+
+def test_reader_handles_shuffle_and_big_endian(h5, tmp_path):
+    """Filters and byte orders this writer never produces but h5py users do (compression='gzip', shuffle=True; '>f4')."""
+    from dgcnn.h5lite import File
+    f = File.__new__(File)
+    raw = np.arange(6, dtype=np.float32)
+    shuffled = raw.view(np.uint8).reshape(6, 4).T.tobytes()
+    assert np.array_equal(np.frombuffer(f._unfilter(zlib.compress(shuffled) + b"abcd", [(2, [4]), (1, [4]), (3, [])], 0,
+                                                    raw.dtype), np.float32), raw)
+    assert np.array_equal(np.frombuffer(f._unfilter(shuffled, [(2, [4]), (1, [4])], 0b10, raw.dtype), np.float32), raw)
+    be = {"x": np.arange(5, dtype=">f4"), "y": np.arange(4, dtype=">i2")}
+    from dgcnn.h5lite import _decode_datatype, _encode_datatype
+    for v in be.values():
+        assert _decode_datatype(_encode_datatype(v.dtype)) == v.dtype
+    with pytest.raises(NotImplementedError):
+        _encode_datatype(np.dtype([("a", "f4")]))
+    with pytest.raises(ValueError):
+        bad = tmp_path / "bad.h5"
+        bad.write_bytes(b"not hdf5" * 100)
+        File(str(bad))
+
+
+def test_io_h5_reads_and_writes_hdf5_files(dg, tmp_path):
+    """-io h5 on real .h5 files: input keys data / label / weight (iotool.py:213-224), output EArrays DATA_KEY / softmax /
+    LABEL_KEY with the label as float32 (iotool.py:226-250)."""
+    from dgcnn import h5lite
+    rng = np.random.RandomState(3)
+    src = {"data": rng.rand(5, 16, 4).astype(np.float32), "label": rng.randint(0, 2, (5, 16)).astype(np.int32),
+           "weight": rng.rand(5, 16).astype(np.float32)}
+    a, b = str(tmp_path / "a.h5"), str(tmp_path / "b.hdf5")
+    h5lite.write(a, {k: v[:3] for k, v in src.items()})
+    h5lite.write(b, {k: v[3:] for k, v in src.items()}, compress=5)
+    out = str(tmp_path / "out.h5")
+    fl = SimpleNamespace(BATCH_SIZE=2, NUM_POINT=16, NUM_CHANNEL=-1, NUM_CLASS=2, LABEL_KEY="label", WEIGHT_KEY="weight",
+                         OUTPUT_FILE=out, SHUFFLE=0, IO_TYPE="h5", INPUT_FILE=[a, b], DATA_KEY="data")
+    io = dg.io_factory(fl)
+    io.initialize()
+    assert io.num_entries() == 5 and io.num_channels() == 4
+    idx, data, label, weight = io.next()
+    assert idx.tolist() == [0, 1] and np.array_equal(data, src["data"][:2]) and np.array_equal(weight, src["weight"][:2])
+    sm = rng.rand(5, 16, 2).astype(np.float32)
+    for i in (3, 0, 4):
+        io.store(i, sm[i])
+    with pytest.raises(ValueError):
+        io.store(5, sm[0])
+    io.finalize()
+    with h5lite.File(out) as f:
+        assert set(f.keys()) == {"data", "softmax", "label", "index"}
+        assert np.array_equal(f["softmax"], sm[[3, 0, 4]]) and np.array_equal(f["data"], src["data"][[3, 0, 4]])
+        assert f["label"].dtype == np.float32 and np.array_equal(f["label"], src["label"][[3, 0, 4]].astype(np.float32))
+        assert f.attrs("softmax")["CLASS"] == "EARRAY" and f["index"].tolist() == [3, 0, 4]
