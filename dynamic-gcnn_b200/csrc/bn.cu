@@ -379,97 +379,80 @@ __global__ void bn_pool_unpack_kernel(const unsigned long long* __restrict__ pac
   pcnt[i] = (float)(unsigned)(w & 0xffffffffull);
 }
 
-// UN elements (of VEC channels each) in flight per thread: every load of a batch is issued before the first is consumed.
 template <int VEC>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256)
     bn_act_bwd_kernel(const float* __restrict__ z, const float* __restrict__ out, const float* __restrict__ gout,
                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ s1,
                       const float* __restrict__ s2, int relu, uint32_t nvec, int C, float inv_rows,
                       float* __restrict__ gz, float* __restrict__ gpre, const float* __restrict__ gbias, int grows,
                       __nv_bfloat16* __restrict__ gz_planes, size_t plane_elems, const float* __restrict__ beta,
                       const BnPool pool) {
-  constexpr int UN = VEC == 4 ? 2 : 1;
   const uint32_t cv = (uint32_t)C / VEC;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const bool use_out = relu && out;
-  for (uint32_t v0 = blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += UN * stride) {
-    float zz[UN][VEC], oo[UN][VEC], gg[UN][VEC], gb[UN][VEC], pm[UN][VEC];
-    uint32_t rr[UN], cc[UN];
-    bool live[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const uint32_t v = v0 + u * stride;
-      live[u] = v < nvec;
-      const uint32_t vv = live[u] ? v : v0;                 // clamped duplicate, skipped below
-      rr[u] = vv / cv;
-      cc[u] = (vv - rr[u] * cv) * VEC;
-      const size_t e = (size_t)rr[u] * C + cc[u];
-      if (VEC == 4) {
-        *reinterpret_cast<float4*>(zz[u]) = *reinterpret_cast<const float4*>(z + e);
-        *reinterpret_cast<float4*>(gg[u]) = *reinterpret_cast<const float4*>(gout + e);
-        if (use_out) *reinterpret_cast<float4*>(oo[u]) = *reinterpret_cast<const float4*>(out + e);
-        if (gbias) *reinterpret_cast<float4*>(gb[u]) = __ldg(reinterpret_cast<const float4*>(gbias + (size_t)(rr[u] / grows) * C + cc[u]));
-        if (pool.pmax)
-          *reinterpret_cast<float4*>(pm[u]) = __ldg(reinterpret_cast<const float4*>(pool.pmax + (size_t)(rr[u] / pool.rows) * C + cc[u]));
-      } else {
-        zz[u][0] = z[e];
-        gg[u][0] = gout[e];
-        if (use_out) oo[u][0] = out[e];
-        if (gbias) gb[u][0] = gbias[(size_t)(rr[u] / grows) * C + cc[u]];
-      }
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
+    const uint32_t r = v / cv;
+    const uint32_t c = (v - r * cv) * VEC;
+    const size_t e = (size_t)r * C + c;
+    float zz[VEC], oo[VEC], gg[VEC], gb[VEC], gzv[VEC], gpv[VEC];
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(zz) = *reinterpret_cast<const float4*>(z + e);
+      *reinterpret_cast<float4*>(gg) = *reinterpret_cast<const float4*>(gout + e);
+      if (relu && out) *reinterpret_cast<float4*>(oo) = *reinterpret_cast<const float4*>(out + e);
+      if (gbias) *reinterpret_cast<float4*>(gb) = *reinterpret_cast<const float4*>(gbias + (size_t)(r / grows) * C + c);
+    } else {
+      zz[0] = z[e];
+      gg[0] = gout[e];
+      if (relu && out) oo[0] = out[e];
+      if (gbias) gb[0] = gbias[(size_t)(r / grows) * C + c];
+    }
+    float mu[VEC], rsv[VEC], be[VEC], a1[VEC], a2[VEC];
+    if (VEC == 4) {   // per-channel constants as 16-byte loads too (they are L1-resident)
+      *reinterpret_cast<float4*>(mu) = __ldg(reinterpret_cast<const float4*>(mean + c));
+      *reinterpret_cast<float4*>(rsv) = __ldg(reinterpret_cast<const float4*>(rstd + c));
+      *reinterpret_cast<float4*>(a1) = __ldg(reinterpret_cast<const float4*>(s1 + c));
+      *reinterpret_cast<float4*>(a2) = __ldg(reinterpret_cast<const float4*>(s2 + c));
+      if (beta) *reinterpret_cast<float4*>(be) = __ldg(reinterpret_cast<const float4*>(beta + c));
+    } else {
+      mu[0] = mean[c];
+      rsv[0] = rstd[c];
+      a1[0] = s1[c];
+      a2[0] = s2[c];
+      if (beta) be[0] = beta[c];
+    }
+    float pm[VEC];
+    size_t po = 0;
+    if (VEC == 4 && pool.pmax) {
+      po = (size_t)(r / pool.rows) * C + c;
+      *reinterpret_cast<float4*>(pm) = __ldg(reinterpret_cast<const float4*>(pool.pmax + po));
     }
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      if (!live[u]) continue;
-      const uint32_t c = cc[u];
-      const size_t e = (size_t)rr[u] * C + c;
-      float mu[VEC], rsv[VEC], be[VEC], a1[VEC], a2[VEC], gzv[VEC], gpv[VEC];
-      if (VEC == 4) {   // per-channel constants as 16-byte loads too (they are L1-resident)
-        *reinterpret_cast<float4*>(mu) = __ldg(reinterpret_cast<const float4*>(mean + c));
-        *reinterpret_cast<float4*>(rsv) = __ldg(reinterpret_cast<const float4*>(rstd + c));
-        *reinterpret_cast<float4*>(a1) = __ldg(reinterpret_cast<const float4*>(s1 + c));
-        *reinterpret_cast<float4*>(a2) = __ldg(reinterpret_cast<const float4*>(s2 + c));
-        if (beta) *reinterpret_cast<float4*>(be) = __ldg(reinterpret_cast<const float4*>(beta + c));
-      } else {
-        mu[0] = mean[c];
-        rsv[0] = rstd[c];
-        a1[0] = s1[c];
-        a2[0] = s2[c];
-        if (beta) be[0] = beta[c];
-      }
+    for (int i = 0; i < VEC; ++i) {
+      float gp = gg[i];
+      const float rs = rsv[i];
+      float zv = zz[i];
+      if (gbias) zv += gb[i];
+      const float t = (relu || pool.pmax) ? (out ? oo[i] : fmaf(zv - mu[i], rs, be[i])) : 1.f;
+      if (VEC == 4 && pool.pmax && fmaxf(t, 0.f) == pm[i]) gp += __ldg(pool.pgrad + po + i) / __ldg(pool.pcnt + po + i);
+      if (relu && !(t > 0.f)) gp = 0.f;
+      const float zh = (zv - mu[i]) * rs;
+      gzv[i] = rs * (gp - a1[i] * inv_rows - zh * (a2[i] * inv_rows));
+      gpv[i] = gp;
+    }
+    if (VEC == 4) {
+      if (gz) *reinterpret_cast<float4*>(gz + e) = *reinterpret_cast<float4*>(gzv);
+      if (gpre) *reinterpret_cast<float4*>(gpre + e) = *reinterpret_cast<float4*>(gpv);
+      if (gz_planes) {   // the gradient as a tcgen05 operand: bf16 hi / lo planes (tc_gemm.cu), no fp32 round trip
+        __nv_bfloat16 h[4], l[4];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        float gp = gg[u][i];
-        const float rs = rsv[i];
-        float zv = zz[u][i];
-        if (gbias) zv += gb[u][i];
-        const float t = (relu || pool.pmax) ? (out ? oo[u][i] : fmaf(zv - mu[i], rs, be[i])) : 1.f;
-        if (VEC == 4 && pool.pmax && fmaxf(t, 0.f) == pm[u][i]) {
-          const size_t po = (size_t)(rr[u] / pool.rows) * C + c + i;
-          gp += __ldg(pool.pgrad + po) / __ldg(pool.pcnt + po);
+        for (int i = 0; i < 4; ++i) {
+          h[i] = __float2bfloat16_rn(gzv[i]);
+          l[i] = __float2bfloat16_rn(gzv[i] - __bfloat162float(h[i]));
         }
-        if (relu && !(t > 0.f)) gp = 0.f;
-        const float zh = (zv - mu[i]) * rs;
-        gzv[i] = rs * (gp - a1[i] * inv_rows - zh * (a2[i] * inv_rows));
-        gpv[i] = gp;
+        *reinterpret_cast<uint2*>(gz_planes + e) = *reinterpret_cast<uint2*>(h);
+        if (plane_elems) *reinterpret_cast<uint2*>(gz_planes + plane_elems + e) = *reinterpret_cast<uint2*>(l);
       }
-      if (VEC == 4) {
-        if (gz) *reinterpret_cast<float4*>(gz + e) = *reinterpret_cast<float4*>(gzv);
-        if (gpre) *reinterpret_cast<float4*>(gpre + e) = *reinterpret_cast<float4*>(gpv);
-        if (gz_planes) {   // the gradient as a tcgen05 operand: bf16 hi / lo planes (tc_gemm.cu), no fp32 round trip
-          __nv_bfloat16 h[4], l[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            h[i] = __float2bfloat16_rn(gzv[i]);
-            l[i] = __float2bfloat16_rn(gzv[i] - __bfloat162float(h[i]));
-          }
-          *reinterpret_cast<uint2*>(gz_planes + e) = *reinterpret_cast<uint2*>(h);
-          if (plane_elems) *reinterpret_cast<uint2*>(gz_planes + plane_elems + e) = *reinterpret_cast<uint2*>(l);
-        }
-      } else {
-        if (gz) gz[e] = gzv[0];
-        if (gpre) gpre[e] = gpv[0];
-      }
+    } else {
+      if (gz) gz[e] = gzv[0];
+      if (gpre) gpre[e] = gpv[0];
     }
   }
 }

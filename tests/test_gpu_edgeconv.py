@@ -98,7 +98,7 @@ def test_edge_conv_duplicate_points_share_max_gradient(dg, oracle, cuda):
     assert torch.allclose(xc.grad.cpu(), xr.grad, atol=1e-3, rtol=1e-3)
 
 
-@pytest.mark.parametrize("name", ["cfg1_dgcnn", "residual", "lattice"])
+@pytest.mark.parametrize("name", ["cfg1_dgcnn", "residual", "lattice", "ref_dgcnn", "ref_residual"])
 def test_edgeconv_stack_against_golden(dg, cuda, name):
     """Committed oracle vectors (tests/golden): per-layer [max, mean, net] with the golden indices teacher-forced,
     and bit-exact free-running indices for layer 0 (its input is the raw cloud)."""
@@ -113,7 +113,7 @@ def test_edgeconv_stack_against_golden(dg, cuda, name):
     filt = [P["EdgeConv%d/conv0/weights" % i].shape[1] for i in range(L)]
     dg.ops._knn_forced = iter([torch.from_numpy(z["idx%d" % i]) for i in range(L)])
     try:
-        fn = dg.ops.repeat_residual_edge_conv if name == "residual" else dg.ops.repeat_edge_conv
+        fn = dg.ops.repeat_residual_edge_conv if "residual" in name else dg.ops.repeat_edge_conv
         tensors = fn(x, L, kval, filt, True)
     finally:
         dg.ops._knn_forced = None

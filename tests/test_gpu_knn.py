@@ -176,3 +176,18 @@ def test_knn_filter_modes_agree(dg, oracle, cuda):
         assert torch.equal(idx.cpu(), ref), mode
     assert L.dgcnn_knn_mode(xc.data_ptr(), 0, idx.data_ptr(), 2, 640, 64, 20, 5, ws.data_ptr(), ws.numel(),
                             nv.stream_ptr(cuda)) == nv.ERR_INVALID
+
+
+def test_knn_and_edges_equal_the_reference_code_bit_for_bit(dg, cuda):
+    """tests/golden/ref_knn_edges.npz: produced by the REFERENCE'S OWN k_nn / edges (ops.py:8-40, executed unmodified through
+    oracle/tf1_shim by tests/golden/make_reference_golden.py) on clouds whose distances are exact in fp32 -- duplicates and
+    lattice ties included; tf.nn.top_k's rule (lower index first) is the only freedom.  The CUDA path must equal them."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_knn_edges.npz"))
+    for name in ("dyadic3", "lattice3", "feat8"):
+        x = torch.from_numpy(z[name + ":x"]).cuda()
+        for k in (1, 7, 20):
+            got = dg.ops.k_nn(x, k).cpu().numpy()
+            assert np.array_equal(got, z["%s:k%d:idx" % (name, k)]), (name, k)
+        e = dg.ops.edges(x, k=5).cpu().numpy()
+        assert np.array_equal(e, z[name + ":edges"]), name

@@ -23,7 +23,7 @@ def _flags_for(oracle, name, z):
     fcf = [P["FC%d/weights" % j].shape[1] for j in range(nfc)]
     fl = oracle.make_flags(EDGE_CONV_LAYERS=L, EDGE_CONV_FILTERS=filt, KVALUE=z["idx0"].shape[-1], FC_LAYERS=nfc,
                            FC_FILTERS=fcf, NUM_CLASS=P["Final/weights"].shape[1],
-                           MODEL_NAME="residual-dgcnn" if name == "residual" else "dgcnn",
+                           MODEL_NAME="residual-dgcnn" if "residual" in name else "dgcnn",
                            TRAIN="dropout_mask" in z.files, NUM_CHANNEL=z["x"].shape[-1])
     return fl, P, L
 
@@ -35,7 +35,8 @@ def _trainer(dg, fl, P):
     return tr
 
 
-@pytest.mark.parametrize("name", ["cfg1_dgcnn", "residual", "lattice"])
+# ref_*: vectors produced by the reference's own ops.py / model.py (tests/golden/make_reference_golden.py)
+@pytest.mark.parametrize("name", ["cfg1_dgcnn", "residual", "lattice", "ref_dgcnn", "ref_residual"])
 def test_model_forward_backward_vs_golden(dg, oracle, cuda, name):
     z = np.load(os.path.join(GOLD, name + ".npz"))
     fl, P, L = _flags_for(oracle, name, z)
@@ -227,7 +228,7 @@ def test_cli_config0_hdf5_in_hdf5_out(dg, cuda, tmp_path):
                                                     "-ld", str(tmp_path / "log")],
                         capture_output=True, text=True, timeout=600)
     assert tr.returncode == 0, tr.stderr[-2000:]
-    assert "Iteration 2" in tr.stdout
+    assert "Iteration 1" in tr.stdout                                  # iterations are reported 0-based
     out = str(tmp_path / "pred.h5")
     inf = subprocess.run(exe + ["inference"] + common + ["-it", "2", "-sh", "0", "-mp", str(tmp_path / "w" / "snap-1"),
                                                          "-of", out, "-ld", str(tmp_path / "ilog")],

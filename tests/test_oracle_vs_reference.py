@@ -1,0 +1,136 @@
+"""The oracle against the REFERENCE'S OWN CODE.  tests/golden/ref_*.npz were produced by executing the unmodified
+/root/reference/dgcnn/ops.py and model.py on top of oracle/tf1_shim (tests/golden/make_reference_golden.py): the index
+arithmetic, concat orders, residual wiring and head are the reference's, only the TF primitives are restated.  This is the
+pin SURVEY.md section 8c asks for: oracle/knn_oracle.c and oracle/dgcnn_oracle.py must reproduce those vectors.
+Where /root/reference exists (this container, not the GPU box) the vectors are also regenerated live from the sources."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MODELS = {"ref_dgcnn": "dgcnn", "ref_residual": "residual-dgcnn", "ref_residual_nofc": "residual-dgcnn-nofc"}
+
+
+def test_knn_and_edges_equal_the_reference_bit_for_bit(oracle):
+    """ops.py:8-19 and :21-40 on clouds whose distances are exact in fp32 (so only the tie rule is left: tf.nn.top_k puts
+    the lower index first): the C oracle, the pure-Python restatement and `edges` equal the reference's output exactly --
+    duplicates and lattice ties included."""
+    z = np.load(os.path.join(GOLD, "ref_knn_edges.npz"))
+    for name in ("dyadic3", "lattice3", "feat8"):
+        x = z[name + ":x"]
+        for k in (1, 7, 20):
+            ref = z["%s:k%d:idx" % (name, k)]
+            assert np.array_equal(oracle.k_nn(x, k).numpy(), ref), (name, k)
+        assert np.array_equal(oracle.knn_pure_python(x[:1, :40], 7),
+                              np.argsort(oracle.pairwise_distance(x[:1, :40]).numpy(), axis=-1, kind="stable")[..., :7])
+        e = oracle.edges(torch.from_numpy(x), k=5, idx=torch.from_numpy(z["%s:k7:idx" % name][..., :5].copy()))
+        assert np.array_equal(e.numpy(), z[name + ":edges"]), name
+        # the distance matrix itself (materialised API, ops.py:11-16) reproduces the reference's ordering
+        D = oracle.pairwise_distance(x).numpy()
+        assert np.array_equal(np.argsort(D, axis=-1, kind="stable")[..., :20], z["%s:k20:idx" % name]), name
+
+
+def _flags_and_params(oracle, name, z):
+    P = {k[len("param:"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param:")}
+    L = len([k for k in z.files if k.startswith("idx")])
+    filt = [P["EdgeConv%d/conv0/weights" % i].shape[1] for i in range(L)]
+    fcn = sorted(k for k in P if k.startswith("FC") and k.endswith("weights"))
+    fl = oracle.make_flags(EDGE_CONV_LAYERS=L, EDGE_CONV_FILTERS=filt, KVALUE=z["idx0"].shape[-1], FC_LAYERS=len(fcn),
+                           FC_FILTERS=[P[k].shape[1] for k in fcn], NUM_CLASS=P["Final/weights"].shape[1],
+                           MODEL_NAME=MODELS[name], TRAIN=True, NUM_CHANNEL=z["x"].shape[-1])
+    return fl, P, L
+
+
+@pytest.mark.parametrize("name", sorted(MODELS))
+def test_oracle_reproduces_the_reference_model(oracle, name):
+    """model.py:9-106 / ops.py:42-163 end to end: every EdgeConv tensor, logits, loss, accuracy and every parameter gradient
+    of the reference's graph (torch autograd through the reference's own composition) against the oracle."""
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    fl, P, L = _flags_and_params(oracle, name, z)
+    assert set(P) == set(oracle.param_shapes(fl, z["x"].shape[-1]))                  # same variable inventory, same names
+    for n, shp in oracle.param_shapes(fl, z["x"].shape[-1]).items():
+        assert tuple(P[n].shape) == tuple(shp), n
+    for t in P.values():
+        t.requires_grad_(True)
+    x = torch.from_numpy(z["x"])
+    # 1. the neighbour graphs: the oracle's exact k_nn on the reference's own layer inputs.  Layer 0 sees the raw cloud;
+    #    layer i > 0 sees the reference's `net` of layer i-1.  The reference's distances come from a matmul (MKL order), the
+    #    oracle's from a fixed fmaf chain: indices may differ only where two distances tie to rounding.
+    inputs = [x] + [torch.from_numpy(z["tensor%d" % (3 * i + 2)]).squeeze(-2) for i in range(L - 1)]
+    for i in range(L):
+        ref_idx = z["idx%d" % i]
+        mine = oracle.k_nn(inputs[i], fl.KVALUE).numpy()
+        diff = mine != ref_idx
+        assert diff.mean() <= 2e-3, (i, diff.mean())
+        if diff.any():
+            D = oracle.pairwise_distance(inputs[i]).numpy()
+            b, r, s = np.nonzero(diff)
+            gap = np.abs(D[b, r, mine[b, r, s]] - D[b, r, ref_idx[b, r, s]])
+            assert np.all(gap <= 4e-6 * np.maximum(1.0, np.abs(D[b, r, mine[b, r, s]]))), (i, gap.max())
+    assert np.array_equal(oracle.k_nn(x, fl.KVALUE).numpy(), z["idx0"])                 # raw cloud: no near-ties here
+    # 2. same graph on both sides: everything downstream
+    tensors = []
+    mask = torch.from_numpy(z["dropout_mask"]) if "dropout_mask" in z.files else None
+    logits = oracle.build(x, fl, P, idx_list=[torch.from_numpy(z["idx%d" % i]) for i in range(L)], dropout_mask=mask,
+                          tensors_out=tensors)
+    assert len(tensors) == 3 * L
+    for i, t in enumerate(tensors):
+        assert torch.allclose(t.detach(), torch.from_numpy(z["tensor%d" % i]), atol=2e-5, rtol=1e-5), i
+    assert torch.allclose(logits.detach(), torch.from_numpy(z["logits"]), atol=5e-5, rtol=1e-5)
+    _, acc, loss = oracle.softmax_loss_accuracy(logits, torch.from_numpy(z["labels"]))
+    assert abs(float(loss.detach()) - float(z["loss"])) <= 1e-6 and abs(float(acc) - float(z["acc"])) <= 1e-7
+    loss.backward()
+    # fp32 gradients of this graph carry percent-level rounding noise on single elements (train-mode BN on random labels,
+    # DESIGN.md section 9), so the fp32 comparison is an L2 one; the formulae are pinned by the fp64 comparison below
+    for n, t in P.items():
+        ref = torch.from_numpy(z["grad:" + n])
+        den = max(float(ref.norm()), 1e-12)
+        assert float((t.grad - ref).norm()) <= 2e-2 * den, (n, float((t.grad - ref).norm()) / den)
+    # 3. the same comparison in fp64 (the reference's graph run in fp64 by the generator): identical formulae agree to
+    #    rounding of the stored fp32 copies
+    P64 = {n: t.detach().double().requires_grad_(True) for n, t in P.items()}
+    idx64 = [torch.from_numpy(z["knn64_%d" % i]) for i in range(L)]
+    logits64 = oracle.build(x.double(), fl, P64, idx_list=idx64, dropout_mask=mask.double() if mask is not None else None)
+    assert torch.allclose(logits64.detach().float(), torch.from_numpy(z["logits64"]), atol=2e-6, rtol=2e-6)
+    _, _, loss64 = oracle.softmax_loss_accuracy(logits64, torch.from_numpy(z["labels"]))
+    assert abs(float(loss64.detach()) - float(z["loss64"])) <= 1e-6
+    loss64.backward()
+    for n, t in P64.items():
+        ref = torch.from_numpy(z["grad64:" + n]).double()
+        den = max(float(ref.norm()), 1e-12)
+        assert float((t.grad - ref).norm()) <= 1e-6 * den, (n, float((t.grad - ref).norm()) / den)
+        assert float((t.grad - ref).abs().max()) <= 1e-6 * max(float(ref.abs().max()), 1e-12), n
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/dgcnn"), reason="the reference sources exist only in the build container")
+def test_committed_reference_vectors_regenerate_from_the_reference_sources():
+    """The fixtures are what the reference's code produces TODAY: re-run it (own process: the synthetic `dgcnn` package of
+    the generator must not meet the product package) and compare."""
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from tests.golden import make_reference_golden as g\n"
+            "import os\n"
+            "for name, fn in g.CASES.items():\n"
+            "    got = fn(); z = np.load(os.path.join(g.HERE, name + '.npz'))\n"
+            "    assert set(got) == set(z.files), name\n"
+            "    for k in z.files:\n"
+            "        a, b = z[k], np.asarray(got[k])\n"
+            "        ok = np.array_equal(a, b) if a.dtype.kind in 'iu' else np.allclose(a, b, rtol=1e-5, atol=1e-6)\n"
+            "        assert ok, (name, k)\n"
+            "print('REGENERATED_OK')\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0 and "REGENERATED_OK" in out.stdout, out.stderr[-3000:]
+
+
+def test_shim_is_test_infrastructure_only():
+    """Neither the product nor bench.py's timed arms may touch the TF1 shim or the reference-run fixtures' generator."""
+    pkg = os.path.join(ROOT, "dynamic-gcnn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "tf1_shim" not in src and "import tensorflow" not in src, os.path.join(dirpath, f)
+    assert "tf1_shim" not in open(os.path.join(ROOT, "bench.py")).read()
