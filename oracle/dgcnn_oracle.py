@@ -8,12 +8,19 @@ reference's hot path and of the model around it, op for op:
     /root/reference/dgcnn/model.py:9-106  build
     /root/reference/dgcnn/trainval.py:38-52  softmax / accuracy / loss
 
-PARITY UNPINNED: the reference has no tests, golden vectors or fixtures, and its
-arithmetic lives in TensorFlow 1.x (`tensorflow >= v1.3`, unpinned, README.md:6), which
-is not vendored and cannot be installed here (no network, no py3.12 wheels; the package
-itself is Python-2 only).  The TF-default semantics restated below come from the TF1
-public API contract and are pinned by this repo's own known-answer
-tests (tests/test_oracle_*.py), not by the reference.
+PIN: the reference has no tests, golden vectors or fixtures, and its arithmetic lives in TensorFlow 1.x
+(`tensorflow >= v1.3`, README.md:6), which cannot be installed here (no network, no py3.12 build).  What CAN run here is
+the reference's own source: /root/reference/dgcnn/ops.py and model.py are executed UNMODIFIED on top of oracle/tf1_shim
+(an eager stand-in for the ~25 TF entry points they call) by tests/golden/make_reference_golden.py, and the committed
+tests/golden/ref_*.npz hold what they produce -- k_nn / edges on exact-arithmetic clouds, and three whole models
+(dgcnn, residual-dgcnn with a shortcut conv, residual-dgcnn-nofc) with every EdgeConv tensor, logits, loss and every
+parameter gradient, in fp32 and in fp64.  tests/test_oracle_vs_reference.py holds this module to those vectors: indices
+bit for bit, tensors / logits to 2e-5 / 5e-5, fp64 logits and gradients to 1e-6 relative (i.e. the same formulae), and
+regenerates them from the sources wherever /root/reference exists.  So the reference's composition -- index arithmetic,
+concat orders, scopes and variable names, residual and head wiring -- is pinned by its own code.  NOT pinned by anything
+executable: the semantics of the TF primitives themselves (slim.conv2d / batch_norm defaults, tf.nn.top_k's tie rule,
+tf.nn.dropout's scaling, max_pool_v2), which shim and oracle both restate from the TF 1.x API documentation, and the
+accumulation order inside TF's kernels.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
 may import this module.  The product package (dynamic-gcnn_b200/dgcnn) never does.

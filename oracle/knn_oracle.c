@@ -8,10 +8,14 @@
  *     nn_dist    = squared + squared^T - 2 * inner_prod (ops.py:16)
  *     _, idx     = top_k(-nn_dist, k)                   (ops.py:18)
  *
- * PARITY UNPINNED: the reference ships no tests / golden vectors and its
- * arithmetic lives in TensorFlow 1.x (not vendored, not installable here), so
- * the accumulation order inside tf.matmul is unknowable.  This file FIXES the
- * order and calls it "the answer":
+ * PIN: the reference ships no tests / golden vectors, and TensorFlow 1.x cannot be installed
+ * here -- but the reference's own k_nn() / edges() (ops.py:8-40, unmodified) run in this
+ * container on top of oracle/tf1_shim, and tests/golden/ref_knn_edges.npz holds what they
+ * return on clouds whose distances are exact in fp32 (duplicates and lattice ties included):
+ * this file must reproduce those indices bit for bit (tests/test_oracle_vs_reference.py), and
+ * on the reference's own feature-space inputs it may differ from them only where two
+ * distances tie to rounding.  What stays unpinned is the accumulation order inside TF's
+ * matmul kernel (unknowable without TF); this file FIXES an order and calls it "the answer":
  *   s_i  = sequential-in-c   s = fl(s + fl(x_c * x_c))   (square is its own TF op => rounded
  *          before the sum; no FMA)
  *   p_ij = sequential-in-c   p = fmaf(x_ic, x_jc, p), p0 = +0   (what a one-thread-per-output
