@@ -4,6 +4,7 @@
 #include <atomic>
 
 #include "common.cuh"
+#include "../../include/dgcnn_b200.h"
 
 namespace dgcnn {
 
@@ -40,3 +41,19 @@ int num_sms() {
 extern "C" int dgcnn_abi_version(void) { return 2; }
 extern "C" const char* dgcnn_last_error(void) { return dgcnn::err_buf(); }
 extern "C" uint64_t dgcnn_launch_count(void) { return dgcnn::g_launches.load(); }
+
+extern "C" size_t dgcnn_workspace_bytes(int op, int B, int N, int C, int k, int F) {
+  (void)k;
+  if (B <= 0 || N <= 0) return 0;
+  const long long P = (long long)B * N;
+  if (P >= (1ll << 31)) return 0;
+  switch (op) {
+    case DGCNN_OP_KNN: return dgcnn_knn_workspace_bytes(B, N, C);
+    case DGCNN_OP_EDGECONV: return dgcnn_edgeconv_workspace_bytes(F);
+    case DGCNN_OP_CONV_FWD: return dgcnn_gemm_workspace_bytes((int)P, F, C, 0, 0);
+    case DGCNN_OP_CONV_DW: return dgcnn_gemm_workspace_bytes(C, F, (int)P, 1, 0);
+    case DGCNN_OP_BN: return dgcnn_bn_workspace_bytes(F);
+    case DGCNN_OP_SOFTMAX_XENT: return dgcnn_softmax_xent_workspace_bytes();
+    default: return 0;
+  }
+}

@@ -57,6 +57,7 @@ SIGNATURES = {
     "dgcnn_bn_apply_fwd": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "dgcnn_bn_act_bwd_planes": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "dgcnn_bn_pool_workspace_bytes": (_sz, [_i, _i]),
+    "dgcnn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "dgcnn_bn_apply_fwd_pool": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _i, _vp, _vp, _vp, _vp]),
     "dgcnn_group_max_fwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "dgcnn_group_max_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),

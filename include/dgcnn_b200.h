@@ -41,6 +41,17 @@ const char* dgcnn_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t dgcnn_launch_count(void);
 
+/* One scratch-size query for every op of the path (dgcnn_workspace_bytes(op, B, N, C, k, F)): the bytes
+ * of `ws` the named op needs for clouds [B,N,C], k neighbours and F output channels -- a dispatcher over the per-op
+ * *_workspace_bytes() below (P = B*N rows).  Pure function of its arguments; 0 for an unknown op or an empty shape.  */
+#define DGCNN_OP_KNN 0          /* dgcnn_knn / dgcnn_knn_hinted / dgcnn_knn_mode / dgcnn_pairwise_distance (k unused) */
+#define DGCNN_OP_EDGECONV 1     /* dgcnn_edgeconv_{fwd,bwd}_{stats,apply} with F filters                            */
+#define DGCNN_OP_CONV_FWD 2     /* dgcnn_gemm, [P,C] . [C,F]: uv (F = 2*filters) / conv1 forward                      */
+#define DGCNN_OP_CONV_DW 3      /* dgcnn_gemm, [C,P] . [P,F]: the weight gradient of the same conv (split over points) */
+#define DGCNN_OP_BN 4           /* dgcnn_bn_act_fwd / bwd and friends on [P,F]                                        */
+#define DGCNN_OP_SOFTMAX_XENT 5 /* dgcnn_softmax_xent                                                                 */
+size_t dgcnn_workspace_bytes(int op, int B, int N, int C, int k, int F);
+
 /* ---- k_nn: dgcnn/ops.py:8-19 -------------------------------------------------------------
  * D[b,i,j] = fl(fl(s_i + s_j) - 2*p_ij), s = sum_c fl(x_c^2) (sequential, no FMA),
  * p = sequential-in-c fmaf chain (oracle/knn_oracle.c fixes this order).                   */

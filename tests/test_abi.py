@@ -41,6 +41,15 @@ def test_workspace_queries_are_pure(dg):
     assert lib.dgcnn_gemm_workspace_bytes(49152, 128, 64, 0, 0) == 0          # enough tiles: no split-K
     assert lib.dgcnn_gemm_workspace_bytes(64, 128, 49152, 1, 0) > 0           # weight gradient: split over points
     assert lib.dgcnn_edgeconv_workspace_bytes(64) > 0 and lib.dgcnn_bn_workspace_bytes(64) > 0
+    # the single query of SURVEY.md 8b dispatches to the per-op ones (op, B, N, C, k, F)
+    OP_KNN, OP_EDGECONV, OP_CONV_FWD, OP_CONV_DW, OP_BN, OP_XENT = range(6)
+    assert lib.dgcnn_workspace_bytes(OP_KNN, 24, 2048, 64, 20, 64) == got
+    assert lib.dgcnn_workspace_bytes(OP_EDGECONV, 24, 2048, 64, 20, 64) == lib.dgcnn_edgeconv_workspace_bytes(64)
+    assert lib.dgcnn_workspace_bytes(OP_CONV_FWD, 24, 2048, 64, 20, 128) == lib.dgcnn_gemm_workspace_bytes(49152, 128, 64, 0, 0)
+    assert lib.dgcnn_workspace_bytes(OP_CONV_DW, 24, 2048, 64, 20, 128) == lib.dgcnn_gemm_workspace_bytes(64, 128, 49152, 1, 0)
+    assert lib.dgcnn_workspace_bytes(OP_BN, 24, 2048, 64, 20, 512) == lib.dgcnn_bn_workspace_bytes(512)
+    assert lib.dgcnn_workspace_bytes(OP_XENT, 24, 2048, 64, 20, 2) == lib.dgcnn_softmax_xent_workspace_bytes()
+    assert lib.dgcnn_workspace_bytes(99, 24, 2048, 64, 20, 64) == 0 and lib.dgcnn_workspace_bytes(OP_KNN, 0, 8, 3, 2, 4) == 0
 
 
 def test_invalid_arguments_return_codes_not_aborts(dg):
