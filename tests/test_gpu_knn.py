@@ -131,8 +131,9 @@ def test_knn_hint_never_changes_the_result(dg, oracle, cuda):
 @pytest.mark.parametrize("B,N,C,k", [(2, 700, 64, 20), (3, 2048, 64, 20), (2, 384, 64, 40), (1, 130, 8, 5),
                                       (2, 1000, 32, 24), (2, 256, 64, 56), (1, 128, 16, 1)])
 def test_knn_tensor_core_path_bit_exact(dg, oracle, cuda, B, N, C, k):
-    """The tcgen05 filter + exact refinement (taken when a hint is given, C % 8 == 0, C <= 64) must reproduce the
-    oracle bit for bit for every kind of hint, including useless ones."""
+    """The tcgen05 filter + exact refinement (taken for clouds of >= 256 points with C <= 64 and k <= 48; smaller clouds
+    and larger k take the SIMT kernel, the only path that uses a hint) must reproduce the oracle bit for bit whatever
+    hint the caller passes, including useless ones."""
     rng = np.random.RandomState(N + C + k)
     x = torch.from_numpy((rng.randn(B, N, C) * rng.uniform(0.2, 3.0, size=(1, 1, C))).astype(np.float32)).cuda()
     ref = oracle.k_nn(x.cpu(), k).cuda()
