@@ -1,6 +1,7 @@
 """dgcnn.h5lite: the built-in HDF5 reader / writer behind `-io h5` (/root/reference/dgcnn/iotool.py:199-280 uses h5py for the
 input and PyTables EArrays for the output; neither exists in this image).  Round trips, the on-disk structures the
 specification fixes (so that other HDF5 libraries read the files), and the io_h5 handler on .h5 files."""
+import os
 import struct
 import zlib
 from types import SimpleNamespace
@@ -160,3 +161,53 @@ def test_io_h5_reads_and_writes_hdf5_files(dg, tmp_path):
         assert np.array_equal(f["softmax"], sm[[3, 0, 4]]) and np.array_equal(f["data"], src["data"][[3, 0, 4]])
         assert f["label"].dtype == np.float32 and np.array_equal(f["label"], src["label"][[3, 0, 4]].astype(np.float32))
         assert f.attrs("softmax")["CLASS"] == "EARRAY" and f["index"].tolist() == [3, 0, 4]
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/dgcnn/iotool.py"), reason="the reference sources exist only in the build container")
+def test_reference_io_h5_runs_unmodified_on_h5lite(dg, tmp_path):
+    """The reference's own IO handler (/root/reference/dgcnn/iotool.py:199-280, loaded by path, unmodified) reads an HDF5
+    file written by dgcnn.h5lite and writes its PyTables output through oracle/h5_shims (h5py.File / tables.open_file served
+    by h5lite): same batches, same stored arrays as this repo's io_h5.  Label-free data: with a label array the reference's
+    `if self._label:` (iotool.py:234,241,274) raises on any numpy array of more than one element."""
+    import importlib.util
+    import sys
+    from dgcnn import h5lite
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rng = np.random.RandomState(9)
+    data = rng.rand(5, 16, 3).astype(np.float32)
+    src = str(tmp_path / "in.h5")
+    h5lite.write(src, {"data": data}, compress=5)
+
+    def flags(out):
+        return SimpleNamespace(BATCH_SIZE=2, NUM_POINT=16, NUM_CHANNEL=-1, NUM_CLASS=3, LABEL_KEY="", WEIGHT_KEY="",
+                               OUTPUT_FILE=out, SHUFFLE=0, IO_TYPE="h5", INPUT_FILE=[src], DATA_KEY="data")
+
+    shims = os.path.join(root, "oracle", "h5_shims")
+    sys.path.insert(0, shims)
+    try:
+        spec = importlib.util.spec_from_file_location("_reference_iotool", "/root/reference/dgcnn/iotool.py")
+        ref_io = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref_io)
+        ref = ref_io.io_factory(flags(str(tmp_path / "ref_out.h5")))
+        ref.initialize()
+        mine = dg.io_factory(flags(str(tmp_path / "my_out.h5")))
+        mine.initialize()
+        assert ref.num_entries() == mine.num_entries() == 5 and ref.num_channels() == mine.num_channels() == 3
+        sm = rng.rand(5, 16, 3).astype(np.float32)          # NUM_CLASS == channels: the reference's softmax EArray has the
+        for _ in range(4):                                   # data's row shape (iotool.py:237-240)
+            a, b = ref.next(), mine.next()                   # sequential mode wraps around the 5 entries
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] is None and b[2] is None
+            for i in a[0]:
+                ref.store(i, sm[i])
+                mine.store(i, sm[i])
+        ref.finalize()
+        mine.finalize()
+    finally:
+        sys.path.remove(shims)
+        for m in ("h5py", "tables", "_h5lite"):
+            sys.modules.pop(m, None)
+    with h5lite.File(str(tmp_path / "ref_out.h5")) as fr, h5lite.File(str(tmp_path / "my_out.h5")) as fm:
+        assert fr.keys() == ["data", "softmax"] and set(fm.keys()) == {"data", "softmax", "index"}
+        assert fm["index"].tolist() == [0, 1, 2, 3, 4, 0, 1, 2]
+        for k in ("data", "softmax"):
+            assert np.array_equal(fr[k], fm[k]) and fr.attrs(k) == fm.attrs(k)
