@@ -14,7 +14,8 @@ the reference's own source: /root/reference/dgcnn/ops.py and model.py are execut
 (an eager stand-in for the ~25 TF entry points they call) by tests/golden/make_reference_golden.py, and the committed
 tests/golden/ref_*.npz hold what they produce -- k_nn / edges on exact-arithmetic clouds, and three whole models
 (dgcnn, residual-dgcnn with a shortcut conv, residual-dgcnn-nofc) with every EdgeConv tensor, logits, loss and every
-parameter gradient, in fp32 and in fp64.  tests/test_oracle_vs_reference.py holds this module to those vectors: indices
+parameter gradient, in fp32 and in fp64, and (trainval.py, through the shim's graph mode) a two-tower trainer over two
+optimizer steps of two micro-steps: losses, accumulated gradients, variables after apply_gradient, inference().  tests/test_oracle_vs_reference.py holds this module to those vectors: indices
 bit for bit, tensors / logits to 2e-5 / 5e-5, fp64 logits and gradients to 1e-6 relative (i.e. the same formulae), and
 regenerates them from the sources wherever /root/reference exists.  So the reference's composition -- index arithmetic,
 concat orders, scopes and variable names, residual and head wiring -- is pinned by its own code.  NOT pinned by anything

@@ -30,13 +30,18 @@ _DEFAULT = object()
 def conv2d(inputs, num_outputs, kernel_size, stride=1, padding="SAME", activation_fn=_DEFAULT, normalizer_fn=None,
            trainable=True, scope=None):
     assert int(kernel_size) == 1 and int(stride) == 1 and padding == "VALID" and normalizer_fn is batch_norm and scope
-    name = tf._scope_name(scope)
-    cin = int(inputs.shape[-1])
-    w = tf._get_variable(name + "/weights", (1, 1, cin, int(num_outputs)), "xavier", inputs.dtype)
-    out = torch.matmul(inputs, w[0, 0])
-    out = batch_norm(out, name)
     if activation_fn is _DEFAULT:
         activation_fn = tf.nn.relu
+    # the variable scope is a property of the CALL SITE (graph construction), not of the moment the op executes
+    return _conv2d(inputs, int(num_outputs), activation_fn, tf._scope_name(scope))
+
+
+@tf.dual
+def _conv2d(inputs, num_outputs, activation_fn, name):
+    cin = int(inputs.shape[-1])
+    w = tf._get_variable(name + "/weights", (1, 1, cin, num_outputs), "xavier", inputs.dtype)
+    out = torch.matmul(inputs, w[0, 0])
+    out = batch_norm(out, name)
     if activation_fn is not None:
         out = activation_fn(out)
     tf.TRACE["conv2d"][name] = out

@@ -1,5 +1,5 @@
-"""Golden vectors produced by the REFERENCE'S OWN SOURCE: /root/reference/dgcnn/ops.py and model.py, unmodified, are
-loaded by path and executed eagerly on top of oracle/tf1_shim (a stand-in for the few TensorFlow 1.x entry points they
+"""Golden vectors produced by the REFERENCE'S OWN SOURCE: /root/reference/dgcnn/ops.py, model.py and trainval.py,
+unmodified, are loaded by path and executed on top of oracle/tf1_shim (a stand-in for the few TensorFlow 1.x entry points they
 call; TF1 itself cannot be installed here).  The reference's index arithmetic (ops.py:21-40), scopes, concat orders,
 residual wiring (ops.py:100-140) and head (model.py:60-104) therefore come from the reference, not from this repo's
 restatement; only the TF primitives are restated (oracle/tf1_shim/tensorflow/__init__.py, contrib/slim.py).
@@ -46,7 +46,7 @@ def load_reference():
     pkg.__path__ = []
     sys.modules["dgcnn"] = pkg
     mods = {}
-    for name in ("ops", "model"):
+    for name in ("ops", "model", "trainval"):
         spec = importlib.util.spec_from_file_location("dgcnn." + name, os.path.join(REFERENCE, "dgcnn", name + ".py"))
         mod = importlib.util.module_from_spec(spec)
         sys.modules["dgcnn." + name] = mod
@@ -209,7 +209,62 @@ def case_ref_knn_edges():
     return out
 
 
-CASES = {"ref_dgcnn": case_ref_dgcnn, "ref_residual": case_ref_residual, "ref_residual_nofc": case_ref_residual_nofc,
+TRAINER_SEED = 6
+
+
+def trainer_flags():
+    return _flags(EDGE_CONV_LAYERS=1, KVALUE=6, FC_FILTERS=[32, 16], GPUS=[0, 1], MINIBATCH_SIZE=2, NUM_CHANNEL=3,
+                  LEARNING_RATE=0.001, WEIGHT_KEY="", TRAIN=True)
+
+
+def case_ref_trainer():
+    """/root/reference/dgcnn/trainval.py executed unmodified (graph mode of the shim: placeholders, towers, compute_gradients,
+    tower mean, accumulation variables, apply_gradients, Session.run): two optimizer steps, each of two micro-steps on two
+    towers (flags.GPUS = [0, 1], MINIBATCH_SIZE = 2), i.e. trainval.py:59-80's mean over towers, sum over micro-steps and
+    Adam update as the reference's code composes them.  Stored: what accum_gradient returns per micro-step, the accumulated
+    gradients before each apply, the variables after each apply, and inference() on the final variables."""
+    tf, ref_ops, ref_model = load_reference()
+    ref_trainval = sys.modules["dgcnn.trainval"]
+    seed = TRAINER_SEED
+    flags = trainer_flags()
+    tf.reset(seed)
+    P = _params(flags, 3, seed)
+    for n, v in P.items():
+        tf.PRESET["dgcnn/" + n] = v
+    rng = np.random.RandomState(41)
+    STEPS, MICRO, T, B, N = 2, 2, 2, 2, 48
+    x = rng.random_sample((STEPS, MICRO, T, B, N, 3)).astype(np.float32)
+    y = rng.randint(0, 2, (STEPS, MICRO, T, B, N)).astype(np.int32)
+    masks = (rng.random_sample((STEPS, MICRO, T, B, N, 1, 16)) < 0.7).astype(np.float32)
+    trainer = ref_trainval.trainval(flags)
+    trainer.initialize()                                                   # builds the two-tower graph (trainval.py:12-85)
+    sess = tf.Session()
+    out = {"x": x, "labels": y, "dropout_masks": masks, "lr": np.float32(flags.LEARNING_RATE)}
+    names = [v.name[:-2][len("dgcnn/"):] for v in tf.trainable_variables()]
+    assert sorted(names) == sorted(P)
+    for s in range(STEPS):
+        trainer.zero_gradients(sess)                                       # main_funcs.py:135
+        for m in range(MICRO):
+            tf.DROPOUT_MASK = [torch.from_numpy(masks[s, m, t]) for t in range(T)]
+            res = trainer.accum_gradient(sess, [x[s, m, t] for t in range(T)], [y[s, m, t] for t in range(T)])   # :155
+            out["acc:%d:%d" % (s, m)] = np.float32(res[1])
+            out["loss:%d:%d" % (s, m)] = np.float32(res[2])
+            out["knn:%d:%d" % (s, m)] = np.stack([t.numpy() for t in tf.TRACE["top_k"]])     # [towers * layers, B, N, k]
+        accum = sess.run([v for v in trainer._apply_grad.args])              # the accumulation variables (reads only)
+        for n, g in zip(names, accum):
+            out["accum:%d:%s" % (s, n)] = g.reshape(P[n].shape).astype(np.float32)
+        trainer.apply_gradient(sess)                                       # main_funcs.py:166
+        for n, v in zip(names, tf.trainable_variables()):
+            out["var:%d:%s" % (s, n)] = v.tensor.detach().numpy().reshape(P[n].shape).astype(np.float32)
+    # (initial values: _params(trainer_flags(), 3, TRAINER_SEED), not stored)
+    tf.DROPOUT_MASK = [torch.from_numpy(masks[0, 0, t]) for t in range(T)]
+    res = trainer.inference(sess, [x[0, 0, t] for t in range(T)], [y[0, 0, t] for t in range(T)])   # trainval.py:103-108
+    out["inference:softmax"] = np.stack(res[:T]).astype(np.float32)       # one per tower, then accuracy, loss
+    out["inference:acc"], out["inference:loss"] = np.float32(res[T]), np.float32(res[T + 1])
+    return out
+
+
+CASES = {"ref_dgcnn": case_ref_dgcnn, "ref_trainer": case_ref_trainer, "ref_residual": case_ref_residual, "ref_residual_nofc": case_ref_residual_nofc,
          "ref_knn_edges": case_ref_knn_edges}
 
 if __name__ == "__main__":

@@ -135,3 +135,64 @@ def test_shim_is_test_infrastructure_only():
                 assert "tf1_shim" not in src and "import tensorflow" not in src and "h5_shims" not in src, os.path.join(dirpath, f)
     bench = open(os.path.join(ROOT, "bench.py")).read()
     assert "tf1_shim" not in bench and "h5_shims" not in bench
+
+
+def test_oracle_reproduces_the_reference_trainer(oracle):
+    """/root/reference/dgcnn/trainval.py run unmodified (tests/golden/ref_trainer.npz: two optimizer steps x two micro-steps x
+    two towers): loss / accuracy as accum_gradient returns them (tower mean, trainval.py:59-60), the accumulated gradient
+    (mean over towers :64-69, SUM over micro-steps :79), the variables after apply_gradient (:80, TF-form Adam) and
+    inference() (:103-108) against the oracle's restatement of the same composition."""
+    from tests.golden import make_reference_golden as mg
+    z = np.load(os.path.join(GOLD, "ref_trainer.npz"))
+    fl_ref = mg.trainer_flags()
+    fl = oracle.make_flags(EDGE_CONV_LAYERS=fl_ref.EDGE_CONV_LAYERS, KVALUE=fl_ref.KVALUE, FC_FILTERS=fl_ref.FC_FILTERS,
+                           GPUS=fl_ref.GPUS, MINIBATCH_SIZE=fl_ref.MINIBATCH_SIZE, NUM_CHANNEL=3, TRAIN=True,
+                           LEARNING_RATE=fl_ref.LEARNING_RATE)
+    P = {n: torch.from_numpy(v.copy()) for n, v in mg._params(fl_ref, 3, mg.TRAINER_SEED).items()}
+    m = {n: torch.zeros_like(t) for n, t in P.items()}
+    v = {n: torch.zeros_like(t) for n, t in P.items()}
+    x, y, masks = z["x"], z["labels"], z["dropout_masks"]
+    STEPS, MICRO, T = x.shape[:3]
+    L = int(fl.EDGE_CONV_LAYERS)
+    G = float(len(fl.GPUS))
+
+    def tower(Pd, s, mi, t, knn):
+        idx = [torch.from_numpy(knn[t * L + i]) for i in range(L)]
+        logits = oracle.build(torch.from_numpy(x[s, mi, t]), fl, Pd, idx_list=idx, dropout_mask=torch.from_numpy(masks[s, mi, t]))
+        return (logits,) + tuple(oracle.softmax_loss_accuracy(logits, torch.from_numpy(y[s, mi, t]).long()))
+
+    for s in range(STEPS):
+        accum = {n: torch.zeros_like(t) for n, t in P.items()}                 # zero_gradients
+        for mi in range(MICRO):
+            Pd = {n: t.detach().clone().requires_grad_(True) for n, t in P.items()}
+            losses, accs = [], []
+            for t in range(T):
+                _, _, acc, loss = tower(Pd, s, mi, t, z["knn:%d:%d" % (s, mi)])
+                (loss / G).backward()                                       # mean over towers
+                losses.append(float(loss.detach()))
+                accs.append(float(acc))
+            assert abs(np.mean(losses) - float(z["loss:%d:%d" % (s, mi)])) <= 2e-6
+            assert abs(np.mean(accs) - float(z["acc:%d:%d" % (s, mi)])) <= 1e-6
+            for n in P:
+                accum[n] += Pd[n].grad                                      # sum over micro-steps
+        for n in P:
+            ref = torch.from_numpy(z["accum:%d:%s" % (s, n)])
+            den = max(float(ref.norm()), 1e-12)
+            assert float((accum[n] - ref).norm()) <= 2e-2 * den, (s, n, float((accum[n] - ref).norm()) / den)
+        # the optimizer step on the REFERENCE'S accumulated gradient: pins the update rule without the gradient noise
+        for n in P:
+            oracle.adam_tf_step(P[n], torch.from_numpy(z["accum:%d:%s" % (s, n)]), m[n], v[n], s + 1, lr=float(z["lr"]))
+            ref = torch.from_numpy(z["var:%d:%s" % (s, n)])
+            assert float((P[n] - ref).abs().max()) <= 2e-7, (s, n, float((P[n] - ref).abs().max()))
+    # inference on the final variables (train-mode graph: dropout and batch statistics active, like the reference)
+    sm, accs, losses = [], [], []
+    idx0 = [[oracle.k_nn(torch.from_numpy(x[0, 0, t]), fl.KVALUE)] for t in range(T)]     # L = 1: the raw cloud's graph
+    for t in range(T):
+        with torch.no_grad():
+            logits = oracle.build(torch.from_numpy(x[0, 0, t]), fl, P, idx_list=idx0[t], dropout_mask=torch.from_numpy(masks[0, 0, t]))
+            softmax, acc, loss = oracle.softmax_loss_accuracy(logits, torch.from_numpy(y[0, 0, t]).long())
+        sm.append(softmax.numpy())
+        accs.append(float(acc))
+        losses.append(float(loss))
+    assert np.allclose(np.stack(sm), z["inference:softmax"], atol=2e-5)
+    assert abs(np.mean(accs) - float(z["inference:acc"])) <= 1e-6 and abs(np.mean(losses) - float(z["inference:loss"])) <= 2e-6
