@@ -3,7 +3,9 @@
 
 --config 1 (default; BASELINE.json configs[1], the configuration the metric is quoted on): 4 EdgeConv layers + FC head,
             N=2048, k=20, C=3, 24 clouds per GPU, fp32.  With --gpus N (under torchrun) every rank keeps 24 clouds (weak
-            scaling: at N=8 this is configs[3], global batch 192) and the step ends with ONE NCCL all-reduce.
+            scaling: at N=8 this is configs[3], global batch 192); the flat gradient buffer is all-reduced (NCCL, the only
+            collective) inside the captured micro-step as two buckets, the head's overlapped with the EdgeConv backward
+            (DGCNN_OVERLAP_AR=0: ONE all-reduce after backward).
 --config 2 (configs[2]): residual-dgcnn, 6 layers, N=4096, k=40, 24 clouds, bf16 (operating point of the reference's
             scripts/lsf/train_dgcnn.sh:4,8,9,28); --dtype f32 runs the same shape on the fp32 path.
 --config 4 (configs[4]): N=16384, k=20, 8 clouds per GPU, 4 layers, fp32 (per-cloud distance matrix 1.07 GB >> L2);
@@ -366,6 +368,10 @@ def run_ours(args, cfg):
         conf = workload_config(world, cfg, dtype)
         conf["l2"] = "no explicit flush: one step streams >2 GB of activations per GPU, far beyond the 126 MB L2"
         conf["launch"] = "micro-step (fwd+bwd) replayed from a CUDA graph captured by dgcnn.trainval after 2 eager runs"
+        if world > 1:
+            conf["collective"] = ("gradient all-reduce inside the captured micro-step: two NCCL buckets, the head's overlapped "
+                                  "with the EdgeConv backward" if getattr(tr, "_buckets", None) is not None else
+                                  "one NCCL all-reduce of the flat gradient buffer after backward")
         line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": conf,
