@@ -16,6 +16,10 @@ B-tree; v4 single-chunk / implicit index) layouts; deflate, shuffle and fletcher
 fixed / extensible-array chunk indexes, compound or variable-length types, external links) raises NotImplementedError
 naming the feature.  Nested groups are reached with "a/b/c" paths.
 
+Verification: byte-level known answers taken from the specification, round trips, and the reference's own io_h5 running
+on these files through oracle/h5_shims (tests/test_h5lite.py).  libhdf5 / h5py / PyTables are absent from this image, so
+interoperability with them is by construction from the specification, not by test.
+
 Host-side IO, out of the hot path.
 """
 from __future__ import annotations
