@@ -17,7 +17,7 @@ fixed / extensible-array chunk indexes, compound or variable-length types, exter
 naming the feature.  Nested groups are reached with "a/b/c" paths.
 
 Verification: byte-level known answers taken from the specification, round trips, and the reference's own io_h5 running
-on these files through oracle/h5_shims (tests/test_h5lite.py).  libhdf5 / h5py / PyTables are absent from this image, so
+on these files through h5py / PyTables stand-ins kept with the test infrastructure (tests/test_h5lite.py).  libhdf5 / h5py / PyTables are absent from this image, so
 interoperability with them is by construction from the specification, not by test.
 
 Host-side IO, out of the hot path.
