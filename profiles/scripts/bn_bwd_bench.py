@@ -1,6 +1,8 @@
 """BN-backward (statistics pass + apply pass) timed alone at the head's shapes of configs[1] (P = 49152 rows), L2 flushed
-by rotating buffer sets.  With a library built with `make EXTRA=-DBN_TUNE` the statistics kernel's grid (blocks per SM) and
-rows in flight per thread can be swept:  python profiles/scripts/bn_bwd_bench.py [sweep]"""
+by rotating buffer sets:  python profiles/scripts/bn_bwd_bench.py
+`sweep` (profiles/r02_bn_bwd_sweep.txt) additionally needed an experiment build whose debug hook `dgcnn_debug_bn_tune(blocks
+per SM, rows in flight)` set the statistics kernel's grid; the hook was removed once the configuration was chosen, so with
+the shipped library `sweep` only repeats the default line."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "dynamic-gcnn_b200"))
@@ -56,7 +58,7 @@ def bench(C, pool, gbias, reps=12):
 
 
 shapes = [(1024, True, False), (512, False, True), (256, False, False), (64, False, False)]
-configs = [(0, 2)] + ([(b, u) for u in (2, 4) for b in (2, 3, 4, 6)] if tune else [])
+configs = [(0, 2)] + ([(b, u) for u in (2, 4) for b in (2, 3, 4, 6)] if tune else [])   # (0, 2) = the library's own choice
 base = {}
 for bps, u in configs:
     if tune:
