@@ -264,7 +264,61 @@ def case_ref_trainer():
     return out
 
 
-CASES = {"ref_dgcnn": case_ref_dgcnn, "ref_trainer": case_ref_trainer, "ref_residual": case_ref_residual, "ref_residual_nofc": case_ref_residual_nofc,
+def case_ref_small():
+    """Two light cases (no big tensors stored).
+    weighted: trainval.py:46-52 with WEIGHT_KEY set -- loss = mean(xent * weight) -- one tower, one micro-step, through the
+              reference's accum_gradient; stored: loss, accuracy, accumulated gradients of the EdgeConv / Final variables.
+    lattice:  model.build (inference graph, TRAIN=False) on a voxel lattice with duplicated points: distance ties inside a
+              whole model, resolved by tf.nn.top_k's rule in layer 0 (exact arithmetic) -- stored: indices, logits."""
+    tf, ref_ops, ref_model = load_reference()
+    ref_trainval = sys.modules["dgcnn.trainval"]
+    out = {}
+    # ---- weighted loss through the trainer
+    flags = _flags(EDGE_CONV_LAYERS=1, KVALUE=5, FC_FILTERS=[16, 8], GPUS=[0], MINIBATCH_SIZE=2, NUM_CHANNEL=3,
+                   LEARNING_RATE=0.001, WEIGHT_KEY="weight", TRAIN=True, NUM_CLASS=3)
+    tf.reset(7)
+    P = _params(flags, 3, 7)
+    for n, v in P.items():
+        tf.PRESET["dgcnn/" + n] = v
+    rng = np.random.RandomState(51)
+    x = rng.random_sample((2, 40, 3)).astype(np.float32)
+    y = rng.randint(0, 3, (2, 40)).astype(np.int32)
+    w = (rng.random_sample((2, 40)) * 2.0).astype(np.float32)
+    mask = (rng.random_sample((2, 40, 1, 8)) < 0.7).astype(np.float32)
+    trainer = ref_trainval.trainval(flags)
+    trainer.initialize()
+    sess = tf.Session()
+    trainer.zero_gradients(sess)
+    tf.DROPOUT_MASK = [torch.from_numpy(mask)]
+    res = trainer.accum_gradient(sess, [x], [y], [w])
+    knn = np.stack([t.numpy() for t in tf.TRACE["top_k"]])                  # (the next run resets the trace)
+    names = [v.name[:-2][len("dgcnn/"):] for v in tf.trainable_variables()]
+    accum = sess.run([v for v in trainer._apply_grad.args])
+    out.update({"weighted:x": x, "weighted:labels": y, "weighted:weight": w, "weighted:mask": mask,
+                "weighted:acc": np.float32(res[1]), "weighted:loss": np.float32(res[2]), "weighted:knn": knn})
+    for n, g_ in zip(names, accum):
+        if n.startswith(("EdgeConv", "Final")) or n.endswith("beta"):
+            out["weighted:accum:" + n] = g_.reshape(P[n].shape).astype(np.float32)
+    # ---- lattice model, inference graph
+    flags = _flags(EDGE_CONV_LAYERS=2, KVALUE=9, FC_FILTERS=[16, 8], TRAIN=False)
+    tf.reset(8)
+    P = _params(flags, 3, 8)
+    for n, v in P.items():
+        tf.PRESET["dgcnn/" + n] = v
+    rng = np.random.RandomState(52)
+    xl = rng.randint(0, 5, (2, 90, 3)).astype(np.float32)
+    xl[:, 60:] = xl[:, :30]                                                  # 30 duplicated points per cloud
+    with tf.variable_scope("dgcnn", reuse=tf.AUTO_REUSE):
+        pred = ref_model.build(torch.from_numpy(xl), flags)
+    out.update({"lattice:x": xl, "lattice:logits": pred.detach().numpy().astype(np.float32)})
+    for i, ix in enumerate(tf.TRACE["top_k"]):
+        out["lattice:idx%d" % i] = ix.numpy()
+    return out
+
+
+SMALL_SEEDS = {"weighted": 7, "lattice": 8}
+
+CASES = {"ref_dgcnn": case_ref_dgcnn, "ref_trainer": case_ref_trainer, "ref_small": case_ref_small, "ref_residual": case_ref_residual, "ref_residual_nofc": case_ref_residual_nofc,
          "ref_knn_edges": case_ref_knn_edges}
 
 if __name__ == "__main__":

@@ -196,3 +196,41 @@ def test_oracle_reproduces_the_reference_trainer(oracle):
         losses.append(float(loss))
     assert np.allclose(np.stack(sm), z["inference:softmax"], atol=2e-5)
     assert abs(np.mean(accs) - float(z["inference:acc"])) <= 1e-6 and abs(np.mean(losses) - float(z["inference:loss"])) <= 2e-6
+
+
+def test_oracle_reproduces_weighted_loss_and_lattice_model(oracle):
+    """tests/golden/ref_small.npz (reference code): (1) trainval.py:46-52 with WEIGHT_KEY -- loss = mean(xent * weight) --
+    through the reference's accum_gradient; (2) model.build on a voxel lattice with duplicated points: layer-0 ties resolved
+    by tf.nn.top_k's rule are reproduced bit for bit by the C oracle, and with the reference's graphs the logits agree."""
+    from tests.golden import make_reference_golden as mg
+    z = np.load(os.path.join(GOLD, "ref_small.npz"))
+    # (1)
+    fl = oracle.make_flags(EDGE_CONV_LAYERS=1, KVALUE=5, FC_FILTERS=[16, 8], NUM_CLASS=3, TRAIN=True, NUM_CHANNEL=3,
+                           WEIGHT_KEY="weight")
+    ref_fl = mg._flags(EDGE_CONV_LAYERS=1, KVALUE=5, FC_FILTERS=[16, 8], NUM_CLASS=3)
+    P = {n: torch.from_numpy(v.copy()).requires_grad_(True) for n, v in mg._params(ref_fl, 3, mg.SMALL_SEEDS["weighted"]).items()}
+    x = torch.from_numpy(z["weighted:x"])
+    assert np.array_equal(oracle.k_nn(x, 5).numpy(), z["weighted:knn"][0])
+    logits = oracle.build(x, fl, P, idx_list=[torch.from_numpy(z["weighted:knn"][0])], dropout_mask=torch.from_numpy(z["weighted:mask"]))
+    _, acc, loss = oracle.softmax_loss_accuracy(logits, torch.from_numpy(z["weighted:labels"]).long(),
+                                                weight=torch.from_numpy(z["weighted:weight"]))
+    assert abs(float(loss.detach()) - float(z["weighted:loss"])) <= 2e-6 and abs(float(acc) - float(z["weighted:acc"])) <= 1e-7
+    loss.backward()
+    checked = 0
+    for key in z.files:
+        if key.startswith("weighted:accum:"):
+            n = key[len("weighted:accum:"):]
+            ref = torch.from_numpy(z[key])
+            den = max(float(ref.norm()), 1e-12)
+            assert float((P[n].grad - ref).norm()) <= 2e-2 * den, (n, float((P[n].grad - ref).norm()) / den)
+            checked += 1
+    assert checked >= 8
+    # (2)
+    fl = oracle.make_flags(EDGE_CONV_LAYERS=2, KVALUE=9, FC_FILTERS=[16, 8], TRAIN=False, NUM_CHANNEL=3)
+    ref_fl = mg._flags(EDGE_CONV_LAYERS=2, KVALUE=9, FC_FILTERS=[16, 8], TRAIN=False)
+    P = {n: torch.from_numpy(v.copy()) for n, v in mg._params(ref_fl, 3, mg.SMALL_SEEDS["lattice"]).items()}
+    xl = torch.from_numpy(z["lattice:x"])
+    assert np.array_equal(oracle.k_nn(xl, 9).numpy(), z["lattice:idx0"])          # duplicates + lattice ties, exact arithmetic
+    with torch.no_grad():
+        logits = oracle.build(xl, fl, P, idx_list=[torch.from_numpy(z["lattice:idx%d" % i]) for i in range(2)])
+    assert torch.allclose(logits, torch.from_numpy(z["lattice:logits"]), atol=5e-5, rtol=1e-5)
